@@ -1,0 +1,672 @@
+"""CPU fp32 restatement of REFace's DDIM face-swap inference path (TEST INFRASTRUCTURE ONLY).
+
+This file is the *oracle*: a plain-PyTorch, CPU, fp32, functional restatement of the reference
+algorithm.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may
+import it; the product (``reface_b200``) never does.  Every function cites the reference file:line
+(relative to /root/reference) it restates.  Parameters live in a flat ``dict[str, Tensor]`` that
+uses the reference's own ``state_dict`` key names, so the very same dict can be loaded into the
+reference ``nn.Module`` (done in ``tests/golden/make_golden.py``, which pins this oracle against
+the real reference modules) and into the CUDA engine's weight packer.
+
+Parity status: pinned against the reference's own modules (UNetModel, AutoencoderKL, Backbone,
+FrozenCLIPEmbedder incl. HF CLIPVisionModel, DDIMSampler) run in the build container; the golden
+outputs live in tests/golden/*.npz.  The reference ships no tests/golden vectors of its own
+(SURVEY.md section 4); the closed-form constants it implies are checked in tests/test_oracle.py.
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------
+# configuration (models/REFace/configs/project_ffhq.yaml:1-99)
+# --------------------------------------------------------------------------------------------
+UNET_CFG = dict(in_channels=9, out_channels=4, model_channels=320, attention_resolutions=(4, 2, 1),
+                num_res_blocks=2, channel_mult=(1, 2, 4, 4), num_heads=8, context_dim=768)
+VAE_CFG = dict(ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, z_channels=4, in_channels=3, out_ch=3,
+               embed_dim=4)
+CLIP_CFG = dict(width=1024, layers=24, heads=16, patch=14, image=224, mlp=4096, proj=768,
+                mapper_layers=5)
+SCALE_FACTOR = 0.18215
+LINEAR_START, LINEAR_END, TIMESTEPS = 0.00085, 0.012, 1000
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+CLIP_WEIGHT, ID_WEIGHT, LANDMARK_WEIGHT = 1.0, 10.0, 0.05
+
+PFX_UNET = "model.diffusion_model."
+PFX_VAE = "first_stage_model."
+PFX_CLIP = "cond_stage_model."
+PFX_ARC = "face_ID_model.facenet."
+
+
+# --------------------------------------------------------------------------------------------
+# parameter access: one code path both *declares* the parameter spec (meta tensors) and *uses* a
+# real state dict, so the spec can never drift from the forward pass.
+# --------------------------------------------------------------------------------------------
+class Params:
+    """sd=None -> spec mode: records (shape, kind) and returns meta tensors."""
+
+    def __init__(self, sd=None, prefix=""):
+        self.sd, self.prefix = sd, prefix
+        self.spec = OrderedDict()
+
+    def __call__(self, name, shape, kind):
+        full = self.prefix + name
+        shape = tuple(int(s) for s in shape)
+        if self.sd is None:
+            if full in self.spec:
+                assert self.spec[full][0] == shape
+            self.spec[full] = (shape, kind)
+            return torch.empty(shape, device="meta")
+        t = self.sd[full]
+        assert tuple(t.shape) == shape, (full, tuple(t.shape), shape)
+        return t
+
+    def sub(self, prefix):
+        p = Params(self.sd, self.prefix + prefix)
+        p.spec = self.spec
+        return p
+
+
+def _seed_for(name: str, seed: int) -> int:
+    return int.from_bytes(hashlib.sha256(f"{seed}:{name}".encode()).digest()[:7], "little")
+
+
+def init_tensor(name, shape, kind, seed=0):
+    """Deterministic per-tensor init (independent of generation order).  'w': N(0, 1/fan_in);
+    zero_module'd tensors of the reference get the same treatment."""
+    g = torch.Generator().manual_seed(_seed_for(name, seed))
+    n = lambda *s: torch.randn(*s, generator=g, dtype=torch.float32)
+    if kind == "w":
+        fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
+        return n(*shape) / math.sqrt(fan_in)
+    if kind == "b":
+        return 0.02 * n(*shape)
+    if kind == "g":
+        return 1.0 + 0.1 * n(*shape)
+    if kind == "emb":
+        return 0.02 * n(*shape)
+    if kind == "unit":
+        return n(*shape)
+    if kind == "bn_mean":
+        return 0.1 * n(*shape)
+    if kind == "bn_var":
+        return 0.5 + torch.rand(*shape, generator=g, dtype=torch.float32)
+    if kind == "prelu":
+        return 0.25 + 0.05 * n(*shape)
+    if kind == "count":
+        return torch.zeros(shape, dtype=torch.long)
+    raise ValueError(kind)
+
+
+def init_state_dict(spec, seed=0):
+    return OrderedDict((k, init_tensor(k, s, kind, seed)) for k, (s, kind) in spec.items())
+
+
+# --------------------------------------------------------------------------------------------
+# schedule (ldm/modules/diffusionmodules/util.py:21-74, ldm/models/diffusion/ddpm.py:255-275,
+# ldm/models/diffusion/ddim.py:110-139)
+# --------------------------------------------------------------------------------------------
+def make_beta_schedule(n=TIMESTEPS, linear_start=LINEAR_START, linear_end=LINEAR_END):
+    # util.py:23-25  (fp64)
+    return (torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n, dtype=torch.float64) ** 2).numpy()
+
+
+def alphas_cumprod_f32():
+    # ddpm.py:262-275: cumprod in fp64, cast to fp32
+    betas = make_beta_schedule()
+    return torch.tensor(np.cumprod(1.0 - betas, axis=0), dtype=torch.float32)
+
+
+def make_ddim_timesteps(S, T=TIMESTEPS):
+    # util.py:46-60 ('uniform'); NB: S=30 yields 31 steps (assert commented out at util.py:55)
+    c = T // S
+    return np.asarray(list(range(0, T, c))) + 1
+
+
+def ddim_schedule(S, eta=0.0):
+    """Returns dict of fp32 numpy tables indexed by ddim index (ddim.py:110-139, util.py:63-74)."""
+    ac = alphas_cumprod_f32()
+    ts = make_ddim_timesteps(S)
+    alphas = ac[ts]                                                        # fp32 tensor
+    alphas_prev = np.asarray([float(ac[0])] + ac[ts[:-1]].tolist())        # fp64 holding fp32 values
+    a64 = alphas.double().numpy()
+    sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - a64) * (1 - a64 / alphas_prev))
+    return dict(timesteps=ts.astype(np.int64),
+                a_t=alphas.numpy().astype(np.float32),
+                a_prev=alphas_prev.astype(np.float32),
+                sigma=np.asarray(sigmas, dtype=np.float32),
+                sqrt_one_minus_a=torch.sqrt(1.0 - alphas).numpy().astype(np.float32))
+
+
+def timestep_embedding(t, dim, max_period=10000):
+    # util.py:151-171 (cos || sin)
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+# --------------------------------------------------------------------------------------------
+# UNet (ldm/modules/diffusionmodules/openaimodel.py, ldm/modules/attention.py)
+# --------------------------------------------------------------------------------------------
+def _conv(P, name, x, cin, cout, k, stride=1, padding=0, bias=True):
+    w = P(name + ".weight", (cout, cin, k, k), "w")
+    b = P(name + ".bias", (cout,), "b") if bias else None
+    return F.conv2d(x, w, b, stride=stride, padding=padding)
+
+
+def _linear(P, name, x, cin, cout, bias=True):
+    w = P(name + ".weight", (cout, cin), "w")
+    b = P(name + ".bias", (cout,), "b") if bias else None
+    return F.linear(x, w, b)
+
+
+def _gn(P, name, x, c, eps):
+    return F.group_norm(x, 32, P(name + ".weight", (c,), "g"), P(name + ".bias", (c,), "b"), eps)
+
+
+def _ln(P, name, x, c, eps=1e-5):
+    return F.layer_norm(x, (c,), P(name + ".weight", (c,), "g"), P(name + ".bias", (c,), "b"), eps)
+
+
+def unet_resblock(P, x, emb, cin, cout):
+    # openaimodel.py:255-275 (use_scale_shift_norm=False, no up/down)
+    h = _conv(P, "in_layers.2", F.silu(_gn(P, "in_layers.0", x, cin, 1e-5)), cin, cout, 3, padding=1)
+    e = _linear(P, "emb_layers.1", F.silu(emb), 1280, cout)
+    h = h + e[:, :, None, None]
+    h = _conv(P, "out_layers.3", F.silu(_gn(P, "out_layers.0", h, cout, 1e-5)), cout, cout, 3, padding=1)
+    if cin != cout:
+        x = _conv(P, "skip_connection", x, cin, cout, 1)
+    return x + h
+
+
+def cross_attention(P, x, ctx, dim, heads, ctx_dim):
+    # attention.py:179-221
+    d = dim // heads
+    q = _linear(P, "to_q", x, dim, dim, bias=False)
+    k = _linear(P, "to_k", ctx, ctx_dim, dim, bias=False)
+    v = _linear(P, "to_v", ctx, ctx_dim, dim, bias=False)
+    b, n, _ = q.shape
+    sp = lambda t: t.reshape(b, t.shape[1], heads, d).permute(0, 2, 1, 3).reshape(b * heads, t.shape[1], d)
+    q, k, v = sp(q), sp(k), sp(v)
+    sim = torch.einsum("bid,bjd->bij", q, k) * (d ** -0.5)
+    attn = sim.softmax(dim=-1)
+    out = torch.einsum("bij,bjd->bid", attn, v)
+    out = out.reshape(b, heads, n, d).permute(0, 2, 1, 3).reshape(b, n, dim)
+    return _linear(P, "to_out.0", out, dim, dim)
+
+
+def spatial_transformer(P, x, ctx, c, heads, ctx_dim):
+    # attention.py:278-289 + BasicTransformerBlock._forward :239-243 + GEGLU :37-45
+    b, _, h, w = x.shape
+    x_in = x
+    x = _gn(P, "norm", x, c, 1e-6)
+    x = _conv(P, "proj_in", x, c, c, 1)
+    x = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
+    B = P.sub("transformer_blocks.0.")
+    xn = _ln(B, "norm1", x, c)
+    x = cross_attention(B.sub("attn1."), xn, xn, c, heads, c) + x
+    x = cross_attention(B.sub("attn2."), _ln(B, "norm2", x, c), ctx, c, heads, ctx_dim) + x
+    y = _linear(B, "ff.net.0.proj", _ln(B, "norm3", x, c), c, 8 * c)
+    a, gate = y.chunk(2, dim=-1)
+    x = _linear(B, "ff.net.2", a * F.gelu(gate), 4 * c, c) + x
+    x = x.reshape(b, h, w, c).permute(0, 3, 1, 2)
+    return _conv(P, "proj_out", x, c, c, 1) + x_in
+
+
+def unet_layout(cfg=UNET_CFG):
+    """Block list mirroring UNetModel.__init__ (openaimodel.py:665-830).  Each entry is a list of
+    ops: ('res', cin, cout) | ('attn', c) | ('down', c) | ('up', c) | ('conv_in', cin, cout)."""
+    mc, mult, nrb = cfg["model_channels"], cfg["channel_mult"], cfg["num_res_blocks"]
+    inp = [[("conv_in", cfg["in_channels"], mc)]]
+    chans, ch, ds = [mc], mc, 1
+    for level, m in enumerate(mult):
+        for _ in range(nrb):
+            ops = [("res", ch, m * mc)]
+            ch = m * mc
+            if ds in cfg["attention_resolutions"]:
+                ops.append(("attn", ch))
+            inp.append(ops)
+            chans.append(ch)
+        if level != len(mult) - 1:
+            inp.append([("down", ch)])
+            chans.append(ch)
+            ds *= 2
+    mid = [("res", ch, ch), ("attn", ch), ("res", ch, ch)]
+    out = []
+    for level, m in list(enumerate(mult))[::-1]:
+        for i in range(nrb + 1):
+            ich = chans.pop()
+            ops = [("res", ch + ich, mc * m)]
+            ch = mc * m
+            if ds in cfg["attention_resolutions"]:
+                ops.append(("attn", ch))
+            if level and i == nrb:
+                ops.append(("up", ch))
+                ds //= 2
+            out.append(ops)
+    return inp, mid, out
+
+
+def _run_ops(P, ops, h, emb, ctx, cfg):
+    for j, op in enumerate(ops):
+        Q = P.sub(f"{j}.")
+        if op[0] == "conv_in":
+            h = F.conv2d(h, Q("weight", (op[2], op[1], 3, 3), "w"), Q("bias", (op[2],), "b"), padding=1)
+        elif op[0] == "res":
+            h = unet_resblock(Q, h, emb, op[1], op[2])
+        elif op[0] == "attn":
+            h = spatial_transformer(Q, h, ctx, op[1], cfg["num_heads"], cfg["context_dim"])
+        elif op[0] == "down":  # openaimodel.py:151,158-160
+            h = _conv(Q, "op", h, op[1], op[1], 3, stride=2, padding=1)
+        elif op[0] == "up":    # openaimodel.py:109-119
+            h = F.interpolate(h, scale_factor=2, mode="nearest") if h.device.type != "meta" else \
+                h.new_empty(h.shape[0], h.shape[1], h.shape[2] * 2, h.shape[3] * 2)
+            h = _conv(Q, "conv", h, op[1], op[1], 3, padding=1)
+    return h
+
+
+def unet_forward(P, x, t, ctx, cfg=UNET_CFG, taps=None):
+    """UNetModel.forward (openaimodel.py:860-907).  x [N,9,L,L] fp32, t [N] int64, ctx [N,T,768]."""
+    mc = cfg["model_channels"]
+    inp, mid, out = unet_layout(cfg)
+    temb = timestep_embedding(t, mc) if x.device.type != "meta" else x.new_empty(x.shape[0], mc)
+    emb = _linear(P, "time_embed.2", F.silu(_linear(P, "time_embed.0", temb, mc, 4 * mc)), 4 * mc, 4 * mc)
+    hs, h = [], x
+    for i, ops in enumerate(inp):
+        h = _run_ops(P.sub(f"input_blocks.{i}."), ops, h, emb, ctx, cfg)
+        hs.append(h)
+        if taps is not None:
+            taps[f"input_blocks.{i}"] = h
+    h = _run_ops(P.sub("middle_block."), mid, h, emb, ctx, cfg)
+    if taps is not None:
+        taps["middle_block"] = h
+    for i, ops in enumerate(out):
+        h = torch.cat([h, hs.pop()], dim=1)
+        h = _run_ops(P.sub(f"output_blocks.{i}."), ops, h, emb, ctx, cfg)
+        if taps is not None:
+            taps[f"output_blocks.{i}"] = h
+    h = F.silu(_gn(P, "out.0", h, mc, 1e-5))
+    return _conv(P, "out.2", h, mc, cfg["out_channels"], 3, padding=1)
+
+
+# --------------------------------------------------------------------------------------------
+# VAE (ldm/modules/diffusionmodules/model.py, ldm/models/autoencoder.py,
+#      ldm/modules/distributions/distributions.py)
+# --------------------------------------------------------------------------------------------
+def _swish(x):  # model.py:33-35
+    return x * torch.sigmoid(x)
+
+
+def vae_resnet(P, x, cin, cout):
+    # model.py:121-141 (temb is None, dropout 0)
+    h = _conv(P, "conv1", _swish(_gn(P, "norm1", x, cin, 1e-6)), cin, cout, 3, padding=1)
+    h = _conv(P, "conv2", _swish(_gn(P, "norm2", h, cout, 1e-6)), cout, cout, 3, padding=1)
+    if cin != cout:
+        x = _conv(P, "nin_shortcut", x, cin, cout, 1)
+    return x + h
+
+
+def vae_attn(P, x, c):
+    # model.py:178-202: single head, d=c, scale c^-0.5
+    h = _gn(P, "norm", x, c, 1e-6)
+    q, k, v = (_conv(P, n, h, c, c, 1) for n in ("q", "k", "v"))
+    b, _, hh, ww = q.shape
+    q = q.reshape(b, c, hh * ww).permute(0, 2, 1)
+    k = k.reshape(b, c, hh * ww)
+    w_ = torch.bmm(q, k) * (int(c) ** (-0.5))
+    w_ = F.softmax(w_, dim=2)
+    v = v.reshape(b, c, hh * ww)
+    h = torch.bmm(v, w_.permute(0, 2, 1)).reshape(b, c, hh, ww)
+    return x + _conv(P, "proj_out", h, c, c, 1)
+
+
+def vae_encoder(P, x, cfg=VAE_CFG):
+    # model.py:434-459
+    ch, mult, nrb = cfg["ch"], cfg["ch_mult"], cfg["num_res_blocks"]
+    h = _conv(P, "conv_in", x, cfg["in_channels"], ch, 3, padding=1)
+    cin = ch
+    for lvl, m in enumerate(mult):
+        for j in range(nrb):
+            h = vae_resnet(P.sub(f"down.{lvl}.block.{j}."), h, cin, ch * m)
+            cin = ch * m
+        if lvl != len(mult) - 1:
+            # model.py:72-79: pad (0,1,0,1) then stride-2 conv, padding 0
+            if h.device.type != "meta":
+                h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)
+            else:
+                h = h.new_empty(h.shape[0], h.shape[1], h.shape[2] + 1, h.shape[3] + 1)
+            h = _conv(P, f"down.{lvl}.downsample.conv", h, cin, cin, 3, stride=2, padding=0)
+    h = vae_resnet(P.sub("mid.block_1."), h, cin, cin)
+    h = vae_attn(P.sub("mid.attn_1."), h, cin)
+    h = vae_resnet(P.sub("mid.block_2."), h, cin, cin)
+    h = _swish(_gn(P, "norm_out", h, cin, 1e-6))
+    return _conv(P, "conv_out", h, cin, 2 * cfg["z_channels"], 3, padding=1)
+
+
+def vae_decoder(P, z, cfg=VAE_CFG):
+    # model.py:535-568
+    ch, mult, nrb = cfg["ch"], cfg["ch_mult"], cfg["num_res_blocks"]
+    cin = ch * mult[-1]
+    h = _conv(P, "conv_in", z, cfg["z_channels"], cin, 3, padding=1)
+    h = vae_resnet(P.sub("mid.block_1."), h, cin, cin)
+    h = vae_attn(P.sub("mid.attn_1."), h, cin)
+    h = vae_resnet(P.sub("mid.block_2."), h, cin, cin)
+    for lvl in reversed(range(len(mult))):
+        cout = ch * mult[lvl]
+        for j in range(nrb + 1):
+            h = vae_resnet(P.sub(f"up.{lvl}.block.{j}."), h, cin, cout)
+            cin = cout
+        if lvl != 0:
+            h = F.interpolate(h, scale_factor=2.0, mode="nearest") if h.device.type != "meta" else \
+                h.new_empty(h.shape[0], h.shape[1], h.shape[2] * 2, h.shape[3] * 2)
+            h = _conv(P, f"up.{lvl}.upsample.conv", h, cin, cin, 3, padding=1)
+    h = _swish(_gn(P, "norm_out", h, cin, 1e-6))
+    return _conv(P, "conv_out", h, cin, cfg["out_ch"], 3, padding=1)
+
+
+def vae_encode_moments(P, x, cfg=VAE_CFG):
+    # autoencoder.py:324-328
+    h = vae_encoder(P.sub("encoder."), x, cfg)
+    m = _conv(P, "quant_conv", h, 2 * cfg["z_channels"], 2 * cfg["embed_dim"], 1)
+    mean, logvar = m.chunk(2, dim=1)
+    return mean, torch.clamp(logvar, -30.0, 20.0)          # distributions.py:27-28
+
+
+def vae_encode(P, x, noise, cfg=VAE_CFG):
+    """get_first_stage_encoding(encode_first_stage(x)) (ddpm.py:850-857, distributions.py:35-37);
+    the posterior noise is an explicit argument."""
+    mean, logvar = vae_encode_moments(P, x, cfg)
+    return SCALE_FACTOR * (mean + torch.exp(0.5 * logvar) * noise)
+
+
+def vae_decode(P, z, cfg=VAE_CFG):
+    # ddpm.py:1277-1337 (z/scale, first 4 channels) -> autoencoder.py:330-333
+    z = (1.0 / SCALE_FACTOR) * z[:, :4]
+    z = _conv(P, "post_quant_conv", z, cfg["embed_dim"], cfg["z_channels"], 1)
+    return vae_decoder(P.sub("decoder."), z, cfg)
+
+
+# --------------------------------------------------------------------------------------------
+# CLIP ViT-L/14 vision tower (third-party: transformers CLIPVisionModel, called at
+# ldm/modules/encoders/modules.py:254-256) + mapper2/final_ln2 (modules.py:259-260, xf.py)
+# --------------------------------------------------------------------------------------------
+def _quick_gelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+def clip_vision_pooled(P, img, cfg=CLIP_CFG):
+    """HF CLIPVisionTransformer: patch conv (no bias) + CLS + pos-emb -> pre_layrnorm -> 24 pre-LN
+    layers (MHA 16x64 with q scaled by d^-0.5, quick-GELU MLP) -> post_layernorm(CLS)."""
+    W, nh, p = cfg["width"], cfg["heads"], cfg["patch"]
+    ntok = (cfg["image"] // p) ** 2 + 1
+    E = P.sub("embeddings.")
+    x = F.conv2d(img, E("patch_embedding.weight", (W, 3, p, p), "w"), None, stride=p)
+    b = x.shape[0]
+    x = x.flatten(2).transpose(1, 2)
+    cls = E("class_embedding", (W,), "emb")
+    x = torch.cat([cls.expand(b, 1, W), x], dim=1) + E("position_embedding.weight", (ntok, W), "emb")[None]
+    x = _ln(P, "pre_layrnorm", x, W)
+    d = W // nh
+    for i in range(cfg["layers"]):
+        L = P.sub(f"encoder.layers.{i}.")
+        h = _ln(L, "layer_norm1", x, W)
+        q = _linear(L, "self_attn.q_proj", h, W, W) * (d ** -0.5)
+        k = _linear(L, "self_attn.k_proj", h, W, W)
+        v = _linear(L, "self_attn.v_proj", h, W, W)
+        sp = lambda t: t.reshape(b, -1, nh, d).transpose(1, 2)
+        a = torch.softmax(sp(q) @ sp(k).transpose(-1, -2), dim=-1) @ sp(v)
+        a = a.transpose(1, 2).reshape(b, -1, W)
+        x = x + _linear(L, "self_attn.out_proj", a, W, W)
+        h = _ln(L, "layer_norm2", x, W)
+        x = x + _linear(L, "mlp.fc2", _quick_gelu(_linear(L, "mlp.fc1", h, W, cfg["mlp"])), cfg["mlp"], W)
+    return _ln(P, "post_layernorm", x[:, 0], W)
+
+
+def xf_block(P, x, width):
+    # xf.py:66-101 with n_ctx=1, heads=1: softmax over one key == 1 -> attention returns v
+    h = _ln(P, "ln_1", x, width)
+    qkv = _linear(P, "attn.c_qkv", h, width, 3 * width)
+    bs, n_ctx, _ = qkv.shape
+    attn_ch = width
+    scale = 1 / math.sqrt(math.sqrt(attn_ch))
+    q, k, v = torch.split(qkv.view(bs, n_ctx, 1, -1), attn_ch, dim=-1)
+    w = torch.softmax(torch.einsum("bthc,bshc->bhts", q * scale, k * scale).float(), dim=-1)
+    a = torch.einsum("bhts,bshc->bthc", w, v).reshape(bs, n_ctx, -1)
+    x = x + _linear(P, "attn.c_proj", a, width, width)
+    h = _ln(P, "ln_2", x, width)
+    return x + _linear(P, "mlp.c_proj", F.gelu(_linear(P, "mlp.c_fc", h, width, 4 * width)), 4 * width, width)
+
+
+def clip_embed(P, img, cfg=CLIP_CFG):
+    """FrozenCLIPEmbedder.forward (encoders/modules.py:253-261): [B,3,224,224] -> [B,1,768]."""
+    z = clip_vision_pooled(P.sub("model.vision_model."), img, cfg)
+    z = F.linear(z, P("model.visual_projection.weight", (cfg["proj"], cfg["width"]), "w"))
+    z = z.unsqueeze(1)
+    for i in range(cfg["mapper_layers"]):
+        z = xf_block(P.sub(f"mapper2.resblocks.{i}."), z, cfg["proj"])
+    return _ln(P, "final_ln2", z, cfg["proj"])
+
+
+# --------------------------------------------------------------------------------------------
+# ArcFace IR-SE50 (src/Face_models/encoders/{model_irse,helpers}.py) + pre-processing
+# (ldm/models/diffusion/ddpm.py:112-124)
+# --------------------------------------------------------------------------------------------
+def _bn(P, name, x, c):
+    return F.batch_norm(x, P(name + ".running_mean", (c,), "bn_mean"), P(name + ".running_var", (c,), "bn_var"),
+                        P(name + ".weight", (c,), "g"), P(name + ".bias", (c,), "b"), False, 0.0, 1e-5)
+
+
+ARC_BLOCKS = [(64, 64, 3), (64, 128, 4), (128, 256, 14), (256, 512, 3)]  # helpers.py:29-36
+
+
+def arcface_units():
+    units = []
+    for cin, depth, n in ARC_BLOCKS:
+        units.append((cin, depth, 2))
+        units += [(depth, depth, 1)] * (n - 1)
+    return units
+
+
+def arcface_backbone(P, x):
+    # model_irse.py:44-69, helpers.py:97-119, :56-72, :15-18
+    x = F.conv2d(x, P("input_layer.0.weight", (64, 3, 3, 3), "w"), None, 1, 1)
+    x = F.prelu(_bn(P, "input_layer.1", x, 64), P("input_layer.2.weight", (64,), "prelu"))
+    for i, (cin, depth, stride) in enumerate(arcface_units()):
+        U = P.sub(f"body.{i}.")
+        if cin == depth:
+            sc = x[:, :, ::stride, ::stride]                                  # MaxPool2d(1, stride)
+        else:
+            sc = _bn(U, "shortcut_layer.1", F.conv2d(x, U("shortcut_layer.0.weight", (depth, cin, 1, 1), "w"),
+                                                     None, stride), depth)
+        r = _bn(U, "res_layer.0", x, cin)
+        r = F.conv2d(r, U("res_layer.1.weight", (depth, cin, 3, 3), "w"), None, 1, 1)
+        r = F.prelu(r, U("res_layer.2.weight", (depth,), "prelu"))
+        r = F.conv2d(r, U("res_layer.3.weight", (depth, depth, 3, 3), "w"), None, stride, 1)
+        r = _bn(U, "res_layer.4", r, depth)
+        s = r.mean(dim=(2, 3), keepdim=True)
+        s = F.relu(F.conv2d(s, U("res_layer.5.fc1.weight", (depth // 16, depth, 1, 1), "w")))
+        s = torch.sigmoid(F.conv2d(s, U("res_layer.5.fc2.weight", (depth, depth // 16, 1, 1), "w")))
+        x = r * s + sc
+    x = _bn(P, "output_layer.0", x, 512)
+    x = x.reshape(x.shape[0], -1)                                             # Flatten (NCHW order)
+    x = _linear(P, "output_layer.3", x, 512 * 7 * 7, 512)
+    x = F.batch_norm(x, P("output_layer.4.running_mean", (512,), "bn_mean"),
+                     P("output_layer.4.running_var", (512,), "bn_var"),
+                     P("output_layer.4.weight", (512,), "g"), P("output_layer.4.bias", (512,), "b"), False, 0.0, 1e-5)
+    return x / torch.norm(x, 2, 1, True)
+
+
+def arcface_preprocess(x):
+    """IDLoss.extract_feats (ddpm.py:112-119): un-CLIP-normalise, to [-1,1], AdaptiveAvgPool 256,
+    crop [35:223, 32:220], AdaptiveAvgPool 112."""
+    mean = torch.tensor(CLIP_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_STD).view(1, 3, 1, 1)
+    x = x * std + mean
+    x = (x - 0.5) / 0.5
+    if x.shape[2] != 256:
+        x = F.adaptive_avg_pool2d(x, (256, 256))
+    x = x[:, :, 35:223, 32:220]
+    return F.adaptive_avg_pool2d(x, (112, 112))
+
+
+def arcface_embed(P, ref_img):
+    return arcface_backbone(P, arcface_preprocess(ref_img))
+
+
+# --------------------------------------------------------------------------------------------
+# conditioning fusion (ldm/models/diffusion/ddpm.py:872-1045, :1068-1099)
+# --------------------------------------------------------------------------------------------
+def resize_bilinear_noaa(x, size):
+    """TF.resize on a tensor with the pinned torchvision 0.14 default (bilinear, antialias off,
+    align_corners False) -- ddpm.py:912; see SURVEY 8(c)(iii)."""
+    return F.interpolate(x, size=size, mode="bilinear", align_corners=False, antialias=False)
+
+
+def target_clip_input(tar):
+    # ddpm.py:907-912
+    mean = torch.tensor(CLIP_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_STD).view(1, 3, 1, 1)
+    t = ((tar + 1.0) / 2.0 - mean) / std
+    return resize_bilinear_noaa(t, (224, 224))
+
+
+def conditioning_with_feat(P, ref_img, tar_img, landmarks136):
+    """c = (clip*1 + id*10 + lm*0.05)/11.05  -> [B,1,768]  (ddpm.py:904-915, :1010-1012, :1038-1039).
+    landmarks136: raw dlib 68x2 landmarks or zeros (ddpm.py:1081-1083) -- an input here."""
+    C = P.sub(PFX_CLIP)
+    c_src = _linear(P, "proj_out_source", clip_embed(C, ref_img), 768, 768)
+    c = _linear(P, "proj_out_target", clip_embed(C, target_clip_input(tar_img)), 768, 768) + c_src
+    c2 = _linear(P, "ID_proj_out", arcface_embed(P.sub(PFX_ARC), ref_img), 512, 768).unsqueeze(1)
+    lm = _linear(P, "landmark_proj_out", landmarks136, 136, 768).unsqueeze(1)
+    tot = CLIP_WEIGHT + ID_WEIGHT + LANDMARK_WEIGHT
+    return (c * CLIP_WEIGHT + c2 * ID_WEIGHT + lm * LANDMARK_WEIGHT) / tot
+
+
+# --------------------------------------------------------------------------------------------
+# DDIM (ldm/models/diffusion/ddim.py:200-251, :323-375)
+# --------------------------------------------------------------------------------------------
+def concat9(x, z_inpaint, mask):
+    return torch.cat([x, z_inpaint, mask], dim=1)                              # ddim.py:330
+
+
+def cfg_ddim_update(x, e_u, e_c, scale, a_t, a_prev, sigma, sqrt_one_minus_at, noise=None):
+    """ddim.py:346, :363-374, all fp32, same op order."""
+    f = lambda v: torch.full((x.shape[0], 1, 1, 1), float(v), dtype=torch.float32)
+    e_t = e_u + scale * (e_c - e_u)
+    pred_x0 = (x - f(sqrt_one_minus_at) * e_t) / f(a_t).sqrt()
+    dir_xt = (1.0 - f(a_prev) - f(sigma) ** 2).sqrt() * e_t
+    nz = f(sigma) * (noise if noise is not None else torch.zeros_like(x))
+    return f(a_prev).sqrt() * pred_x0 + dir_xt + nz, pred_x0, e_t
+
+
+def ddim_sample(P_unet, x_T, z_inpaint, mask, c, uc, S, scale, eta=0.0, log_every_t=100, cfg=UNET_CFG,
+                n_steps_limit=None):
+    """DDIMSampler.sample with test_model_kwargs (ddim.py:142-251,323-375).  Returns (x0, inter)."""
+    sch = ddim_schedule(S, eta)
+    ts = sch["timesteps"]
+    total = len(ts)
+    img = x_T
+    inter = {"x_inter": [img], "pred_x0": [img]}
+    b = x_T.shape[0]
+    for i, step in enumerate(np.flip(ts)):
+        if n_steps_limit is not None and i >= n_steps_limit:
+            break
+        index = total - i - 1
+        t = torch.full((b,), int(step), dtype=torch.long)
+        x9 = concat9(img, z_inpaint, mask)
+        x_in, t_in, c_in = torch.cat([x9] * 2), torch.cat([t] * 2), torch.cat([uc, c])
+        e_u, e_c = unet_forward(P_unet, x_in, t_in, c_in, cfg).chunk(2)
+        img, pred_x0, _ = cfg_ddim_update(img, e_u, e_c, scale, sch["a_t"][index], sch["a_prev"][index],
+                                          sch["sigma"][index], sch["sqrt_one_minus_a"][index])
+        if index % log_every_t == 0 or index == total - 1:
+            inter["x_inter"].append(img)
+            inter["pred_x0"].append(pred_x0)
+    return img, inter
+
+
+# --------------------------------------------------------------------------------------------
+# specs + whole pipeline (scripts/inference_test_bench.py:438-495)
+# --------------------------------------------------------------------------------------------
+def _meta(*shape, dtype=torch.float32):
+    return torch.empty(*shape, device="meta", dtype=dtype)
+
+
+def unet_spec(prefix=PFX_UNET, cfg=UNET_CFG):
+    P = Params(None, prefix)
+    unet_forward(P, _meta(1, cfg["in_channels"], 32, 32), _meta(1, dtype=torch.long), _meta(1, 1, cfg["context_dim"]), cfg)
+    return P.spec
+
+
+def vae_spec(prefix=PFX_VAE, cfg=VAE_CFG):
+    P = Params(None, prefix)
+    vae_encode_moments(P, _meta(1, 3, 64, 64), cfg)
+    vae_decode(P, _meta(1, 4, 8, 8), cfg)
+    return P.spec
+
+
+def clip_spec(prefix=PFX_CLIP, cfg=CLIP_CFG):
+    P = Params(None, prefix)
+    clip_embed(P, _meta(1, 3, cfg["image"], cfg["image"]), cfg)
+    return P.spec
+
+
+def arcface_spec(prefix=PFX_ARC):
+    P = Params(None, prefix)
+    with torch.no_grad():
+        arcface_backbone(P, _meta(1, 3, 112, 112))
+    return P.spec
+
+
+def fusion_spec():
+    spec = OrderedDict()
+    spec["learnable_vector"] = ((1, 1, 768), "unit")                      # ddpm.py:698
+    for n, (i, o) in dict(proj_out_source=(768, 768), proj_out_target=(768, 768), ID_proj_out=(512, 768),
+                          landmark_proj_out=(136, 768)).items():
+        spec[n + ".weight"] = ((o, i), "w")
+        spec[n + ".bias"] = ((o,), "b")
+    return spec
+
+
+def full_spec():
+    spec = OrderedDict()
+    for s in (unet_spec(), vae_spec(), clip_spec(), arcface_spec(), fusion_spec()):
+        spec.update(s)
+    return spec
+
+
+@torch.no_grad()
+def swap_pipeline(sd, ref_img, tar_img, inpaint_img, mask_lat, landmarks136, x_T, enc_noise, S=50, scale=3.5,
+                  n_steps_limit=None):
+    """scripts/inference_test_bench.py:438-495 restated on explicit tensors.
+    Returns dict(c, z_inpaint, samples, image)."""
+    P = Params(sd)
+    b = ref_img.shape[0]
+    uc = sd["learnable_vector"].repeat(b, 1, 1)                                 # :441
+    c = conditioning_with_feat(P, ref_img, tar_img, landmarks136)              # :447-448
+    z_inpaint = vae_encode(P.sub(PFX_VAE), inpaint_img, enc_noise)             # :462-463
+    samples, _ = ddim_sample(P.sub(PFX_UNET), x_T, z_inpaint, mask_lat, c, uc, S, scale,
+                             n_steps_limit=n_steps_limit)                      # :469-479
+    x = vae_decode(P.sub(PFX_VAE), samples)                                     # :493
+    return dict(c=c, z_inpaint=z_inpaint, samples=samples, image=torch.clamp((x + 1.0) / 2.0, 0.0, 1.0))
+
+
+def synthetic_inputs(B, H, seed=42):
+    """Synthetic inputs of SURVEY 8(d): target U(-1,1), centred-ellipse mask, ref N(0,1), x_T, noise."""
+    g = torch.Generator().manual_seed(seed)
+    L = H // 8
+    tar = torch.rand(B, 3, H, H, generator=g) * 2 - 1
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, H), indexing="ij")
+    mask = ((xx / 0.55) ** 2 + (yy / 0.7) ** 2 > 1.0).float()[None, None].repeat(B, 1, 1, 1)
+    mask_lat = F.interpolate(mask, size=(L, L), mode="bilinear", align_corners=False)
+    ref = torch.randn(B, 3, 224, 224, generator=g)
+    x_T = torch.randn(B, 4, L, L, generator=g)
+    enc_noise = torch.randn(B, 4, L, L, generator=g)
+    return dict(ref_img=ref, tar_img=tar, inpaint_img=tar * mask, mask_lat=mask_lat,
+                landmarks136=torch.zeros(B, 136), x_T=x_T, enc_noise=enc_noise)

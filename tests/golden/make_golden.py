@@ -1,0 +1,257 @@
+"""Pins oracle/reface_oracle.py against the REAL reference modules and writes golden vectors.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+For every component it (1) builds the reference nn.Module from /root/reference (with the import
+shims of oracle/ref_shims for packages missing in this image), (2) loads the oracle's seeded
+state dict with strict=True -- which proves the oracle's parameter spec equals the reference's --
+(3) runs both on the same seeded inputs, asserts agreement (fp32 round-off only) and (4) stores the
+REFERENCE outputs in tests/golden/<name>.npz.  tests/test_oracle.py re-checks the oracle against
+these files everywhere (no /root/reference needed).
+"""
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_shims"))
+sys.path.insert(0, "/root/reference")
+sys.dont_write_bytecode = True
+
+import reface_oracle as O  # noqa: E402
+
+torch.set_grad_enabled(False)
+SEED = 0
+
+
+def sub_sd(spec, prefix, seed=SEED):
+    sd = O.init_state_dict(spec, seed)
+    return sd, {k[len(prefix):]: v for k, v in sd.items()}
+
+
+def check(name, ref, ora, tol):
+    err = (ref - ora).abs().max().item()
+    mag = ref.abs().max().item()
+    print(f"  {name}: max|ref-oracle|={err:.3e}  max|ref|={mag:.3e}")
+    assert err <= tol * max(1.0, mag), (name, err, mag)
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()})
+    print(f"  wrote {path} ({os.path.getsize(path)/1024:.1f} KiB)")
+
+
+def golden_schedule():
+    print("schedule")
+    from ldm.modules.diffusionmodules.util import make_beta_schedule, make_ddim_timesteps, \
+        make_ddim_sampling_parameters, timestep_embedding
+    betas = make_beta_schedule("linear", 1000, linear_start=O.LINEAR_START, linear_end=O.LINEAR_END)
+    ac = torch.tensor(np.cumprod(1.0 - betas, axis=0), dtype=torch.float32)
+    out = {}
+    for S in (5, 30, 50):
+        ts = make_ddim_timesteps("uniform", S, 1000, verbose=False)
+        sig, a, ap = make_ddim_sampling_parameters(ac.cpu(), ts, 0.0, verbose=False)
+        sch = O.ddim_schedule(S, 0.0)
+        assert np.array_equal(ts, sch["timesteps"])
+        assert np.array_equal(a.numpy(), sch["a_t"]) and np.array_equal(np.float32(ap), sch["a_prev"])
+        assert np.array_equal(np.sqrt(1.0 - a).numpy(), sch["sqrt_one_minus_a"])
+        out[f"ts{S}"], out[f"a{S}"], out[f"ap{S}"] = ts, a.numpy(), np.float32(ap)
+    t = torch.tensor([981, 1, 500])
+    te = timestep_embedding(t, 320)
+    assert torch.equal(te, O.timestep_embedding(t, 320))
+    save("schedule", alphas_cumprod=ac, temb=te, temb_t=t, **out)
+
+
+def golden_unet():
+    print("unet")
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    cfg = O.UNET_CFG
+    m = UNetModel(image_size=32, in_channels=9, out_channels=4, model_channels=320, attention_resolutions=[4, 2, 1],
+                  num_res_blocks=2, channel_mult=[1, 2, 4, 4], num_heads=8, use_spatial_transformer=True,
+                  transformer_depth=1, context_dim=768, use_checkpoint=True, legacy=False,
+                  add_conv_in_front_of_unet=False).eval()
+    sd, sub = sub_sd(O.unet_spec(), O.PFX_UNET)
+    m.load_state_dict(sub, strict=True)
+    g = torch.Generator().manual_seed(1)
+    for L, N in ((16, 2), (32, 2)):
+        x = torch.randn(N, 9, L, L, generator=g)
+        t = torch.tensor([981, 401][:N])
+        ctx = torch.randn(N, 1, 768, generator=g)
+        ref = m(x, t, context=ctx)
+        taps = {}
+        ora = O.unet_forward(O.Params(sd, O.PFX_UNET), x, t, ctx, cfg, taps=taps)
+        check(f"unet L={L}", ref, ora, 2e-5)
+        save(f"unet_L{L}", x=x, t=t, ctx=ctx, eps=ref,
+             **{"tapmean_" + k.replace(".", "_"): v.mean() for k, v in taps.items()},
+             **{"tapstd_" + k.replace(".", "_"): v.std() for k, v in taps.items()})
+    return m, sd
+
+
+def golden_ddim(unet, sd):
+    print("ddim (reference DDIMSampler driving the reference UNet)")
+    from ldm.models.diffusion.ddim import DDIMSampler
+    DDIMSampler.register_buffer = lambda self, n, a: setattr(self, n, a)   # ddim.py:104-108 hard-codes cuda
+    ac = O.alphas_cumprod_f32()
+
+    class FakeLD:   # the attributes DDIMSampler touches (ddim.py:100,113-119,207,345)
+        num_timesteps = 1000
+        betas = torch.tensor(O.make_beta_schedule(), dtype=torch.float32)
+        alphas_cumprod = ac
+        alphas_cumprod_prev = torch.tensor(np.append(1.0, ac.double().numpy()[:-1]), dtype=torch.float32)
+        device = torch.device("cpu")
+
+        def apply_model(self, x, t, c):          # ddpm.py:1519-1617 + DiffusionWrapper :2244-2246
+            return unet(x, t, context=torch.cat([c], 1))
+
+    g = torch.Generator().manual_seed(2)
+    B, L, S, scale = 1, 16, 5, 3.5
+    x_T = torch.randn(B, 4, L, L, generator=g)
+    z = torch.randn(B, 4, L, L, generator=g)
+    mask = (torch.rand(B, 1, L, L, generator=g) > 0.5).float()
+    c = torch.randn(B, 1, 768, generator=g)
+    uc = torch.randn(B, 1, 768, generator=g)
+    smp = DDIMSampler(FakeLD())
+    ref, inter = smp.sample(S=S, conditioning=c, batch_size=B, shape=[4, L, L], verbose=False,
+                            unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0, x_T=x_T,
+                            log_every_t=2, test_model_kwargs={"inpaint_image": z, "inpaint_mask": mask})
+    ora, ointer = O.ddim_sample(O.Params(sd, O.PFX_UNET), x_T, z, mask, c, uc, S, scale, log_every_t=2)
+    check("ddim x0", ref, ora, 5e-5)
+    assert len(inter["x_inter"]) == len(ointer["x_inter"])
+    save("ddim_S5_L16", x_T=x_T, z=z, mask=mask, c=c, uc=uc, x0=ref, n_inter=len(inter["x_inter"]),
+         pred_x0_last=inter["pred_x0"][-1])
+    # the concat must be a pure copy (bit exact)
+    assert torch.equal(O.concat9(x_T, z, mask), torch.cat([x_T, z, mask], 1))
+
+
+def golden_vae():
+    print("vae")
+    from ldm.models.autoencoder import AutoencoderKL
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    m = AutoencoderKL(ddconfig=dd, lossconfig={"target": "torch.nn.Identity"}, embed_dim=4).eval()
+    sd, sub = sub_sd(O.vae_spec(), O.PFX_VAE)
+    m.load_state_dict(sub, strict=True)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 3, 64, 64, generator=g) * 2 - 1
+    noise = torch.randn(1, 4, 8, 8, generator=g)
+    post = m.encode(x)
+    ref_z = O.SCALE_FACTOR * (post.mean + post.std * noise)      # distributions.py:35-37 with explicit noise
+    P = O.Params(sd, O.PFX_VAE)
+    mean, logvar = O.vae_encode_moments(P, x)
+    check("vae mean", post.mean, mean, 2e-5)
+    check("vae logvar", post.logvar, logvar, 2e-5)
+    ora_z = O.vae_encode(P, x, noise)
+    check("vae z", ref_z, ora_z, 2e-5)
+    zz = torch.randn(1, 4, 8, 8, generator=g) * 0.18215 * 4
+    ref_img = m.decode((1.0 / O.SCALE_FACTOR) * zz)
+    check("vae decode", ref_img, O.vae_decode(P, zz), 2e-5)
+    save("vae_64", x=x, noise=noise, mean=post.mean, logvar=post.logvar, z=ref_z, zdec=zz, img=ref_img)
+
+
+def _build_clip_embedder():
+    import transformers
+    from transformers import CLIPConfig, CLIPModel
+    conf = CLIPConfig(vision_config=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24,
+                                         num_attention_heads=16, image_size=224, patch_size=14, hidden_act="quick_gelu"),
+                      text_config=dict(hidden_size=64, intermediate_size=64, num_hidden_layers=1, num_attention_heads=1),
+                      projection_dim=768)
+    transformers.CLIPModel.from_pretrained = classmethod(lambda cls, *a, **k: CLIPModel(conf))
+    transformers.CLIPTokenizer.from_pretrained = classmethod(lambda cls, *a, **k: None)
+    import ldm.modules.encoders.modules as em
+    em.CLIPModel, em.CLIPTokenizer = transformers.CLIPModel, transformers.CLIPTokenizer
+    return em.FrozenCLIPEmbedder().eval()
+
+
+def golden_clip():
+    print("clip (+mapper2/final_ln2)")
+    m = _build_clip_embedder()
+    sd, sub = sub_sd(O.clip_spec(), O.PFX_CLIP)
+    missing, unexpected = m.load_state_dict(sub, strict=False)
+    # the embedder also constructs the unused text tower / mapper / final_ln / projection_back
+    # (encoders/modules.py:215-233): they must be the ONLY keys our spec lacks.
+    assert not unexpected, unexpected
+    for k in missing:
+        assert k.startswith(("model.text_model", "model.text_projection", "model.logit_scale", "mapper.", "final_ln.",
+                             "projection_back.", "model.vision_model.embeddings.position_ids")), k
+    g = torch.Generator().manual_seed(4)
+    img = torch.randn(1, 3, 224, 224, generator=g)
+    ref = m.encode(img)
+    ora = O.clip_embed(O.Params(sd, O.PFX_CLIP), img)
+    check("clip", ref, ora, 5e-5)
+    save("clip_B1", img_seed=4, out=ref)
+    return m, sd
+
+
+def golden_arcface_and_fusion(clip_mod, clip_sd):
+    print("arcface + conditioning fusion")
+    from src.Face_models.encoders.model_irse import Backbone
+    import ldm.models.diffusion.ddpm as ddpm
+    bb = Backbone(input_size=112, num_layers=50, drop_ratio=0.6, mode="ir_se").eval()
+    sd, sub = sub_sd(O.arcface_spec(), O.PFX_ARC)
+    missing, unexpected = bb.load_state_dict(sub, strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
+    g = torch.Generator().manual_seed(5)
+    ref_img = torch.randn(2, 3, 224, 224, generator=g)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "arc.pth")
+        torch.save(bb.state_dict(), path)
+        opts = types.SimpleNamespace(other_params=types.SimpleNamespace(arcface_path=path))
+        idl = ddpm.IDLoss(opts).eval()
+    ref = idl.extract_feats(ref_img)[0]
+    ora = O.arcface_embed(O.Params(sd, O.PFX_ARC), ref_img)
+    check("arcface", ref, ora, 5e-5)
+
+    fsd = O.init_state_dict(O.fusion_spec(), SEED)
+    lin = lambda n, i, o: _mk_linear(fsd, n, i, o)
+    tar = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    lm_raw = torch.zeros(2, 136)
+    fake = types.SimpleNamespace(
+        training=False, update_weight=False, clip_weight=1.0, ID_weight=10.0, Landmarks_weight=0.05,
+        Source_CLIP_feat=True, Target_CLIP_feat=True, use_3dmm=False, normalize=False, Landmark_cond=True,
+        weight_division=True, concat_feat=False, stack_feat=False, land_mark_id_seperate_layers=False,
+        sep_head_att=False, device=torch.device("cpu"),
+        get_learned_conditioning=lambda x: clip_mod.encode(x), face_ID_model=idl,
+        proj_out_source=lin("proj_out_source", 768, 768), proj_out_target=lin("proj_out_target", 768, 768),
+        ID_proj_out=lin("ID_proj_out", 512, 768))
+    # torchvision>=0.17 defaults to antialias=True on tensors; the pinned 0.14 does not
+    import torchvision.transforms.functional as TF
+    _resize = TF.resize
+    ddpm.TF.resize = lambda img, size, *a, **k: _resize(img, list(size), antialias=False)
+    lm = lin("landmark_proj_out", 136, 768)(lm_raw)                     # ddpm.py:1096
+    ref_c = ddpm.LatentDiffusion.conditioning_with_feat(fake, ref_img, lm, tar=tar)
+    ddpm.TF.resize = _resize
+    full = dict(clip_sd); full.update(sd); full.update(fsd)
+    ora_c = O.conditioning_with_feat(O.Params(full), ref_img, tar, lm_raw)
+    check("conditioning", ref_c, ora_c, 5e-5)
+    save("cond_B2", ref_seed=5, id_feat=ref, c=ref_c, tar=tar)
+
+
+def _mk_linear(sd, name, i, o):
+    l = torch.nn.Linear(i, o)
+    l.weight.copy_(sd[name + ".weight"]); l.bias.copy_(sd[name + ".bias"])
+    return l
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["schedule", "unet", "vae", "clip"]
+    if "schedule" in which:
+        golden_schedule()
+    if "unet" in which:
+        m, sd = golden_unet()
+        golden_ddim(m, sd)
+        del m, sd
+    if "vae" in which:
+        golden_vae()
+    if "clip" in which:
+        cm, csd = golden_clip()
+        golden_arcface_and_fusion(cm, csd)
+    print("OK")
