@@ -1,0 +1,107 @@
+/* reface_b200 -- C ABI of the B200-native REFace inference hot path.
+ *
+ * The reference (Sanoojan/REFace) is pure Python/PyTorch and has no FFI boundary of its own; its plugin
+ * mechanism is ldm/util.py:78-93 `instantiate_from_config` (YAML `target:` -> constructor).  The Python
+ * classes in reface_b200/ are the drop-in targets for those slots and call this library through ctypes.
+ * Every entry point below names the reference interface it replaces (file:line relative to the reference).
+ *
+ * Conventions: plain pointers and sizes only, no torch types.  All tensor pointers are DEVICE pointers
+ * (fp32, contiguous, NCHW for images/latents, row-major otherwise) unless marked [host].  The caller owns
+ * every buffer; the library borrows them for the duration of the call.  Work is enqueued on `stream`
+ * (a cudaStream_t passed as void*) and is asynchronous w.r.t. the host.  Return value: 0 = OK, negative =
+ * error (message via rfb_last_error).  One context per GPU; a context is not re-entrant.
+ */
+#ifndef REFACE_B200_H
+#define REFACE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rfb_ctx rfb_ctx;
+
+/* ---- context / weights ------------------------------------------------------------------------ */
+/* One context per device: owns weights, the activation arena (arena_bytes; 0 = default) and workspaces. */
+int rfb_init(int device, size_t arena_bytes, rfb_ctx** out);
+void rfb_destroy(rfb_ctx* ctx);
+const char* rfb_last_error(rfb_ctx* ctx);
+/* Replaces model.load_state_dict(sd) (scripts/inference_test_bench.py:98-103): one call per state-dict
+ * entry, keyed by the reference's own key (e.g. "model.diffusion_model.input_blocks.0.0.weight").
+ * `data` may be a host or a device pointer (fp32). */
+int rfb_set_param(rfb_ctx* ctx, const char* name, const float* data, int ndim, const int64_t* shape);
+int rfb_has_param(rfb_ctx* ctx, const char* name);
+/* Build the packed (fp16, implicit-GEMM layout) networks from the registered parameters.  `prefix` is the
+ * state-dict prefix ("model.diffusion_model.", "first_stage_model.", "cond_stage_model.",
+ * "face_ID_model.facenet.").  Replace the constructors reached through instantiate_from_config:
+ * UNetModel (openaimodel.py:558), AutoencoderKL (autoencoder.py:285), FrozenCLIPEmbedder
+ * (encoders/modules.py:211), Backbone (model_irse.py:10). */
+int rfb_build_unet(rfb_ctx* ctx, const char* prefix);
+int rfb_build_vae(rfb_ctx* ctx, const char* prefix);
+int rfb_build_clip(rfb_ctx* ctx, const char* prefix);
+int rfb_build_arcface(rfb_ctx* ctx, const char* prefix);
+/* Tunables ("gemm_bn", "gemm_stages", "gemm_smem_budget", "attn_flash"); returns 0 if known. */
+int rfb_set_option(rfb_ctx* ctx, const char* key, long long value);
+long long rfb_launch_count(rfb_ctx* ctx); /* kernels launched by this library so far */
+size_t rfb_arena_peak(rfb_ctx* ctx);
+
+/* ---- hot path ---------------------------------------------------------------------------------- */
+/* UNetModel.forward (openaimodel.py:860-907) behind LatentDiffusion.apply_model (ddpm.py:1519-1617):
+ * x9 [N,9,L,L], t [N] int64, context [N,T,768] -> eps [N,4,L,L]. */
+int rfb_unet_forward(rfb_ctx* ctx, const float* x9, const int64_t* t, const float* context, int N, int L, int T,
+                     float* eps, void* stream);
+/* torch.cat([x, inpaint_image, inpaint_mask], 1) and the CFG duplication (ddim.py:330,338): out [dup*B,9,L,L]. */
+int rfb_concat9(rfb_ctx* ctx, const float* x, const float* z_inpaint, const float* mask, int B, int L, int dup,
+                float* out, void* stream);
+/* CFG combine + DDIM x_{t-1} (ddim.py:346,363-374).  eps2 = [e_uncond ; e_cond] ([2B,4,L,L]) when has_uncond,
+ * else [B,4,L,L].  noise may be NULL (eta = 0).  pred_x0 may be NULL. */
+int rfb_cfg_ddim_update(rfb_ctx* ctx, const float* x, const float* eps2, const float* noise, long long count,
+                        float scale, float a_t, float a_prev, float sigma, float sqrt_one_minus_at, int has_uncond,
+                        float* x_prev, float* pred_x0, void* stream);
+/* DDIMSampler.ddim_sampling with test_model_kwargs (ddim.py:200-251 driving p_sample_ddim :323-375).
+ * Schedule tables are [host] arrays of length n_steps indexed by DDIM index (computed by the caller exactly
+ * as make_schedule does, ddim.py:110-139).  cond/uncond [B,T,768]; uncond NULL or scale==1 disables CFG.
+ * noise: NULL or [n_steps,B,4,L,L].  inter_x/inter_pred_x0: NULL or room for every logged step
+ * (index % log_every_t == 0 or index == n_steps-1, ddim.py:247-249), in loop order. */
+int rfb_ddim_sample(rfb_ctx* ctx, const float* x_T, const float* z_inpaint, const float* mask, const float* cond,
+                    const float* uncond, int B, int L, int T, const int64_t* timesteps, const float* a_t,
+                    const float* a_prev, const float* sigma, const float* sqrt_one_minus_a, int n_steps, float cfg_scale,
+                    const float* noise, int log_every_t, float* x0_out, float* inter_x, float* inter_pred_x0,
+                    void* stream);
+/* get_first_stage_encoding(encode_first_stage(x)) (ddpm.py:1402-1439, 850-857; autoencoder.py:324-328;
+ * distributions.py:24-37): img [B,3,H,W] -> z = 0.18215*(mean + std*noise) [B,4,H/8,W/8].
+ * noise NULL => mode() (z = scaled mean).  mean/logvar outputs optional (NULL). */
+int rfb_vae_encode(rfb_ctx* ctx, const float* img, const float* noise, int B, int H, int W, float* z, float* mean,
+                   float* logvar, void* stream);
+/* decode_first_stage (ddpm.py:1277-1337; autoencoder.py:330-333): z [B,4,h,w] -> img [B,3,8h,8w]. */
+int rfb_vae_decode(rfb_ctx* ctx, const float* z, int B, int h, int w, float* img, void* stream);
+/* FrozenCLIPEmbedder.encode (encoders/modules.py:253-264): img [B,3,224,224] -> [B,1,768]. */
+int rfb_clip_encode(rfb_ctx* ctx, const float* img224, int B, float* out768, void* stream);
+/* IDLoss.extract_feats(x)[0] (ddpm.py:112-124 + model_irse.py:44-69): CLIP-normalised [B,3,224,224] -> [B,512]. */
+int rfb_arcface_embed(rfb_ctx* ctx, const float* img224_clipnorm, int B, float* out512, void* stream);
+/* LatentDiffusion.conditioning_with_feat (ddpm.py:872-1045) for the shipped config:
+ * c = (w_clip*(proj_src(clip_src)+proj_tgt(clip_tgt)) + w_id*ID_proj(id) + w_lm*landmark_proj(lm136)) / sum(w).
+ * clip_src/clip_tgt [B,768], id_feat [B,512], lm136 [B,136] -> c [B,1,768]. Uses the registered
+ * proj_out_source/proj_out_target/ID_proj_out/landmark_proj_out parameters. */
+int rfb_condition_fuse(rfb_ctx* ctx, const float* clip_src, const float* clip_tgt, const float* id_feat,
+                       const float* lm136, int B, float w_clip, float w_id, float w_lm, float* c_out, void* stream);
+/* tar -> un_norm -> CLIP normalise -> bilinear 224 (ddpm.py:907-912): [B,3,H,W] in [-1,1] -> [B,3,224,224]. */
+int rfb_target_clip_input(rfb_ctx* ctx, const float* tar, int B, int H, int W, float* out224, void* stream);
+
+/* ---- single-op entry points (kernel-level parity tests; fp32 in/out, converted internally) ------ */
+int rfb_op_linear(rfb_ctx* ctx, const float* x, const float* w, const float* bias, const float* residual, long long M,
+                  int K, int N, int act, int geglu, float* out, void* stream);
+int rfb_op_conv2d(rfb_ctx* ctx, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int O,
+                  int ksz, int stride, int pad_t, int pad_l, int pad_b, int pad_r, float* out, void* stream);
+int rfb_op_groupnorm(rfb_ctx* ctx, const float* x, const float* gamma, const float* beta, int N, int C, int H, int W,
+                     float eps, int silu, float* out, void* stream);
+int rfb_op_layernorm(rfb_ctx* ctx, const float* x, const float* gamma, const float* beta, long long rows, int C,
+                     float eps, float* out, void* stream);
+int rfb_op_attention(rfb_ctx* ctx, const float* qkv, int N, int L, int heads, int d, float scale, float* out,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REFACE_B200_H */

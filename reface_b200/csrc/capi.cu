@@ -1,0 +1,411 @@
+// extern "C" boundary (include/reface_b200.h).  Exceptions never cross it: every entry point returns an
+// error code and stores the message in the context.
+#include "../../include/reface_b200.h"
+
+#include <cudaTypedefs.h>
+
+#include <cstring>
+
+#include "models.h"
+
+using namespace rfb;
+
+struct rfb_ctx {
+  Ctx c;
+};
+
+#define API_BEGIN(ctx_)                                 \
+  if (!(ctx_)) return -1;                               \
+  Ctx& c = (ctx_)->c;                                   \
+  try {                                                 \
+    CUDA_OK(cudaSetDevice(c.device));
+#define API_END                                         \
+    return 0;                                           \
+  } catch (const std::exception& e) {                   \
+    c.err = e.what();                                   \
+    c.arena_off = 0;                                    \
+    return -2;                                          \
+  }
+
+extern "C" {
+
+int rfb_init(int device, size_t arena_bytes, rfb_ctx** out) {
+  if (!out) return -1;
+  *out = nullptr;
+  rfb_ctx* h = new rfb_ctx();
+  Ctx& c = h->c;
+  try {
+    c.device = device;
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev <= 0)
+      throw std::runtime_error("reface_b200 requires a CUDA device (sm_100a); none is visible -- there is no CPU fallback");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      throw std::runtime_error(std::string("reface_b200 kernels are built for sm_100a only; device is sm_") +
+                               std::to_string(prop.major) + std::to_string(prop.minor));
+    c.num_sms = prop.multiProcessorCount;
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled not available");
+    c.encode_fn = fn;
+    c.arena_cap = arena_bytes ? arena_bytes : (size_t)40 << 30;
+    CUDA_OK(cudaMalloc((void**)&c.arena, c.arena_cap));
+  } catch (const std::exception& e) {
+    // keep the handle alive so that the caller can read the message
+    c.err = e.what();
+    *out = h;
+    return -2;
+  }
+  *out = h;
+  return 0;
+}
+
+void rfb_destroy(rfb_ctx* h) {
+  if (!h) return;
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  cudaDeviceSynchronize();
+  for (auto& kv : c.params) cudaFree(kv.second.f32);
+  for (void* p : c.owned) cudaFree(p);
+  if (c.arena) cudaFree(c.arena);
+  delete c.unet;
+  delete c.vae;
+  delete c.clip;
+  delete c.arc;
+  delete h;
+}
+
+const char* rfb_last_error(rfb_ctx* h) { return h ? h->c.err.c_str() : "null context"; }
+
+int rfb_set_param(rfb_ctx* h, const char* name, const float* data, int ndim, const int64_t* shape) {
+  API_BEGIN(h)
+  Param p;
+  p.numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    p.shape.push_back(shape[i]);
+    p.numel *= (size_t)shape[i];
+  }
+  auto it = c.params.find(name);
+  if (it != c.params.end()) {
+    cudaFree(it->second.f32);
+    c.params.erase(it);
+  }
+  CUDA_OK(cudaMalloc((void**)&p.f32, std::max<size_t>(p.numel * sizeof(float), 256)));
+  CUDA_OK(cudaMemcpy(p.f32, data, p.numel * sizeof(float), cudaMemcpyDefault));
+  c.params[name] = p;
+  API_END
+}
+int rfb_has_param(rfb_ctx* h, const char* name) { return (h && h->c.has(name)) ? 1 : 0; }
+
+int rfb_build_unet(rfb_ctx* h, const char* prefix) {
+  API_BEGIN(h)
+  delete c.unet;
+  c.unet = nullptr;
+  c.unet = build_unet(c, prefix, UNetCfg());
+  API_END
+}
+int rfb_build_vae(rfb_ctx* h, const char* prefix) {
+  API_BEGIN(h)
+  delete c.vae;
+  c.vae = nullptr;
+  c.vae = build_vae(c, prefix);
+  API_END
+}
+int rfb_build_clip(rfb_ctx* h, const char* prefix) {
+  API_BEGIN(h)
+  delete c.clip;
+  c.clip = nullptr;
+  c.clip = build_clip(c, prefix);
+  API_END
+}
+int rfb_build_arcface(rfb_ctx* h, const char* prefix) {
+  API_BEGIN(h)
+  delete c.arc;
+  c.arc = nullptr;
+  c.arc = build_arcface(c, prefix);
+  API_END
+}
+
+int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
+  if (!h) return -1;
+  Ctx& c = h->c;
+  const std::string k = key;
+  if (k == "gemm_bn") c.force_bn = (int)value;
+  else if (k == "gemm_stages") c.force_stages = (int)value;
+  else if (k == "gemm_smem_budget") c.gemm_smem_budget = (int)value;
+  else if (k == "attn_flash") c.attn_flash = (int)value;
+  else return -1;
+  return 0;
+}
+long long rfb_launch_count(rfb_ctx* h) { return h ? h->c.launches : 0; }
+size_t rfb_arena_peak(rfb_ctx* h) { return h ? h->c.arena_peak : 0; }
+
+// ------------------------------------------------------------------------------------------ hot path
+int rfb_unet_forward(rfb_ctx* h, const float* x9, const int64_t* t, const float* context, int N, int L, int T,
+                     float* eps, void* stream) {
+  API_BEGIN(h)
+  RFB_CHECK(c.unet, "rfb_build_unet has not been called");
+  c.stream = (cudaStream_t)stream;
+  unet_forward(c, *c.unet, x9, (const long long*)t, context, N, L, T, eps);
+  API_END
+}
+int rfb_concat9(rfb_ctx* h, const float* x, const float* z, const float* mask, int B, int L, int dup, float* out,
+                void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  concat9(c, x, z, mask, out, B, L * L, dup);
+  API_END
+}
+int rfb_cfg_ddim_update(rfb_ctx* h, const float* x, const float* eps2, const float* noise, long long count, float scale,
+                        float a_t, float a_prev, float sigma, float sqrt_one_minus_at, int has_uncond, float* x_prev,
+                        float* pred_x0, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  cfg_ddim_update(c, x, eps2, noise, x_prev, pred_x0, count, scale, a_t, a_prev, sigma, sqrt_one_minus_at, has_uncond);
+  API_END
+}
+int rfb_ddim_sample(rfb_ctx* h, const float* x_T, const float* z_inpaint, const float* mask, const float* cond,
+                    const float* uncond, int B, int L, int T, const int64_t* timesteps, const float* a_t,
+                    const float* a_prev, const float* sigma, const float* sqrt_one_minus_a, int n_steps, float cfg_scale,
+                    const float* noise, int log_every_t, float* x0_out, float* inter_x, float* inter_pred_x0,
+                    void* stream) {
+  API_BEGIN(h)
+  RFB_CHECK(c.unet, "rfb_build_unet has not been called");
+  c.stream = (cudaStream_t)stream;
+  DdimSchedule s;
+  s.n = n_steps;
+  s.timesteps.assign(timesteps, timesteps + n_steps);
+  s.a_t.assign(a_t, a_t + n_steps);
+  s.a_prev.assign(a_prev, a_prev + n_steps);
+  s.sigma.assign(sigma, sigma + n_steps);
+  s.sqrt_one_minus_a.assign(sqrt_one_minus_a, sqrt_one_minus_a + n_steps);
+  ddim_sample(c, *c.unet, x_T, z_inpaint, mask, cond, uncond, B, L, T, s, cfg_scale, noise, x0_out, inter_x,
+              inter_pred_x0, log_every_t);
+  API_END
+}
+int rfb_vae_encode(rfb_ctx* h, const float* img, const float* noise, int B, int H, int W, float* z, float* mean,
+                   float* logvar, void* stream) {
+  API_BEGIN(h)
+  RFB_CHECK(c.vae, "rfb_build_vae has not been called");
+  c.stream = (cudaStream_t)stream;
+  vae_encode(c, *c.vae, img, noise, B, H, W, z, mean, logvar);
+  API_END
+}
+int rfb_vae_decode(rfb_ctx* h, const float* z, int B, int hh, int ww, float* img, void* stream) {
+  API_BEGIN(h)
+  RFB_CHECK(c.vae, "rfb_build_vae has not been called");
+  c.stream = (cudaStream_t)stream;
+  vae_decode(c, *c.vae, z, B, hh, ww, img);
+  API_END
+}
+int rfb_clip_encode(rfb_ctx* h, const float* img224, int B, float* out768, void* stream) {
+  API_BEGIN(h)
+  RFB_CHECK(c.clip, "rfb_build_clip has not been called");
+  c.stream = (cudaStream_t)stream;
+  clip_embed(c, *c.clip, img224, B, out768);
+  API_END
+}
+int rfb_arcface_embed(rfb_ctx* h, const float* img, int B, float* out512, void* stream) {
+  API_BEGIN(h)
+  RFB_CHECK(c.arc, "rfb_build_arcface has not been called");
+  c.stream = (cudaStream_t)stream;
+  arcface_embed(c, *c.arc, img, B, out512);
+  API_END
+}
+
+// c = (w_clip*(Ps(clip_src)+Pt(clip_tgt)) + w_id*Pid(id) + w_lm*Plm(lm)) / (w_clip+w_id+w_lm)   [ddpm.py:904-915,1010-1039]
+__global__ void fuse_cond_kernel(const float* a, const float* b, const float* id, const float* lm, float* out, int n,
+                                 float wc, float wi, float wl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = ((a[i] + b[i]) * wc + id[i] * wi + lm[i] * wl) / (wc + wi + wl);
+}
+int rfb_condition_fuse(rfb_ctx* h, const float* clip_src, const float* clip_tgt, const float* id_feat,
+                       const float* lm136, int B, float w_clip, float w_id, float w_lm, float* c_out, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  const size_t mk = c.mark();
+  float* t = c.alloc_t<float>((size_t)4 * B * 768);
+  Lin32 ps = lin32(c, "proj_out_source.weight", "proj_out_source.bias");
+  Lin32 pt = lin32(c, "proj_out_target.weight", "proj_out_target.bias");
+  Lin32 pi = lin32(c, "ID_proj_out.weight", "ID_proj_out.bias");
+  Lin32 pl = lin32(c, "landmark_proj_out.weight", "landmark_proj_out.bias");
+  for (int r0 = 0; r0 < B; r0 += 16) {
+    const int R = std::min(16, B - r0);
+    linear_small(c, clip_src + (size_t)r0 * 768, 768, R, ps, t + (size_t)r0 * 768, 768, 0, 0);
+    linear_small(c, clip_tgt + (size_t)r0 * 768, 768, R, pt, t + (size_t)(B + r0) * 768, 768, 0, 0);
+    linear_small(c, id_feat + (size_t)r0 * 512, 512, R, pi, t + (size_t)(2 * B + r0) * 768, 768, 0, 0);
+    linear_small(c, lm136 + (size_t)r0 * 136, 136, R, pl, t + (size_t)(3 * B + r0) * 768, 768, 0, 0);
+  }
+  const int n = B * 768;
+  fuse_cond_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(t, t + n, t + 2 * n, t + 3 * n, c_out, n, w_clip, w_id, w_lm);
+  CUDA_OK(cudaGetLastError());
+  c.launches++;
+  c.release(mk);
+  API_END
+}
+
+// ((tar+1)/2 - mean)/std, then bilinear resize to 224 without antialiasing, align_corners=False [ddpm.py:907-912]
+__global__ void target_clip_input_kernel(const float* __restrict__ tar, float* __restrict__ out, int B, int H, int W) {
+  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+  const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+  const long long total = (long long)B * 3 * 224 * 224;
+  const float sy = (float)H / 224.0f, sx = (float)W / 224.0f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % 224), oy = (int)((i / 224) % 224);
+    const int ch = (int)((i / (224 * 224)) % 3);
+    const long long b = i / (3 * 224 * 224);
+    float fy = fmaxf((oy + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sx - 0.5f, 0.f);
+    const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float* p = tar + (b * 3 + ch) * (long long)H * W;
+    auto nrm = [&](float v) { return ((v + 1.0f) * 0.5f - mean[ch]) / stdv[ch]; };
+    const float v00 = nrm(p[(long long)y0 * W + x0]), v01 = nrm(p[(long long)y0 * W + x1]);
+    const float v10 = nrm(p[(long long)y1 * W + x0]), v11 = nrm(p[(long long)y1 * W + x1]);
+    out[i] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  }
+}
+int rfb_target_clip_input(rfb_ctx* h, const float* tar, int B, int H, int W, float* out224, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  target_clip_input_kernel<<<grid_for((long long)B * 3 * 224 * 224), 256, 0, c.stream>>>(tar, out224, B, H, W);
+  CUDA_OK(cudaGetLastError());
+  c.launches++;
+  API_END
+}
+
+// ------------------------------------------------------------------------------------------ single ops (tests)
+struct TempParams {  // registers temporaries under "__op." and frees everything packed from them on exit
+  Ctx& c;
+  size_t owned0;
+  std::vector<std::string> names;
+  explicit TempParams(Ctx& c_) : c(c_), owned0(c_.owned.size()) {}
+  void add(const std::string& n, const float* dev, std::vector<int64_t> shape) {
+    Param p;
+    p.shape = shape;
+    p.numel = 1;
+    for (auto s : shape) p.numel *= (size_t)s;
+    p.f32 = const_cast<float*>(dev);
+    c.params[n] = p;
+    names.push_back(n);
+  }
+  ~TempParams() {
+    cudaStreamSynchronize(c.stream);
+    for (auto& n : names) c.params.erase(n);
+    for (size_t i = owned0; i < c.owned.size(); ++i) cudaFree(c.owned[i]);
+    c.owned.resize(owned0);
+  }
+};
+
+__global__ void f32_to_f16_kernel(const float* s, __half* d, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = __float2half_rn(s[i]);
+}
+__global__ void f16_to_f32_kernel(const __half* s, float* d, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = __half2float(s[i]);
+}
+
+int rfb_op_linear(rfb_ctx* h, const float* x, const float* w, const float* bias, const float* residual, long long M,
+                  int K, int N, int act, int geglu, float* out, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  const size_t mk = c.mark();
+  {
+    TempParams tp(c);
+    tp.add("__op.w", w, {N, K});
+    if (bias) tp.add("__op.b", bias, {N});
+    const int NO = geglu ? N / 2 : N;
+    Tens xt = c.new_tens(1, 1, (int)M, K);
+    f32_to_f16_kernel<<<grid_for(M * K), 256, 0, c.stream>>>(x, xt.p, M * K);
+    Epi e;
+    e.act = act, e.geglu = geglu;
+    __half* r16 = nullptr;
+    if (residual) {
+      r16 = c.alloc_t<__half>((size_t)M * NO);
+      f32_to_f16_kernel<<<grid_for(M * NO), 256, 0, c.stream>>>(residual, r16, M * NO);
+      e.res = r16, e.ldr = NO;
+    }
+    LinW lw;
+    if (geglu) {
+      RFB_CHECK(bias, "geglu needs a bias");
+      int bn = 256;
+      while (N % bn) bn /= 2;
+      lw = pack_geglu(c, "__op.w", "__op.b", bn);
+    } else {
+      lw = pack_linear(c, "__op.w", bias ? "__op.b" : "");
+    }
+    Tens y = linear_t(c, xt, lw, e);
+    f16_to_f32_kernel<<<grid_for(M * NO), 256, 0, c.stream>>>(y.p, out, M * NO);
+    CUDA_OK(cudaGetLastError());
+  }
+  c.release(mk);
+  API_END
+}
+
+int rfb_op_conv2d(rfb_ctx* h, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int O,
+                  int ksz, int stride, int pad_t, int pad_l, int pad_b, int pad_r, float* out, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  const size_t mk = c.mark();
+  {
+    TempParams tp(c);
+    tp.add("__op.w", w, {O, C, ksz, ksz});
+    if (bias) tp.add("__op.b", bias, {O});
+    ConvW cw = pack_conv(c, "__op.w", bias ? "__op.b" : "");
+    Tens xt = from_nchw_f32(c, x, N, C, H, W, C);
+    Tens y = conv3x3_t(c, xt, cw, Epi(), stride, pad_t, pad_l, pad_b, pad_r);
+    to_nchw_f32(c, y, out);
+  }
+  c.release(mk);
+  API_END
+}
+
+int rfb_op_groupnorm(rfb_ctx* h, const float* x, const float* gamma, const float* beta, int N, int C, int H, int W,
+                     float eps, int silu, float* out, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  const size_t mk = c.mark();
+  Tens xt = from_nchw_f32(c, x, N, C, H, W, C);
+  Tens y = groupnorm(c, xt, gamma, beta, eps, silu != 0);
+  to_nchw_f32(c, y, out);
+  c.release(mk);
+  API_END
+}
+
+int rfb_op_layernorm(rfb_ctx* h, const float* x, const float* gamma, const float* beta, long long rows, int C, float eps,
+                     float* out, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  const size_t mk = c.mark();
+  Tens xt = c.new_tens(1, 1, (int)rows, C);
+  f32_to_f16_kernel<<<grid_for(rows * C), 256, 0, c.stream>>>(x, xt.p, rows * C);
+  Tens y = layernorm(c, xt, gamma, beta, eps);
+  f16_to_f32_kernel<<<grid_for(rows * C), 256, 0, c.stream>>>(y.p, out, rows * C);
+  CUDA_OK(cudaGetLastError());
+  c.release(mk);
+  API_END
+}
+
+int rfb_op_attention(rfb_ctx* h, const float* qkv, int N, int L, int heads, int d, float scale, float* out,
+                     void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  const size_t mk = c.mark();
+  const int C = heads * d;
+  const long long n_in = (long long)N * L * 3 * C, n_out = (long long)N * L * C;
+  __half* q16 = c.alloc_t<__half>(n_in);
+  __half* o16 = c.alloc_t<__half>(n_out);
+  f32_to_f16_kernel<<<grid_for(n_in), 256, 0, c.stream>>>(qkv, q16, n_in);
+  attention(c, q16, 3 * C, N, L, heads, d, o16, C, scale, 0, C, 2 * C);
+  f16_to_f32_kernel<<<grid_for(n_out), 256, 0, c.stream>>>(o16, out, n_out);
+  CUDA_OK(cudaGetLastError());
+  c.release(mk);
+  API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,416 @@
+// HBM-bound helper kernels (layout changes, normalisation, softmax, small GEMV, DDIM update).
+// All activations are NHWC fp16 ([rows = n*h*w, C]); statistics, schedules and latents stay fp32.
+#pragma once
+#include "ptx.cuh"
+
+namespace rfb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------ layout
+// fp32 NCHW -> fp16 NHWC (channels padded with zeros up to Cp)
+__global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int N, int C,
+                                            int HW, int Cp) {
+  const long long total = (long long)N * HW * Cp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const long long p = i / Cp;
+    const int n = (int)(p / HW);
+    const int px = (int)(p % HW);
+    dst[i] = (c < C) ? __float2half_rn(src[((long long)n * C + c) * HW + px]) : __float2half_rn(0.f);
+  }
+}
+// fp16 NHWC -> fp32 NCHW
+__global__ void nhwc_f16_to_nchw_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, int N, int C,
+                                            int HW, int ld) {
+  const long long total = (long long)N * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % HW);
+    const long long t = i / HW;
+    const int c = (int)(t % C);
+    const int n = (int)(t / C);
+    dst[i] = __half2float(src[((long long)n * HW + px) * ld + c]);
+  }
+}
+
+// Generic im2col for the convolutions that do not fit the TMA implicit-GEMM tile (stride 2, asymmetric
+// padding, tiny Cin, non power-of-two maps): dst[m, (ky*KW+kx)*C + c], row stride Kp (zero padded).
+__global__ void im2col_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int H, int W, int C,
+                              int KH, int KW, int stride, int pad_t, int pad_l, int Ho, int Wo, int Kp) {
+  const int taps = KH * KW;
+  const int K = taps * C;
+  const long long M = (long long)N * Ho * Wo;
+  if ((C & 7) == 0) {
+    const int cv = C >> 3;
+    const int kv = Kp >> 3;
+    const long long total = M * kv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int kc = (int)(i % kv);
+      const long long m = i / kv;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (kc * 8 < K) {
+        const int tap = kc / cv, c8 = kc % cv;
+        const int ky = tap / KW, kx = tap % KW;
+        const int ox = (int)(m % Wo);
+        const long long t = m / Wo;
+        const int oy = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        const int iy = oy * stride - pad_t + ky, ix = ox * stride - pad_l + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+          val = *reinterpret_cast<const uint4*>(src + (((long long)n * H + iy) * W + ix) * C + c8 * 8);
+      }
+      *reinterpret_cast<uint4*>(dst + m * Kp + kc * 8) = val;
+    }
+  } else {
+    const long long total = M * Kp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int k = (int)(i % Kp);
+      const long long m = i / Kp;
+      __half val = __float2half_rn(0.f);
+      if (k < K) {
+        const int tap = k / C, c = k % C;
+        const int ky = tap / KW, kx = tap % KW;
+        const int ox = (int)(m % Wo);
+        const long long t = m / Wo;
+        const int oy = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        const int iy = oy * stride - pad_t + ky, ix = ox * stride - pad_l + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = src[(((long long)n * H + iy) * W + ix) * C + c];
+      }
+      dst[i] = val;
+    }
+  }
+}
+
+// nearest 2x upsample, NHWC, C % 8 == 0
+__global__ void upsample2x_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int H, int W, int C) {
+  const int cv = C >> 3;
+  const long long total = (long long)N * (2 * H) * (2 * W) * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    long long p = i / cv;
+    const int ox = (int)(p % (2 * W));
+    p /= (2 * W);
+    const int oy = (int)(p % (2 * H));
+    const int n = (int)(p / (2 * H));
+    reinterpret_cast<uint4*>(dst)[i] =
+        *reinterpret_cast<const uint4*>(src + (((long long)n * H + (oy >> 1)) * W + (ox >> 1)) * C + c8 * 8);
+  }
+}
+
+// channel concat of two NHWC tensors ([rows,Ca] ++ [rows,Cb]); Ca, Cb % 8 == 0
+__global__ void concat_c_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ dst,
+                                long long rows, int Ca, int Cb) {
+  const int cv = (Ca + Cb) >> 3, av = Ca >> 3;
+  const long long total = rows * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const long long r = i / cv;
+    reinterpret_cast<uint4*>(dst)[i] = (c8 < av) ? reinterpret_cast<const uint4*>(a)[r * av + c8]
+                                                 : reinterpret_cast<const uint4*>(b)[r * (cv - av) + (c8 - av)];
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm (fp32 statistics)
+// Phase 1: per-(n, channel) sum / sum of squares over a slab of pixels -> atomics into stats[n][C][2].
+// blockDim = (C/8) * R; thread (pr, cq) owns 8 channels and pixel rows pr, pr+R, ...
+__global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ stats, int HW, int C, int slab) {
+  extern __shared__ float sh[];  // [2*C]
+  const int cv = C >> 3;
+  const int R = blockDim.x / cv;
+  const int cq = threadIdx.x % cv, pr = threadIdx.x / cv;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * slab;
+  const int p1 = min(HW, p0 + slab);
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  if (pr < R) {
+    for (int p = p0 + pr; p < p1; p += R) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + ((long long)n * HW + p) * C + cq * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack_h2(w[t]);
+        s[2 * t] += f.x;
+        ss[2 * t] += f.x * f.x;
+        s[2 * t + 1] += f.y;
+        ss[2 * t + 1] += f.y * f.y;
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  if (pr < R) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[2 * (cq * 8 + j)], s[j]);
+      atomicAdd(&sh[2 * (cq * 8 + j) + 1], ss[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[(long long)n * 2 * C + i], sh[i]);
+}
+// Phase 2: y = (x-mean)*rstd*gamma+beta [* sigmoid]  (one thread per 8 channels of one pixel)
+__global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ y,
+                                int N, int HW, int C, int G, float eps, int silu) {
+  extern __shared__ float sh[];  // per-block cache of mean/rstd for one sample: [2*G]
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  for (int gidx = threadIdx.x; gidx < G; gidx += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int c = gidx * cpg; c < (gidx + 1) * cpg; ++c) {
+      s += stats[((long long)n * C + c) * 2];
+      ss += stats[((long long)n * C + c) * 2 + 1];
+    }
+    const float cnt = (float)cpg * (float)HW;
+    const float mean = s / cnt;
+    const float var = fmaxf(ss / cnt - mean * mean, 0.f);
+    sh[2 * gidx] = mean;
+    sh[2 * gidx + 1] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int cv = C >> 3;
+  const long long total = (long long)HW * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const long long p = i / cv;
+    const long long off = ((long long)n * HW + p) * C + c8 * 8;
+    const uint4 u = *reinterpret_cast<const uint4*>(x + off);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float v[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = unpack_h2(w[t]);
+      v[2 * t] = f.x;
+      v[2 * t + 1] = f.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      const int gi = c / cpg;
+      float t = (v[j] - sh[2 * gi]) * sh[2 * gi + 1] * __ldg(gamma + c) + __ldg(beta + c);
+      if (silu) t = t / (1.0f + __expf(-t));
+      v[j] = t;
+    }
+    uint4 o;
+    o.x = pack_h2(v[0], v[1]);
+    o.y = pack_h2(v[2], v[3]);
+    o.z = pack_h2(v[4], v[5]);
+    o.w = pack_h2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(y + off) = o;
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm: one warp per row, C % 64 == 0, C <= 2048
+__global__ void layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, __half* __restrict__ y, long long rows, int C,
+                                 long long ldx, long long ldy, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int npair = C >> 6;  // half2 per lane
+  float2 v[32];
+  const __half2* xp = reinterpret_cast<const __half2*>(x + row * ldx);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < npair) {
+      v[k] = __half22float2(xp[lane + 32 * k]);
+      s += v[k].x + v[k].y;
+    }
+  const float mean = warp_sum(s) / (float)C;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < npair) {
+      const float a = v[k].x - mean, b = v[k].y - mean;
+      ss += a * a + b * b;
+    }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+  __half2* yp = reinterpret_cast<__half2*>(y + row * ldy);
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < npair) {
+      const int c = 2 * (lane + 32 * k);
+      const float a = (v[k].x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      const float b = (v[k].y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+      yp[lane + 32 * k] = __floats2half2_rn(a, b);
+    }
+}
+
+// ------------------------------------------------------------------ row softmax (materialised attention path)
+// x: [rows, ld] fp16 in place over the first L columns; columns [L, ld) are zeroed (K padding for the P.V GEMM).
+__global__ void softmax_rows_kernel(__half* __restrict__ x, long long rows, int L, int ld) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  __half* p = x + row * ld;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) mx = fmaxf(mx, __half2float(p[i]));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
+  mx = warp_max(mx);
+  mx = __shfl_sync(0xffffffffu, mx, 0);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) s += __expf(__half2float(p[i]) - mx);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  s = warp_sum(s);
+  s = __shfl_sync(0xffffffffu, s, 0);
+  const float inv = 1.0f / s;
+  for (int i = threadIdx.x; i < ld; i += blockDim.x)
+    p[i] = (i < L) ? __float2half_rn(__expf(__half2float(p[i]) - mx) * inv) : __float2half_rn(0.f);
+}
+
+// V section of a fused [N, L, ldq] projection -> Vt [N*heads, d, Lp] (keys contiguous), zero padded to Lp
+__global__ void transpose_v_kernel(const __half* __restrict__ v, __half* __restrict__ vt, int N, int L, int heads, int d,
+                                   long long ldq, int Lp) {
+  __shared__ __half tile[32][33];
+  const int z = blockIdx.z;  // n*heads + h
+  const int n = z / heads, h = z % heads;
+  const int l0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int l = l0 + i, dd = d0 + threadIdx.x;
+    tile[i][threadIdx.x] = (l < L && dd < d) ? v[((long long)n * L + l) * ldq + h * d + dd] : __float2half_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int dd = d0 + i, l = l0 + threadIdx.x;
+    if (dd < d && l < Lp) vt[((long long)z * d + dd) * Lp + l] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------ small-M linear (fp32 in, fp32 weights)
+// out[r, o] = act(bias[o] + sum_k act_in(x[r, k]) * W[o, k]) for r < R <= 16; one warp per output o.
+template <int RMAX>
+__global__ void linear_small_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                    const float* __restrict__ bias, float* __restrict__ out, int R, int K, int O,
+                                    long long ldx, long long ldo, int act_in, int act_out,
+                                    const float* __restrict__ res) {
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= O) return;
+  const int lane = threadIdx.x & 31;
+  float acc[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) acc[r] = 0.f;
+  const float* w = W + (long long)o * K;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = __ldg(w + k);
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r)
+      if (r < R) {
+        float xv = x[r * ldx + k];
+        if (act_in == 1) xv = xv / (1.0f + __expf(-xv));
+        acc[r] += xv * wv;
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) {
+    if (r < R) {
+      float v = warp_sum(acc[r]);
+      if (lane == 0) {
+        if (bias) v += bias[o];
+        if (act_out == 1) v = v / (1.0f + __expf(-v));
+        else if (act_out == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+        else if (act_out == 3) v = fmaxf(v, 0.f);
+        else if (act_out == 4) v = 1.0f / (1.0f + __expf(-v));
+        if (res) v += res[r * ldo + o];
+        out[r * ldo + o] = v;
+      }
+    }
+  }
+}
+
+// timestep_embedding (cos || sin), fp32  [ref: ldm/modules/diffusionmodules/util.py:151-171]
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, float* __restrict__ out, int N, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * half) return;
+  const int n = i / half, j = i % half;
+  const float freq = expf(-logf(10000.0f) * (float)j / (float)half);
+  const float a = (float)t[n] * freq;
+  out[n * dim + j] = cosf(a);
+  out[n * dim + half + j] = sinf(a);
+}
+
+// ------------------------------------------------------------------ DDIM glue (fp32, bit-exact data movement)
+// x9[n] = cat(x[n%B], z[n%B], mask[n%B]) for n < dup*B   [ref: ldm/models/diffusion/ddim.py:330,338]
+__global__ void concat9_kernel(const float* __restrict__ x, const float* __restrict__ z, const float* __restrict__ mask,
+                               float* __restrict__ out, int B, int HW, int dup) {
+  const long long total = (long long)dup * B * 9 * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % HW);
+    const long long t = i / HW;
+    const int c = (int)(t % 9);
+    const int b = (int)((t / 9) % B);
+    float v;
+    if (c < 4) v = x[((long long)b * 4 + c) * HW + px];
+    else if (c < 8) v = z[((long long)b * 4 + (c - 4)) * HW + px];
+    else v = mask[(long long)b * HW + px];
+    out[i] = v;
+  }
+}
+// classifier-free guidance combine + DDIM x_{t-1} (same fp32 op order as ddim.py:346,363-374; no FMA contraction)
+__global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ eps2,
+                                       const float* __restrict__ noise, float* __restrict__ x_prev,
+                                       float* __restrict__ pred_x0, long long count, float scale, float a_t, float a_prev,
+                                       float sigma, float sqrt_one_minus_at, int has_uncond) {
+  const float sqrt_at = __fsqrt_rn(a_t);
+  const float sqrt_aprev = __fsqrt_rn(a_prev);
+  const float dir_coef = __fsqrt_rn(__fsub_rn(__fsub_rn(1.0f, a_prev), __fmul_rn(sigma, sigma)));
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    float e;
+    if (has_uncond) {
+      const float eu = eps2[i], ec = eps2[count + i];
+      e = __fadd_rn(eu, __fmul_rn(scale, __fsub_rn(ec, eu)));
+    } else {
+      e = eps2[i];
+    }
+    const float p0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(sqrt_one_minus_at, e)), sqrt_at);
+    const float dir = __fmul_rn(dir_coef, e);
+    const float nz = noise ? __fmul_rn(sigma, noise[i]) : 0.0f;
+    x_prev[i] = __fadd_rn(__fadd_rn(__fmul_rn(sqrt_aprev, p0), dir), nz);
+    if (pred_x0) pred_x0[i] = p0;
+  }
+}
+
+// fp32 -> fp16 copy with optional row padding: dst[r, 0..Kp) = src[r, 0..K) (zeros beyond K)
+__global__ void pack_rows_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long rows, int K,
+                                     int Kp) {
+  const long long total = rows * Kp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kp);
+    const long long r = i / Kp;
+    dst[i] = (k < K) ? __float2half_rn(src[r * K + k]) : __float2half_rn(0.f);
+  }
+}
+// conv weight [O, I, KH, KW] fp32 -> [O, taps*Ip] fp16 with k = tap*Ip + i (Ip >= I zero padded)
+__global__ void pack_conv_w_kernel(const float* __restrict__ src, __half* __restrict__ dst, int O, int I, int taps,
+                                   int Ip, int Kp, const float* __restrict__ oscale) {
+  const long long total = (long long)O * Kp;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % Kp);
+    const int o = (int)(idx / Kp);
+    const int tap = k / Ip, i = k % Ip;
+    const float sc = oscale ? oscale[o] : 1.0f;
+    dst[idx] = (tap < taps && i < I) ? __float2half_rn(sc * src[((long long)o * I + i) * taps + tap])
+                                     : __float2half_rn(0.f);
+  }
+}
+
+}  // namespace rfb

@@ -1,0 +1,442 @@
+// Host-side engine: context, weight packing, TMA descriptor construction and kernel launchers.
+#include "engine.h"
+
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "elem.cuh"
+#include "gemm_tc.cuh"
+
+namespace rfb {
+
+// ------------------------------------------------------------------------------------------ context
+void* Ctx::alloc(size_t bytes) {
+  size_t off = (arena_off + 255) & ~size_t(255);
+  if (off + bytes > arena_cap)
+    throw std::runtime_error("activation arena exhausted: need " + std::to_string(off + bytes) + " of " +
+                             std::to_string(arena_cap) + " bytes (raise arena_bytes in rfb_init)");
+  arena_off = off + bytes;
+  arena_peak = std::max(arena_peak, arena_off);
+  return arena + off;
+}
+void* Ctx::dmalloc(size_t bytes) {
+  void* p = nullptr;
+  CUDA_OK(cudaMalloc(&p, std::max<size_t>(bytes, 256)));
+  owned.push_back(p);
+  return p;
+}
+const Param& Ctx::param(const std::string& name) const {
+  auto it = params.find(name);
+  if (it == params.end()) throw std::runtime_error("missing parameter: " + name);
+  return it->second;
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+#define LAUNCH_CHECK(c)          \
+  do {                           \
+    CUDA_OK(cudaGetLastError()); \
+    (c).launches++;              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ packing
+ConvW pack_conv(Ctx& c, const std::string& wname, const std::string& bname, const float* oscale) {
+  const Param& p = c.param(wname);
+  RFB_CHECK(p.shape.size() == 4 && p.shape[2] == p.shape[3], "conv weight must be [O,I,k,k]");
+  ConvW w;
+  w.cout = (int)p.shape[0], w.cin = (int)p.shape[1], w.ksz = (int)p.shape[2], w.taps = w.ksz * w.ksz;
+  w.cin_p = w.cin;
+  w.kp = round_up(w.taps * w.cin, 64);
+  const int cout_p = round_up(w.cout, 32);
+  w.w = (__half*)c.dmalloc((size_t)cout_p * w.kp * sizeof(__half));
+  CUDA_OK(cudaMemsetAsync(w.w, 0, (size_t)cout_p * w.kp * sizeof(__half), c.stream));
+  pack_conv_w_kernel<<<grid_for((long long)w.cout * w.kp), 256, 0, c.stream>>>(p.f32, w.w, w.cout, w.cin, w.taps,
+                                                                               w.cin_p, w.kp, oscale);
+  LAUNCH_CHECK(c);
+  w.b = bname.empty() ? nullptr : c.pf(bname);
+  return w;
+}
+
+LinW pack_linear_rows(Ctx& c, const std::vector<std::string>& wnames) {
+  LinW w;
+  int total = 0;
+  for (auto& n : wnames) {
+    const Param& p = c.param(n);
+    RFB_CHECK(p.shape.size() >= 2, "linear weight must be at least 2-D");
+    int in = 1;
+    for (size_t i = 1; i < p.shape.size(); ++i) in *= (int)p.shape[i];
+    RFB_CHECK(w.in == 0 || w.in == in, "fused linear weights must share the input width");
+    w.in = in;
+    total += (int)p.shape[0];
+  }
+  w.out = total;
+  w.kp = round_up(w.in, 64);
+  const int out_p = round_up(w.out, 32);
+  w.w = (__half*)c.dmalloc((size_t)out_p * w.kp * sizeof(__half));
+  CUDA_OK(cudaMemsetAsync(w.w, 0, (size_t)out_p * w.kp * sizeof(__half), c.stream));
+  int row = 0;
+  for (auto& n : wnames) {
+    const Param& p = c.param(n);
+    const int rows = (int)p.shape[0];
+    pack_rows_f16_kernel<<<grid_for((long long)rows * w.kp), 256, 0, c.stream>>>(p.f32, w.w + (size_t)row * w.kp, rows,
+                                                                                 w.in, w.kp);
+    LAUNCH_CHECK(c);
+    row += rows;
+  }
+  return w;
+}
+LinW pack_linear(Ctx& c, const std::string& wname, const std::string& bname) {
+  LinW w = pack_linear_rows(c, {wname});
+  w.b = bname.empty() ? nullptr : c.pf(bname);
+  return w;
+}
+
+// GEGLU projection [2*inner, in]: rows permuted so that every BN-wide output tile holds BN/2 value rows
+// followed by the matching BN/2 gate rows (the epilogue multiplies them in registers).
+__global__ void pack_geglu_kernel(const float* __restrict__ w, const float* __restrict__ b, __half* __restrict__ wo,
+                                  float* __restrict__ bo, int inner, int in, int kp, int BN) {
+  const int hb = BN / 2;
+  const long long total = (long long)2 * inner * kp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kp);
+    const int r = (int)(i / kp);  // packed row
+    const int tile = r / BN, j = r % BN;
+    const int src = (j < hb) ? tile * hb + j : inner + tile * hb + (j - hb);
+    wo[i] = (k < in) ? __float2half_rn(w[(long long)src * in + k]) : __float2half_rn(0.f);
+    if (k == 0) bo[r] = b[src];
+  }
+}
+LinW pack_geglu(Ctx& c, const std::string& wname, const std::string& bname, int BN) {
+  const Param& p = c.param(wname);
+  LinW w;
+  w.out = (int)p.shape[0], w.in = (int)p.shape[1], w.kp = round_up(w.in, 64);
+  const int inner = w.out / 2;
+  RFB_CHECK(w.out % BN == 0 && BN % 64 == 0, "GEGLU tile must divide the projection width");
+  w.w = (__half*)c.dmalloc((size_t)w.out * w.kp * sizeof(__half));
+  float* bo = (float*)c.dmalloc((size_t)w.out * sizeof(float));
+  pack_geglu_kernel<<<grid_for((long long)w.out * w.kp), 256, 0, c.stream>>>(p.f32, c.pf(bname), w.w, bo, inner, w.in,
+                                                                             w.kp, BN);
+  LAUNCH_CHECK(c);
+  w.b = bo;
+  return w;
+}
+Lin32 lin32(Ctx& c, const std::string& wname, const std::string& bname) {
+  const Param& p = c.param(wname);
+  Lin32 w;
+  w.w = p.f32, w.out = (int)p.shape[0], w.in = (int)(p.numel / p.shape[0]);
+  w.b = bname.empty() ? nullptr : c.pf(bname);
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------ TMA descriptors
+static CUtensorMap make_tmap(Ctx& c, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                             const uint32_t* box) {
+  CUtensorMap m;
+  uint32_t estr[5] = {1, 1, 1, 1, 1};
+  RFB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+  for (int i = 0; i + 1 < rank; ++i) RFB_CHECK(strides_b[i] % 16 == 0, "TMA strides must be multiples of 16 bytes");
+  auto fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(c.encode_fn);
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return m;
+}
+
+int pick_bn(Ctx& c, long long M, int N, bool geglu) {
+  if (c.force_bn) return c.force_bn;
+  if (geglu) return (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  if (N <= 32) return 32;
+  static const int cand[] = {256, 224, 192, 160, 128, 96, 64, 32};
+  int best = 32;
+  long long best_cost = -1;
+  for (int bn : cand) {
+    const long long padded = (long long)((N + bn - 1) / bn) * bn;
+    if (best_cost < 0 || padded < best_cost) best_cost = padded, best = bn;
+  }
+  // small problems: prefer more CTAs over the widest tile
+  const long long mt = (M + GEMM_BM - 1) / GEMM_BM;
+  while (best > 64 && mt * ((N + best - 1) / best) < c.num_sms) {
+    int next = 0;
+    for (int bn : cand)
+      if (bn < best && (long long)((N + bn - 1) / bn) * bn <= best_cost + 32) { next = bn; break; }
+    if (!next) break;
+    best = next;
+  }
+  return best;
+}
+
+static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, dim3 grid) {
+  const int stage_bytes = GEMM_A_STAGE_BYTES + g.BN * 128;
+  int stages = c.force_stages ? c.force_stages : std::max(2, std::min(6, c.gemm_smem_budget / stage_bytes));
+  stages = std::min(stages, std::max(1, g.nk));
+  g.stages = stages;
+  g.tmem_cols = g.BN <= 32 ? 32 : g.BN <= 64 ? 64 : g.BN <= 128 ? 128 : 256;
+  const size_t smem = gemm_smem_bytes(stages, g.BN);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  RFB_CHECK(smem <= 227 * 1024, "GEMM smem over budget");
+  RFB_CHECK(g.BN % 32 == 0 && g.BN >= 32 && g.BN <= 256, "BN must be a multiple of 32 in [32,256]");
+  if (g.zdiv <= 0) g.zdiv = 1;
+  if (g.rows_per_vec <= 0) g.rows_per_vec = 1;
+  if (g.o32_rpn <= 0) g.o32_rpn = 1;
+  if (g.heads <= 0) g.heads = 1;
+  gemm_tc_kernel<<<grid, GEMM_THREADS, smem, c.stream>>>(tmA, tmB, g);
+  LAUNCH_CHECK(c);
+}
+
+static void fill_epi(GemmArgs& g, const Epi& e, __half* out, long long ldo) {
+  g.alpha = e.alpha, g.bias = e.bias, g.rowvec = e.rowvec, g.rows_per_vec = e.rows_per_vec, g.ldv = e.ldv;
+  g.act_param = e.act_param, g.act = e.act, g.geglu = e.geglu, g.res = e.res, g.ldr = e.ldr;
+  g.out = out, g.ldo = ldo, g.out32 = e.out32, g.o32_sn = e.o32_sn, g.o32_sp = e.o32_sp, g.o32_sc = e.o32_sc;
+  g.o32_rpn = e.o32_rpn;
+}
+
+void gemm(Ctx& c, const __half* A, long long lda, long long M, int K, const __half* W, int kp, int N, __half* out,
+          long long ldo, const Epi& e, int force_bn) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = (int)M, g.N = N, g.nk = (K + 63) / 64;
+  g.BN = force_bn ? force_bn : pick_bn(c, M, N, e.geglu != 0);
+  g.a_mode = A_PLAIN, g.b_mode = B_PLAIN;
+  fill_epi(g, e, out, ldo);
+  const uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
+  const uint64_t sa[1] = {(uint64_t)lda * 2};
+  const uint32_t ba[2] = {64, 128};
+  const int nrows_w = round_up(N, 32);
+  const uint64_t db[2] = {(uint64_t)kp, (uint64_t)nrows_w};
+  const uint64_t sb[1] = {(uint64_t)kp * 2};
+  const uint32_t bb[2] = {64, (uint32_t)g.BN};
+  CUtensorMap tmA = make_tmap(c, A, 2, da, sa, ba);
+  CUtensorMap tmB = make_tmap(c, W, 2, db, sb, bb);
+  dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + g.BN - 1) / g.BN), 1);
+  launch_gemm(c, tmA, tmB, g, grid);
+}
+
+Tens linear_t(Ctx& c, const Tens& x, const LinW& w, Epi e) {
+  RFB_CHECK(x.c == w.in, "linear: input width mismatch");
+  const int out_c = e.geglu ? w.out / 2 : w.out;
+  Tens y = c.new_tens(x.n, x.h, x.w, out_c);
+  if (!e.bias) e.bias = w.b;
+  gemm(c, x.p, x.c, x.rows(), x.c, w.w, w.kp, w.out, y.p, out_c, e);
+  return y;
+}
+
+static bool conv_tma_ok(const Tens& x, const ConvW& w, int stride, int pt, int pl, int pb, int pr) {
+  if (w.ksz != 3 || stride != 1 || pt != 1 || pl != 1 || pb != 1 || pr != 1) return false;
+  if (w.cin % 64 != 0) return false;
+  const int W = x.w, H = x.h;
+  if (W >= 128) return W % 128 == 0;
+  if (128 % W != 0) return false;
+  const int rows = 128 / W;  // image rows per tile
+  if (H >= rows) return H % rows == 0;
+  return rows % H == 0;
+}
+
+Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad_t, int pad_l, int pad_b, int pad_r) {
+  RFB_CHECK(x.c == w.cin, "conv: channel mismatch");
+  const int Ho = (x.h + pad_t + pad_b - w.ksz) / stride + 1;
+  const int Wo = (x.w + pad_l + pad_r - w.ksz) / stride + 1;
+  Tens y;
+  y.n = x.n, y.h = Ho, y.w = Wo, y.c = w.cout;
+  const bool f16_out = (e.out32 == nullptr);
+  if (f16_out) y.p = c.alloc_t<__half>((size_t)y.rows() * y.c);
+  if (!e.bias) e.bias = w.b;
+  if (e.rowvec && e.rows_per_vec <= 1) e.rows_per_vec = Ho * Wo;
+  const long long M = y.rows();
+  if (w.ksz == 1 && stride == 1) {
+    gemm(c, x.p, x.c, M, x.c, w.w, w.kp, w.cout, y.p, y.c, e);
+    return y;
+  }
+  if (conv_tma_ok(x, w, stride, pad_t, pad_l, pad_b, pad_r)) {
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = (int)M, g.N = w.cout, g.cblocks = w.cin / 64, g.nk = 9 * g.cblocks;
+    g.BN = pick_bn(c, M, w.cout, false);
+    g.a_mode = A_CONV3, g.b_mode = B_PLAIN;
+    g.bw = std::min(x.w, 128);
+    g.bh = std::min(x.h, 128 / g.bw);
+    g.bimg = 128 / (g.bw * g.bh);
+    g.tiles_w = x.w / g.bw, g.tiles_h = x.h / g.bh;
+    fill_epi(g, e, y.p, y.c);
+    const uint64_t da[4] = {(uint64_t)x.c, (uint64_t)x.w, (uint64_t)x.h, (uint64_t)x.n};
+    const uint64_t sa[3] = {(uint64_t)x.c * 2, (uint64_t)x.w * x.c * 2, (uint64_t)x.h * x.w * x.c * 2};
+    const uint32_t ba[4] = {64, (uint32_t)g.bw, (uint32_t)g.bh, (uint32_t)g.bimg};
+    const uint64_t db[2] = {(uint64_t)w.kp, (uint64_t)round_up(w.cout, 32)};
+    const uint64_t sb[1] = {(uint64_t)w.kp * 2};
+    const uint32_t bb[2] = {64, (uint32_t)g.BN};
+    CUtensorMap tmA = make_tmap(c, x.p, 4, da, sa, ba);
+    CUtensorMap tmB = make_tmap(c, w.w, 2, db, sb, bb);
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)((w.cout + g.BN - 1) / g.BN), 1);
+    launch_gemm(c, tmA, tmB, g, grid);
+    return y;
+  }
+  // generic path: explicit im2col then a plain GEMM
+  const size_t mk = c.mark();
+  __half* col = nullptr;
+  {
+    // allocate after the output so that releasing the mark keeps y alive
+    col = c.alloc_t<__half>((size_t)M * w.kp);
+  }
+  im2col_kernel<<<grid_for(M * (w.kp / 8)), 256, 0, c.stream>>>(x.p, col, x.n, x.h, x.w, x.c, w.ksz, w.ksz, stride, pad_t,
+                                                              pad_l, Ho, Wo, w.kp);
+  LAUNCH_CHECK(c);
+  gemm(c, col, w.kp, M, w.kp, w.w, w.kp, w.cout, y.p, y.c, e);
+  c.release(mk);
+  return y;
+}
+
+// ------------------------------------------------------------------------------------------ attention (materialised)
+// qkv: fused projection rows [N*L, ldq]; q/k/v start at column offsets q_off/k_off/v_off, head h at +h*d.
+// S = scale * Q K^T (fp16, [N*heads, L, Lp]) -> row softmax -> O = P V written to out[N*L, ldo] at column h*d.
+// [ref: ldm/modules/attention.py:204-220]
+void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads, int d, __half* out, long long ldo,
+               float scale, int q_off, int k_off, int v_off) {
+  const size_t mk = c.mark();
+  const int Z = N * heads;
+  const int Lp = round_up(L, 8);
+  __half* S = c.alloc_t<__half>((size_t)Z * L * Lp);
+  __half* Vt = c.alloc_t<__half>((size_t)Z * d * Lp);
+  {
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = L, g.N = L, g.nk = (d + 63) / 64;
+    g.BN = pick_bn(c, (long long)L * Z, L, false);
+    g.a_mode = A_HEADS4, g.b_mode = B_HEADS4, g.heads = heads;
+    Epi e;
+    e.alpha = scale;
+    fill_epi(g, e, S, Lp);
+    g.zdiv = 1, g.zs_outer = (long long)L * Lp, g.zs_inner = 0;
+    const uint64_t dq[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)L, (uint64_t)N};
+    const uint64_t sq[3] = {(uint64_t)d * 2, (uint64_t)ldq * 2, (uint64_t)L * ldq * 2};
+    const uint32_t bq[4] = {64, 1, 128, 1};
+    const uint32_t bk[4] = {64, 1, (uint32_t)g.BN, 1};
+    CUtensorMap tmA = make_tmap(c, qkv + q_off, 4, dq, sq, bq);
+    CUtensorMap tmB = make_tmap(c, qkv + k_off, 4, dq, sq, bk);
+    dim3 grid((unsigned)((L + 127) / 128), (unsigned)((L + g.BN - 1) / g.BN), (unsigned)Z);
+    launch_gemm(c, tmA, tmB, g, grid);
+  }
+  softmax_rows_kernel<<<(unsigned)((long long)Z * L), L >= 1024 ? 256 : 128, 0, c.stream>>>(S, (long long)Z * L, L, Lp);
+  LAUNCH_CHECK(c);
+  {
+    dim3 grid((unsigned)((Lp + 31) / 32), (unsigned)((d + 31) / 32), (unsigned)Z), block(32, 8);
+    transpose_v_kernel<<<grid, block, 0, c.stream>>>(qkv + v_off, Vt, N, L, heads, d, ldq, Lp);
+    LAUNCH_CHECK(c);
+  }
+  {
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = L, g.N = d, g.nk = (Lp + 63) / 64;
+    g.BN = std::min(256, round_up(d, 32));
+    g.a_mode = A_BATCH3, g.b_mode = B_BATCH3;
+    Epi e;
+    fill_epi(g, e, out, ldo);
+    g.zdiv = heads, g.zs_outer = (long long)L * ldo, g.zs_inner = d;
+    const uint64_t dp[3] = {(uint64_t)Lp, (uint64_t)L, (uint64_t)Z};
+    const uint64_t sp[2] = {(uint64_t)Lp * 2, (uint64_t)L * Lp * 2};
+    const uint32_t bp[3] = {64, 128, 1};
+    const uint64_t dv[3] = {(uint64_t)Lp, (uint64_t)d, (uint64_t)Z};
+    const uint64_t sv[2] = {(uint64_t)Lp * 2, (uint64_t)d * Lp * 2};
+    const uint32_t bv[3] = {64, (uint32_t)g.BN, 1};
+    CUtensorMap tmA = make_tmap(c, S, 3, dp, sp, bp);
+    CUtensorMap tmB = make_tmap(c, Vt, 3, dv, sv, bv);
+    dim3 grid((unsigned)((L + 127) / 128), (unsigned)((d + g.BN - 1) / g.BN), (unsigned)Z);
+    launch_gemm(c, tmA, tmB, g, grid);
+  }
+  c.release(mk);
+}
+
+// ------------------------------------------------------------------------------------------ normalisation etc.
+Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps, bool silu) {
+  RFB_CHECK(x.c % 32 == 0 && x.c % 8 == 0, "GroupNorm(32) needs C % 32 == 0");
+  Tens y = c.new_tens(x.n, x.h, x.w, x.c);
+  const size_t mk = c.mark();
+  const int HW = x.h * x.w, C = x.c, cv = C / 8;
+  RFB_CHECK(cv <= 1024, "GroupNorm: too many channels");
+  float* stats = c.alloc_t<float>((size_t)x.n * C * 2);
+  CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)x.n * C * 2 * sizeof(float), c.stream));
+  const int R = std::max(1, 512 / cv);
+  const int want_blocks = std::max(1, (4 * c.num_sms) / std::max(1, x.n));
+  int slab = std::max(R, (HW + want_blocks - 1) / want_blocks);
+  dim3 g1((unsigned)((HW + slab - 1) / slab), (unsigned)x.n);
+  gn_stats_kernel<<<g1, cv * R, 2 * C * sizeof(float), c.stream>>>(x.p, stats, HW, C, slab);
+  LAUNCH_CHECK(c);
+  dim3 g2((unsigned)grid_for((long long)HW * cv, 256, 148 * 8), (unsigned)x.n);
+  gn_apply_kernel<<<g2, 256, 2 * 32 * sizeof(float), c.stream>>>(x.p, stats, gamma, beta, y.p, x.n, HW, C, 32, eps,
+                                                               silu ? 1 : 0);
+  LAUNCH_CHECK(c);
+  c.release(mk);
+  return y;
+}
+
+Tens layernorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps) {
+  RFB_CHECK(x.c % 64 == 0 && x.c <= 2048, "LayerNorm: C must be a multiple of 64, <= 2048");
+  Tens y = c.new_tens(x.n, x.h, x.w, x.c);
+  const long long rows = x.rows();
+  layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, c.stream>>>(x.p, gamma, beta, y.p, rows, x.c, x.c, x.c, eps);
+  LAUNCH_CHECK(c);
+  return y;
+}
+
+Tens upsample2x(Ctx& c, const Tens& x) {
+  Tens y = c.new_tens(x.n, x.h * 2, x.w * 2, x.c);
+  upsample2x_kernel<<<grid_for(y.rows() * (x.c / 8)), 256, 0, c.stream>>>(x.p, y.p, x.n, x.h, x.w, x.c);
+  LAUNCH_CHECK(c);
+  return y;
+}
+Tens concat_c(Ctx& c, const Tens& a, const Tens& b) {
+  RFB_CHECK(a.rows() == b.rows() && a.c % 8 == 0 && b.c % 8 == 0, "concat: shape mismatch");
+  Tens y = c.new_tens(a.n, a.h, a.w, a.c + b.c);
+  concat_c_kernel<<<grid_for(y.rows() * (y.c / 8)), 256, 0, c.stream>>>(a.p, b.p, y.p, a.rows(), a.c, b.c);
+  LAUNCH_CHECK(c);
+  return y;
+}
+Tens from_nchw_f32(Ctx& c, const float* src, int N, int C, int H, int W, int Cp) {
+  Tens y = c.new_tens(N, H, W, Cp);
+  nchw_f32_to_nhwc_f16_kernel<<<grid_for(y.rows() * Cp), 256, 0, c.stream>>>(src, y.p, N, C, H * W, Cp);
+  LAUNCH_CHECK(c);
+  return y;
+}
+void to_nchw_f32(Ctx& c, const Tens& x, float* dst) {
+  nhwc_f16_to_nchw_f32_kernel<<<grid_for(x.rows() * x.c), 256, 0, c.stream>>>(x.p, dst, x.n, x.c, x.h * x.w, x.c);
+  LAUNCH_CHECK(c);
+}
+void linear_small(Ctx& c, const float* x, long long ldx, int R, const Lin32& w, float* out, long long ldo, int act_in,
+                  int act_out, const float* res) {
+  dim3 grid((unsigned)((w.out + 7) / 8));
+  for (int r0 = 0; r0 < R; r0 += 16) {
+    const int r = std::min(16, R - r0);
+    const float* xs = x + (long long)r0 * ldx;
+    float* os = out + (long long)r0 * ldo;
+    const float* rs = res ? res + (long long)r0 * ldo : nullptr;
+    if (r <= 2)
+      linear_small_kernel<2><<<grid, 256, 0, c.stream>>>(xs, w.w, w.b, os, r, w.in, w.out, ldx, ldo, act_in, act_out, rs);
+    else if (r <= 4)
+      linear_small_kernel<4><<<grid, 256, 0, c.stream>>>(xs, w.w, w.b, os, r, w.in, w.out, ldx, ldo, act_in, act_out, rs);
+    else
+      linear_small_kernel<16><<<grid, 256, 0, c.stream>>>(xs, w.w, w.b, os, r, w.in, w.out, ldx, ldo, act_in, act_out, rs);
+    LAUNCH_CHECK(c);
+  }
+}
+void timestep_embedding(Ctx& c, const long long* t, float* out, int N, int dim) {
+  timestep_embedding_kernel<<<(N * dim / 2 + 127) / 128, 128, 0, c.stream>>>(t, out, N, dim);
+  LAUNCH_CHECK(c);
+}
+void concat9(Ctx& c, const float* x, const float* z, const float* mask, float* out, int B, int HW, int dup) {
+  concat9_kernel<<<grid_for((long long)dup * B * 9 * HW), 256, 0, c.stream>>>(x, z, mask, out, B, HW, dup);
+  LAUNCH_CHECK(c);
+}
+void cfg_ddim_update(Ctx& c, const float* x, const float* eps2, const float* noise, float* x_prev, float* pred_x0,
+                     long long count, float scale, float a_t, float a_prev, float sigma, float sqrt_one_minus_at,
+                     int has_uncond) {
+  cfg_ddim_update_kernel<<<grid_for(count), 256, 0, c.stream>>>(x, eps2, noise, x_prev, pred_x0, count, scale, a_t,
+                                                                a_prev, sigma, sqrt_one_minus_at, has_uncond);
+  LAUNCH_CHECK(c);
+}
+
+}  // namespace rfb

@@ -1,0 +1,152 @@
+// Host-side engine: context (weights, activation arena, stream), op launchers over the CUDA kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace rfb {
+
+struct Param {
+  float* f32 = nullptr;  // device copy, fp32, original layout
+  std::vector<int64_t> shape;
+  size_t numel = 0;
+};
+
+struct Tens {  // NHWC fp16 activation
+  __half* p = nullptr;
+  int n = 0, h = 0, w = 0, c = 0;
+  long long rows() const { return (long long)n * h * w; }
+};
+
+struct ConvW {  // packed [cout_p, kp] fp16, k = tap*cin_p + c
+  __half* w = nullptr;
+  const float* b = nullptr;
+  int cin = 0, cout = 0, cin_p = 0, taps = 0, kp = 0, ksz = 0;
+};
+struct LinW {  // packed [out_p, kp] fp16
+  __half* w = nullptr;
+  const float* b = nullptr;
+  int in = 0, out = 0, kp = 0;
+};
+struct Lin32 {  // small-M path keeps fp32 weights
+  const float* w = nullptr;
+  const float* b = nullptr;
+  int in = 0, out = 0;
+};
+
+struct Epi {
+  const float* bias = nullptr;
+  const float* rowvec = nullptr;
+  int rows_per_vec = 1, ldv = 0;
+  int act = 0;
+  const float* act_param = nullptr;
+  int geglu = 0;
+  const __half* res = nullptr;
+  long long ldr = 0;
+  float alpha = 1.0f;
+  float* out32 = nullptr;
+  long long o32_sn = 0, o32_sp = 0, o32_sc = 0;
+  int o32_rpn = 1;
+};
+
+struct Ctx;
+struct UNet;
+struct VAE;
+struct ClipVision;
+struct ArcFace;
+
+struct Ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  std::unordered_map<std::string, Param> params;
+  std::vector<void*> owned;  // packed weights etc. (cudaMalloc'd)
+  char* arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0, arena_peak = 0;
+  std::string err;
+  void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
+  long long launches = 0;     // kernels launched by this library (reported by bench)
+  int gemm_smem_budget = 110 * 1024;  // per-CTA smem target (2 CTAs/SM)
+  int force_bn = 0, force_stages = 0, attn_flash = 1;
+  UNet* unet = nullptr;
+  VAE* vae = nullptr;
+  ClipVision* clip = nullptr;
+  ArcFace* arc = nullptr;
+
+  void* alloc(size_t bytes);  // arena bump allocation (256 B aligned)
+  size_t mark() const { return arena_off; }
+  void release(size_t m) { arena_off = m; }
+  template <class T>
+  T* alloc_t(size_t n) { return reinterpret_cast<T*>(alloc(n * sizeof(T))); }
+  Tens new_tens(int n, int h, int w, int c) {
+    Tens t;
+    t.n = n, t.h = h, t.w = w, t.c = c;
+    t.p = alloc_t<__half>((size_t)t.rows() * c);
+    return t;
+  }
+  void* dmalloc(size_t bytes);  // persistent device allocation (weights)
+  const Param& param(const std::string& name) const;
+  const float* pf(const std::string& name) const { return param(name).f32; }
+  bool has(const std::string& name) const { return params.count(name) != 0; }
+};
+
+#define RFB_CHECK(cond, msg)                                                                  \
+  do {                                                                                        \
+    if (!(cond)) throw std::runtime_error(std::string(msg) + " [" #cond "] at " __FILE__ ":" + \
+                                          std::to_string(__LINE__));                          \
+  } while (0)
+#define CUDA_OK(expr)                                                                                     \
+  do {                                                                                                    \
+    cudaError_t e_ = (expr);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " in " #expr " at " \
+                               __FILE__ ":" + std::to_string(__LINE__));                                  \
+  } while (0)
+
+// ---- weight packing (device side, at build time)
+// [O,I,KH,KW] -> implicit-GEMM layout; oscale (device, [O]) optionally folds a per-output-channel scale (BatchNorm)
+ConvW pack_conv(Ctx& c, const std::string& wname, const std::string& bname, const float* oscale = nullptr);
+LinW pack_linear(Ctx& c, const std::string& wname, const std::string& bname);
+LinW pack_linear_rows(Ctx& c, const std::vector<std::string>& wnames);  // concatenated along out (fused QKV)
+LinW pack_geglu(Ctx& c, const std::string& wname, const std::string& bname, int BN);
+Lin32 lin32(Ctx& c, const std::string& wname, const std::string& bname);
+int pick_bn(Ctx& c, long long M, int N, bool geglu);
+
+// ---- op launchers (all asynchronous on c.stream)
+void gemm(Ctx& c, const __half* A, long long lda, long long M, int K, const __half* W, int kp, int N, __half* out,
+          long long ldo, const Epi& e, int force_bn = 0);
+void conv3x3(Ctx& c, const Tens& x, const ConvW& w, __half* out, long long ldo, Epi e, int stride = 1, int pad_t = 1,
+             int pad_l = 1, int Ho = -1, int Wo = -1);
+Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride = 1, int pad_t = 1, int pad_l = 1,
+               int pad_b = 1, int pad_r = 1);
+Tens linear_t(Ctx& c, const Tens& x, const LinW& w, Epi e);
+void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads, int d, __half* out, long long ldo,
+               float scale, int q_off, int k_off, int v_off);
+Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps, bool silu);
+Tens layernorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps);
+Tens upsample2x(Ctx& c, const Tens& x);
+Tens concat_c(Ctx& c, const Tens& a, const Tens& b);
+Tens from_nchw_f32(Ctx& c, const float* src, int N, int C, int H, int W, int Cp);
+void to_nchw_f32(Ctx& c, const Tens& x, float* dst);
+// out[r,:] = act_out(W act_in(x[r,:]) + b) (+ res[r,:]); any R (chunked by 16 rows internally)
+void linear_small(Ctx& c, const float* x, long long ldx, int R, const Lin32& w, float* out, long long ldo, int act_in,
+                  int act_out, const float* res = nullptr);
+void timestep_embedding(Ctx& c, const long long* t, float* out, int N, int dim);
+void concat9(Ctx& c, const float* x, const float* z, const float* mask, float* out, int B, int HW, int dup);
+void cfg_ddim_update(Ctx& c, const float* x, const float* eps2, const float* noise, float* x_prev, float* pred_x0,
+                     long long count, float scale, float a_t, float a_prev, float sigma, float sqrt_one_minus_at,
+                     int has_uncond);
+
+inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g < 1) g = 1;
+  return (int)(g > cap ? cap : g);
+}
+
+}  // namespace rfb

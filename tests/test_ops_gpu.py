@@ -1,0 +1,125 @@
+"""GPU: every hand-written kernel against a plain PyTorch fp32 reference of the same op.
+Inputs are rounded to fp16 first (the kernels' storage type) so the tolerance only has to cover
+fp32-accumulated fp16 products and the fp16 rounding of the result."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def h(x):
+    return x.half().float()
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+
+
+def g(seed=0):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+def rn(*s, seed=0):
+    return torch.randn(*s, generator=g(seed), device="cuda")
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 32), (256, 320, 320), (1000, 768, 1280), (65, 1280, 640), (4096, 320, 960),
+                                   (8, 136, 768), (300, 2560, 1280)])
+def test_linear_tcgen05(engine, M, K, N):
+    x, w, b = h(rn(M, K, seed=1)), h(rn(N, K, seed=2) / math.sqrt(K)), rn(N, seed=3)
+    y = engine.op_linear(x, w, b)
+    ref = F.linear(x, w, b)
+    assert rel(y, ref) < 4e-3, rel(y, ref)
+
+
+@pytest.mark.parametrize("act,fn", [(1, F.silu), (2, F.gelu), (3, lambda v: v * torch.sigmoid(1.702 * v))])
+def test_linear_epilogues(engine, act, fn):
+    M, K, N = 512, 640, 640
+    x, w, b, r = h(rn(M, K, seed=1)), h(rn(N, K, seed=2) / math.sqrt(K)), rn(N, seed=3), h(rn(M, N, seed=4))
+    y = engine.op_linear(x, w, b, residual=r, act=act)
+    ref = fn(F.linear(x, w, b)) + r
+    assert rel(y, ref) < 4e-3, rel(y, ref)
+
+
+@pytest.mark.parametrize("C", [320, 640, 1280])
+def test_geglu(engine, C):
+    M = 384
+    x, w, b = h(rn(M, C, seed=1)), h(rn(8 * C, C, seed=2) / math.sqrt(C)), rn(8 * C, seed=3)
+    y = engine.op_linear(x, w, b, geglu=True)
+    a, gate = F.linear(x, w, b).chunk(2, dim=-1)
+    ref = a * F.gelu(gate)
+    assert rel(y, ref) < 4e-3, rel(y, ref)
+
+
+@pytest.mark.parametrize("N,C,H,O", [(2, 64, 8, 64), (2, 320, 64, 320), (1, 640, 32, 1280), (3, 128, 16, 96),
+                                     (2, 1280, 8, 1280), (1, 128, 128, 128), (1, 64, 256, 64), (4, 64, 4, 64), (2, 64, 2, 32)])
+def test_conv3x3_implicit_gemm_tma(engine, N, C, H, O):
+    x, w, b = h(rn(N, C, H, H, seed=1)), h(rn(O, C, 3, 3, seed=2) / math.sqrt(9 * C)), rn(O, seed=3)
+    y = engine.op_conv2d(x, w, b)
+    ref = F.conv2d(x, w, b, padding=1)
+    assert rel(y, ref) < 4e-3, rel(y, ref)
+
+
+@pytest.mark.parametrize("N,C,H,O,k,s,pad", [(2, 9, 16, 320, 3, 1, (1, 1, 1, 1)), (2, 320, 16, 320, 3, 2, (1, 1, 1, 1)),
+                                             (1, 128, 32, 128, 3, 2, (0, 0, 1, 1)), (2, 3, 28, 64, 3, 1, (1, 1, 1, 1)),
+                                             (2, 64, 14, 128, 1, 2, (0, 0, 0, 0)), (1, 3, 56, 128, 14, 14, (0, 0, 0, 0)),
+                                             (2, 64, 28, 64, 3, 1, (1, 1, 1, 1)), (2, 4, 8, 512, 3, 1, (1, 1, 1, 1)),
+                                             (2, 960, 8, 320, 1, 1, (0, 0, 0, 0))])
+def test_conv_generic_im2col(engine, N, C, H, O, k, s, pad):
+    x, w, b = h(rn(N, C, H, H, seed=1)), h(rn(O, C, k, k, seed=2) / math.sqrt(k * k * C)), rn(O, seed=3)
+    y = engine.op_conv2d(x, w, b, stride=s, pad=pad)
+    pt, pl, pb, pr = pad
+    ref = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, b, stride=s)
+    assert y.shape == ref.shape
+    assert rel(y, ref) < 4e-3, rel(y, ref)
+
+
+@pytest.mark.parametrize("N,C,H,eps,silu", [(2, 320, 16, 1e-5, True), (2, 960, 8, 1e-5, True), (1, 128, 64, 1e-6, True),
+                                            (3, 1280, 4, 1e-6, False), (2, 2560, 8, 1e-5, True)])
+def test_groupnorm(engine, N, C, H, eps, silu):
+    x = h(rn(N, C, H, H, seed=1) * 2 + 0.5)
+    gam, bet = 1 + 0.1 * rn(C, seed=2), 0.1 * rn(C, seed=3)
+    y = engine.op_groupnorm(x, gam, bet, eps, silu)
+    ref = F.group_norm(x, 32, gam, bet, eps)
+    ref = F.silu(ref) if silu else ref
+    assert float((y - ref).abs().max()) < 6e-3
+
+
+@pytest.mark.parametrize("rows,C", [(100, 320), (4096, 640), (17, 1280), (257, 1024), (5, 768)])
+def test_layernorm(engine, rows, C):
+    x = h(rn(rows, C, seed=1) * 3 + 1)
+    gam, bet = 1 + 0.1 * rn(C, seed=2), 0.1 * rn(C, seed=3)
+    y = engine.op_layernorm(x, gam, bet)
+    assert float((y - F.layer_norm(x, (C,), gam, bet)).abs().max()) < 6e-3
+
+
+@pytest.mark.parametrize("N,L,heads,d", [(2, 256, 8, 40), (1, 1024, 8, 80), (2, 64, 8, 160), (1, 257, 16, 64),
+                                         (1, 256, 1, 512), (2, 16, 8, 40), (1, 4096, 8, 40)])
+def test_attention(engine, N, L, heads, d):
+    C = heads * d
+    qkv = h(rn(N, L, 3 * C, seed=1))
+    y = engine.op_attention(qkv, heads)
+    q, k, v = qkv.chunk(3, dim=-1)
+    sp = lambda t: t.reshape(N, L, heads, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(N, L, C)
+    assert float((y - ref).abs().max()) < 8e-3, float((y - ref).abs().max())
+
+
+def test_concat9_bit_exact_and_ddim_update(engine, oracle):
+    gen = torch.Generator().manual_seed(7)
+    B, L = 3, 16
+    x, z = torch.randn(B, 4, L, L, generator=gen), torch.randn(B, 4, L, L, generator=gen)
+    m = torch.rand(B, 1, L, L, generator=gen)
+    out = engine.concat9(x, z, m, dup=2).cpu()
+    ref = torch.cat([torch.cat([x, z, m], 1)] * 2)
+    assert torch.equal(out, ref)                      # pure data movement: bit exact
+    eps2 = torch.randn(2 * B, 4, L, L, generator=gen)
+    sch = oracle.ddim_schedule(50)
+    for idx in (49, 20, 0):
+        a = [sch[k][idx] for k in ("a_t", "a_prev", "sigma", "sqrt_one_minus_a")]
+        xp, p0 = engine.cfg_ddim_update(x, eps2, 3.5, *a)
+        rxp, rp0, _ = oracle.cfg_ddim_update(x, eps2[:B], eps2[B:], 3.5, *a)
+        assert torch.equal(xp.cpu(), rxp) and torch.equal(p0.cpu(), rp0)   # same fp32 op order: bit exact

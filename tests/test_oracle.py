@@ -1,0 +1,73 @@
+"""CPU: the oracle (oracle/reface_oracle.py) reproduces the golden vectors generated from the REAL
+reference modules by tests/golden/make_golden.py, plus the closed-form constants of SURVEY 8(c)."""
+import os
+
+import numpy as np
+import torch
+
+from conftest import GOLDEN
+
+torch.set_grad_enabled(False)
+
+
+def _g(name):
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, name + ".npz")).items()}
+
+
+def test_closed_form_constants(oracle):
+    ac = oracle.alphas_cumprod_f32()
+    assert abs(float(ac[0]) - 0.99915) < 1e-6 and abs(float(ac[999]) - 0.0046600985) < 1e-9
+    assert list(oracle.make_ddim_timesteps(50)[:3]) == [1, 21, 41] and oracle.make_ddim_timesteps(50)[-1] == 981
+    assert len(oracle.make_ddim_timesteps(30)) == 31 and list(oracle.make_ddim_timesteps(5)) == [1, 201, 401, 601, 801]
+    te = oracle.timestep_embedding(torch.tensor([981]), 320)
+    assert abs(float(te[0, 0]) - 0.67995721) < 1e-6 and abs(float(te[0, 160]) - 0.73325181) < 1e-6
+    g = _g("schedule")
+    assert torch.equal(g["alphas_cumprod"], ac)
+    assert torch.equal(g["temb"], oracle.timestep_embedding(g["temb_t"], 320))
+
+
+def test_unet_matches_reference_golden(oracle, unet_sd):
+    g = _g("unet_L16")
+    taps = {}
+    eps = oracle.unet_forward(oracle.Params(unet_sd, oracle.PFX_UNET), g["x"], g["t"], g["ctx"], taps=taps)
+    assert (eps - g["eps"]).abs().max() < 1e-4
+    assert abs(float(taps["middle_block"].std()) - float(g["tapstd_middle_block"])) < 1e-4
+    assert float(eps.abs().max()) > 0.1      # zero_module'd layers are re-randomised: the net is not vacuous
+
+
+def test_ddim_matches_reference_sampler(oracle, unet_sd):
+    g = _g("ddim_S5_L16")
+    x0, inter = oracle.ddim_sample(oracle.Params(unet_sd, oracle.PFX_UNET), g["x_T"], g["z"], g["mask"], g["c"], g["uc"],
+                                   5, 3.5, log_every_t=2)
+    assert (x0 - g["x0"]).abs().max() < 1e-3 * float(g["x0"].abs().max())
+    assert len(inter["x_inter"]) == int(g["n_inter"])
+    assert (inter["pred_x0"][-1] - g["pred_x0_last"]).abs().max() < 1e-3 * float(g["x0"].abs().max())
+
+
+def test_vae_matches_reference_golden(oracle, vae_sd):
+    g = _g("vae_64")
+    P = oracle.Params(vae_sd, oracle.PFX_VAE)
+    mean, logvar = oracle.vae_encode_moments(P, g["x"])
+    assert (mean - g["mean"]).abs().max() < 1e-4 and (logvar - g["logvar"]).abs().max() < 1e-4
+    assert (oracle.vae_encode(P, g["x"], g["noise"]) - g["z"]).abs().max() < 1e-4
+    assert (oracle.vae_decode(P, g["zdec"]) - g["img"]).abs().max() < 1e-4
+
+
+def test_clip_and_conditioning_match_reference_golden(oracle, clip_sd, arc_sd, fusion_sd):
+    g = _g("clip_B1")
+    img = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(int(g["img_seed"])))
+    out = oracle.clip_embed(oracle.Params(clip_sd, oracle.PFX_CLIP), img)
+    assert (out - g["out"]).abs().max() < 1e-4
+    g = _g("cond_B2")
+    ref_img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(int(g["ref_seed"])))
+    idf = oracle.arcface_embed(oracle.Params(arc_sd, oracle.PFX_ARC), ref_img)
+    assert (idf - g["id_feat"]).abs().max() < 1e-5
+    full = dict(clip_sd); full.update(arc_sd); full.update(fusion_sd)
+    c = oracle.conditioning_with_feat(oracle.Params(full), ref_img, g["tar"], torch.zeros(2, 136))
+    assert (c - g["c"]).abs().max() < 1e-4
+
+
+def test_concat_and_update_are_exact(oracle):
+    g = torch.Generator().manual_seed(0)
+    x, z, m = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g), torch.rand(2, 1, 8, 8, generator=g)
+    assert torch.equal(oracle.concat9(x, z, m), torch.cat([x, z, m], 1))

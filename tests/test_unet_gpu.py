@@ -1,0 +1,61 @@
+"""GPU: the UNet forward and the DDIM loop through the C ABI against the oracle / the reference goldens.
+
+Stated tolerance (fp16 operands, fp32 accumulation, fp32 statistics/latents): max-abs error of eps
+<= 2e-2 * max|eps_ref| per UNet call."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _g(name):
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, name + ".npz")).items()}
+
+
+@pytest.mark.parametrize("name", ["unet_L16", "unet_L32"])
+def test_unet_forward_vs_reference_golden(unet_engine, name):
+    g = _g(name)
+    eps = unet_engine.unet_forward(g["x"], g["t"], g["ctx"]).cpu()
+    err = float((eps - g["eps"]).abs().max()) / float(g["eps"].abs().max())
+    print(name, "rel err", err)
+    assert err < TOL, err
+
+
+def test_unet_forward_L64_vs_oracle(unet_engine, oracle, unet_sd):
+    gen = torch.Generator().manual_seed(11)
+    x, t = torch.randn(2, 9, 64, 64, generator=gen), torch.tensor([981, 21])
+    ctx = torch.randn(2, 1, 768, generator=gen)
+    with torch.no_grad():
+        ref = oracle.unet_forward(oracle.Params(unet_sd, oracle.PFX_UNET), x, t, ctx)
+    eps = unet_engine.unet_forward(x, t, ctx).cpu()
+    err = float((eps - ref).abs().max()) / float(ref.abs().max())
+    print("L64 rel err", err)
+    assert err < TOL, err
+
+
+def test_batch_independence(unet_engine):
+    """No cross-sample arithmetic: a batch of 4 equals the per-sample results bit for bit (multi-GPU invariant)."""
+    gen = torch.Generator().manual_seed(12)
+    x, t = torch.randn(4, 9, 16, 16, generator=gen), torch.tensor([981, 21, 401, 401])
+    ctx = torch.randn(4, 1, 768, generator=gen)
+    full = unet_engine.unet_forward(x, t, ctx)
+    for i in range(0, 4, 2):
+        part = unet_engine.unet_forward(x[i:i + 2], t[i:i + 2], ctx[i:i + 2])
+        assert torch.equal(part, full[i:i + 2])
+
+
+def test_ddim_loop_vs_reference_golden(unet_engine):
+    g = _g("ddim_S5_L16")
+    x0, ix, ip = unet_engine.ddim_sample(g["x_T"], g["z"], g["mask"], g["c"], g["uc"], S=5, scale=3.5, log_every_t=2)
+    err = float((x0.cpu() - g["x0"]).abs().max()) / float(g["x0"].abs().max())
+    print("ddim rel err", err)
+    assert err < 5e-2, err
+    assert ix.shape[0] == int(g["n_inter"]) - 1      # the reference list also holds x_T as its first entry
+    perr = float((ip[-1].cpu() - g["pred_x0_last"]).abs().max()) / float(g["x0"].abs().max())
+    assert perr < 5e-2, perr
