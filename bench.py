@@ -1,0 +1,241 @@
+#!/usr/bin/env python
+"""bench.py -- faces/sec of the REFace DDIM face-swap path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3            # our arm (hand-written sm_100a kernels)
+    python bench.py --impl reference --steps 2 --warmup 1    # the reference algorithm's CPU port (oracle)
+
+One "step" = one batch of B faces through the whole path: conditioning (CLIP x2 + ArcFace + fusion) ->
+VAE encode -> S-step CFG DDIM over the 9-channel UNet -> VAE decode (config[1]: 512x512, 50 steps, CFG 3.5, B=8
+per GPU).  Synthetic inputs / random-init weights of the reference architecture (no checkpoints offline).
+Multi-GPU: one process per GPU (torchrun), weights broadcast once over NCCL, batch sharded, no collective in the
+step loop ("scaling": "weak").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_FACE = {(512, 50): 83.65e12, (256, 5): 2.98e12, (1024, 50): 481.4e12}   # SURVEY 8(d), reference-equivalent
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", 1386.9), burst=d.get("bf16_tflops", 1654.2),
+                    hbm=d.get("hbm_gbs", 6566.7), source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].startswith("Active") for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+def cpu_baseline(args, steps, warmup):
+    """The reference algorithm (oracle port, fp32, all host cores): bounded sample of the same workload --
+    UNet CFG calls for ONE face (N=2) at the benchmark resolution + one VAE encode/decode + one conditioning pass;
+    faces/s = 1 / (S * t_unet_call + t_enc + t_dec + t_cond)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reface_oracle as O
+    torch.set_grad_enabled(False)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    H, S = args.size, args.ddim_steps
+    L = H // 8
+    sd = O.init_state_dict(O.full_spec(), 0)
+    P = O.Params(sd)
+    inp = O.synthetic_inputs(1, H)
+    t0 = time.time()
+    c = O.conditioning_with_feat(P, inp["ref_img"], inp["tar_img"], inp["landmarks136"])
+    t_cond = time.time() - t0
+    t0 = time.time()
+    z = O.vae_encode(P.sub(O.PFX_VAE), inp["inpaint_img"], inp["enc_noise"])
+    t_enc = time.time() - t0
+    uc = sd["learnable_vector"]
+    x9 = torch.cat([O.concat9(inp["x_T"], z, inp["mask_lat"])] * 2)
+    tt = torch.tensor([981, 981])
+    cc = torch.cat([uc, c])
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.time()
+        eps = O.unet_forward(P.sub(O.PFX_UNET), x9, tt, cc)
+        if i >= warmup:
+            ts.append(time.time() - t0)
+    t_unet = sum(ts) / len(ts)
+    t0 = time.time()
+    O.vae_decode(P.sub(O.PFX_VAE), inp["x_T"] * 0.18215)
+    t_dec = time.time() - t0
+    fps = 1.0 / (S * t_unet + t_enc + t_dec + t_cond)
+    return dict(value=fps, unit="faces/s", cores=cores, kind="port",
+                sample=f"{steps} timed UNet CFG calls (1 face, N=2, L={L}) + 1 VAE encode + 1 decode + 1 conditioning pass; "
+                       f"t_unet={t_unet:.2f}s t_enc={t_enc:.2f}s t_dec={t_dec:.2f}s t_cond={t_cond:.2f}s; "
+                       f"faces/s = 1/({S}*t_unet+t_enc+t_dec+t_cond)"), t_unet * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="faces per GPU per step")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--ddim-steps", type=int, default=50)
+    ap.add_argument("--scale", type=float, default=3.5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    config = dict(workload=f"{args.size}x{args.size}, {args.ddim_steps} DDIM steps, CFG {args.scale}, batch={args.batch}/GPU "
+                           f"(BASELINE configs[1]); full path: CLIPx2+ArcFace+fusion, VAE encode, DDIM, VAE decode",
+                  global_batch=args.batch * world, parallelism=f"dp{world}",
+                  l2_policy="per-step working set (activations + 2.7 GB fp16 weights) exceeds the 126 MB L2")
+    metric = "faces/sec @512x512, 50 DDIM steps, CFG 3.5" if (args.size, args.ddim_steps) == (512, 50) else \
+        f"faces/sec @{args.size}x{args.size}, {args.ddim_steps} DDIM steps, CFG {args.scale}"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, step_ms = cpu_baseline(args, max(1, args.steps), max(0, args.warmup))
+        line = dict(metric=metric, value=cb["value"], unit="faces/s", n_gpus=args.gpus, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32", data="synthetic", config=config, impl="reference", cpu_baseline=cb,
+                    e2e=dict(value=cb["value"], unit="faces/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    from reface_b200 import synth
+    from reface_b200.ldm_api import LatentDiffusion, swap_faces
+    from reface_b200.runtime import Engine
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    # weights: generated once on rank 0, one NCCL broadcast of the flat checkpoint over NVLink
+    if rank == 0:
+        flat = synth.random_flat(dev, seed=0)
+    else:
+        flat = torch.empty(synth.flat_layout()[1], dtype=torch.float32, device=dev)
+    if world > 1:
+        dist.broadcast(flat, 0)
+    eng = Engine(local)
+    model = LatentDiffusion(synth.state_dict_from_flat(flat), engine=eng)
+    del flat
+    torch.cuda.empty_cache()
+
+    B, H, S = args.batch, args.size, args.ddim_steps
+    dev_in = synth.synthetic_inputs(B, H, dev, seed=42 + rank)
+    host_in = synth.synthetic_inputs(B, H, dev, seed=42 + rank, pinned_host=True)
+    out_host = torch.empty(B, 3, H, H, dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        return swap_faces(model, S=S, scale=args.scale, **dev_in)["image"]
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
+        img = swap_faces(model, S=S, scale=args.scale, **d)["image"]
+        out_host.copy_(img, non_blocking=True)
+        return img
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    ms = timed(step_resident, args.steps)
+    launches = eng.launch_count - l0
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+    faces = B * world * args.steps
+    value = faces / (ms / 1e3)
+    e2e_val = faces / (ms_e2e / 1e3)
+    # roofline of the dominant kernel (gemm_tc_kernel: tcgen05 GEMM / implicit-GEMM conv / attention products):
+    # one more step with every such launch bracketed by CUDA events on the launching stream
+    eng.set_option("profile", 1)
+    step_resident()
+    g_ms, g_flops, g_n = eng.profile_read()
+    eng.set_option("profile", 0)
+    pk = peaks()
+    achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+    d2h = out_host.numel() * out_host.element_size()
+    fpf = FLOP_PER_FACE.get((H, S))
+    line = dict(metric=metric, value=value, unit="faces/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",
+                data="synthetic", config=config,
+                e2e=dict(value=e2e_val, unit="faces/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         ms_per_step=ms_e2e / args.steps),
+                gpu_launches=int(launches),
+                roofline=dict(bound="tensor", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s",
+                              frac=achieved / pk["tflops"], traffic=None, kernel="gemm_tc_kernel",
+                              launches_per_step=int(g_n), kernel_ms_per_step=g_ms, alg_tflop_per_step=g_flops / 1e12,
+                              share_of_step=g_ms / (ms / args.steps), peak_source=pk["source"] + ", sustained bf16",
+                              whole_path_frac=(value / world) * fpf / (pk["tflops"] * 1e12) if fpf else None),
+                clocks=sampler.summary() if rank == 0 else None, arena_peak_gb=eng.arena_peak / 2 ** 30)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(args, 2, 1)[0]
+            except Exception as e:  # the GPU number stands on its own
+                line["cpu_baseline"] = dict(error=repr(e))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

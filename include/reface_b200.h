@@ -41,9 +41,13 @@ int rfb_build_unet(rfb_ctx* ctx, const char* prefix);
 int rfb_build_vae(rfb_ctx* ctx, const char* prefix);
 int rfb_build_clip(rfb_ctx* ctx, const char* prefix);
 int rfb_build_arcface(rfb_ctx* ctx, const char* prefix);
-/* Tunables ("gemm_bn", "gemm_stages", "gemm_smem_budget", "attn_flash"); returns 0 if known. */
+/* Tunables ("gemm_bn", "gemm_stages", "gemm_smem_budget", "attn_flash", "profile"); returns 0 if known. */
 int rfb_set_option(rfb_ctx* ctx, const char* key, long long value);
 long long rfb_launch_count(rfb_ctx* ctx); /* kernels launched by this library so far */
+/* With option "profile"=1 every tensor-core (tcgen05 GEMM / implicit-GEMM conv / attention) launch is bracketed
+ * by CUDA events on the launching stream; this drains them: summed device time [ms], summed ALGORITHMIC FLOPs
+ * (2*M*N*K of the reference-equivalent contraction, no padding) and the number of launches. */
+int rfb_profile_read(rfb_ctx* ctx, double* ms, double* flops, long long* n_launches);
 size_t rfb_arena_peak(rfb_ctx* ctx);
 
 /* ---- hot path ---------------------------------------------------------------------------------- */

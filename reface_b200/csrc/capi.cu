@@ -138,10 +138,28 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "gemm_stages") c.force_stages = (int)value;
   else if (k == "gemm_smem_budget") c.gemm_smem_budget = (int)value;
   else if (k == "attn_flash") c.attn_flash = (int)value;
+  else if (k == "profile") c.profile = (int)value;
   else return -1;
   return 0;
 }
 long long rfb_launch_count(rfb_ctx* h) { return h ? h->c.launches : 0; }
+int rfb_profile_read(rfb_ctx* h, double* ms, double* flops, long long* n) {
+  API_BEGIN(h)
+  CUDA_OK(cudaDeviceSynchronize());
+  double tms = 0, tf = 0;
+  for (auto& r : c.prof) {
+    float e = 0;
+    CUDA_OK(cudaEventElapsedTime(&e, r.a, r.b));
+    tms += e, tf += r.flops;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  if (ms) *ms = tms;
+  if (flops) *flops = tf;
+  if (n) *n = (long long)c.prof.size();
+  c.prof.clear();
+  API_END
+}
 size_t rfb_arena_peak(rfb_ctx* h) { return h ? h->c.arena_peak : 0; }
 
 // ------------------------------------------------------------------------------------------ hot path

@@ -168,7 +168,7 @@ int pick_bn(Ctx& c, long long M, int N, bool geglu) {
   return best;
 }
 
-static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, dim3 grid) {
+static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, dim3 grid, double kalg) {
   const int stage_bytes = GEMM_A_STAGE_BYTES + g.BN * 128;
   int stages = c.force_stages ? c.force_stages : std::max(2, std::min(6, c.gemm_smem_budget / stage_bytes));
   stages = std::min(stages, std::max(1, g.nk));
@@ -186,8 +186,20 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   if (g.rows_per_vec <= 0) g.rows_per_vec = 1;
   if (g.o32_rpn <= 0) g.o32_rpn = 1;
   if (g.heads <= 0) g.heads = 1;
+  Ctx::ProfRec rec;
+  if (c.profile) {
+    CUDA_OK(cudaEventCreate(&rec.a));
+    CUDA_OK(cudaEventCreate(&rec.b));
+    rec.flops = 2.0 * (double)g.M * (double)(g.geglu ? g.N : g.N) * kalg * (double)grid.z;
+    rec.kind = 0;
+    CUDA_OK(cudaEventRecord(rec.a, c.stream));
+  }
   gemm_tc_kernel<<<grid, GEMM_THREADS, smem, c.stream>>>(tmA, tmB, g);
   LAUNCH_CHECK(c);
+  if (c.profile) {
+    CUDA_OK(cudaEventRecord(rec.b, c.stream));
+    c.prof.push_back(rec);
+  }
 }
 
 static void fill_epi(GemmArgs& g, const Epi& e, __half* out, long long ldo) {
@@ -198,7 +210,7 @@ static void fill_epi(GemmArgs& g, const Epi& e, __half* out, long long ldo) {
 }
 
 void gemm(Ctx& c, const __half* A, long long lda, long long M, int K, const __half* W, int kp, int N, __half* out,
-          long long ldo, const Epi& e, int force_bn) {
+          long long ldo, const Epi& e, int force_bn, int kalg) {
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M = (int)M, g.N = N, g.nk = (K + 63) / 64;
@@ -215,7 +227,7 @@ void gemm(Ctx& c, const __half* A, long long lda, long long M, int K, const __ha
   CUtensorMap tmA = make_tmap(c, A, 2, da, sa, ba);
   CUtensorMap tmB = make_tmap(c, W, 2, db, sb, bb);
   dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + g.BN - 1) / g.BN), 1);
-  launch_gemm(c, tmA, tmB, g, grid);
+  launch_gemm(c, tmA, tmB, g, grid, (double)(kalg > 0 ? kalg : K));
 }
 
 Tens linear_t(Ctx& c, const Tens& x, const LinW& w, Epi e) {
@@ -273,7 +285,7 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
     CUtensorMap tmA = make_tmap(c, x.p, 4, da, sa, ba);
     CUtensorMap tmB = make_tmap(c, w.w, 2, db, sb, bb);
     dim3 grid((unsigned)((M + 127) / 128), (unsigned)((w.cout + g.BN - 1) / g.BN), 1);
-    launch_gemm(c, tmA, tmB, g, grid);
+    launch_gemm(c, tmA, tmB, g, grid, 9.0 * w.cin);
     return y;
   }
   // generic path: explicit im2col then a plain GEMM
@@ -286,7 +298,7 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
   im2col_kernel<<<grid_for(M * (w.kp / 8)), 256, 0, c.stream>>>(x.p, col, x.n, x.h, x.w, x.c, w.ksz, w.ksz, stride, pad_t,
                                                               pad_l, Ho, Wo, w.kp);
   LAUNCH_CHECK(c);
-  gemm(c, col, w.kp, M, w.kp, w.w, w.kp, w.cout, y.p, y.c, e);
+  gemm(c, col, w.kp, M, w.kp, w.w, w.kp, w.cout, y.p, y.c, e, 0, w.taps * w.cin);
   c.release(mk);
   return y;
 }
@@ -319,7 +331,7 @@ void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads
     CUtensorMap tmA = make_tmap(c, qkv + q_off, 4, dq, sq, bq);
     CUtensorMap tmB = make_tmap(c, qkv + k_off, 4, dq, sq, bk);
     dim3 grid((unsigned)((L + 127) / 128), (unsigned)((L + g.BN - 1) / g.BN), (unsigned)Z);
-    launch_gemm(c, tmA, tmB, g, grid);
+    launch_gemm(c, tmA, tmB, g, grid, (double)d);
   }
   softmax_rows_kernel<<<(unsigned)((long long)Z * L), L >= 1024 ? 256 : 128, 0, c.stream>>>(S, (long long)Z * L, L, Lp);
   LAUNCH_CHECK(c);
@@ -346,7 +358,7 @@ void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads
     CUtensorMap tmA = make_tmap(c, S, 3, dp, sp, bp);
     CUtensorMap tmB = make_tmap(c, Vt, 3, dv, sv, bv);
     dim3 grid((unsigned)((L + 127) / 128), (unsigned)((d + g.BN - 1) / g.BN), (unsigned)Z);
-    launch_gemm(c, tmA, tmB, g, grid);
+    launch_gemm(c, tmA, tmB, g, grid, (double)L);
   }
   c.release(mk);
 }

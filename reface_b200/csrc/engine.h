@@ -74,6 +74,10 @@ struct Ctx {
   long long launches = 0;     // kernels launched by this library (reported by bench)
   int gemm_smem_budget = 110 * 1024;  // per-CTA smem target (2 CTAs/SM)
   int force_bn = 0, force_stages = 0, attn_flash = 1;
+  // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline)
+  int profile = 0;
+  struct ProfRec { cudaEvent_t a, b; double flops; int kind; };
+  std::vector<ProfRec> prof;
   UNet* unet = nullptr;
   VAE* vae = nullptr;
   ClipVision* clip = nullptr;
@@ -120,7 +124,7 @@ int pick_bn(Ctx& c, long long M, int N, bool geglu);
 
 // ---- op launchers (all asynchronous on c.stream)
 void gemm(Ctx& c, const __half* A, long long lda, long long M, int K, const __half* W, int kp, int N, __half* out,
-          long long ldo, const Epi& e, int force_bn = 0);
+          long long ldo, const Epi& e, int force_bn = 0, int kalg = 0);
 void conv3x3(Ctx& c, const Tens& x, const ConvW& w, __half* out, long long ldo, Epi e, int stride = 1, int pad_t = 1,
              int pad_l = 1, int Ho = -1, int Wo = -1);
 Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride = 1, int pad_t = 1, int pad_l = 1,

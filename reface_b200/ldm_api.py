@@ -1,0 +1,316 @@
+"""Drop-in API surface: the reference's Python signatures on top of the CUDA engine.
+
+The reference's plugin mechanism is `instantiate_from_config` (ldm/util.py:78-93): YAML `target:` strings
+name classes.  Pointing those strings (and the `from ldm.models.diffusion.ddim import DDIMSampler` import of
+scripts/inference_test_bench.py:339) at this module swaps the hot path for the sm_100a kernels while the
+driver script stays as it is:
+
+    unet_config.target         ldm.modules.diffusionmodules.openaimodel.UNetModel   -> reface_b200.ldm_api.UNetModel
+    first_stage_config.target  ldm.models.autoencoder.AutoencoderKL                  -> reface_b200.ldm_api.AutoencoderKL
+    cond_stage_config.target   ldm.modules.encoders.modules.FrozenCLIPEmbedder       -> reface_b200.ldm_api.FrozenCLIPEmbedder
+    model.target               ldm.models.diffusion.ddpm.LatentDiffusion             -> reface_b200.ldm_api.LatentDiffusion
+
+Only tensors cross the boundary (PyTorch CUDA tensors in/out); nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import contextlib
+
+import numpy as np
+import torch
+
+from .runtime import Engine, ddim_schedule
+
+_ENGINES = {}
+
+
+def get_engine(device: int = 0, arena_bytes: int = 0) -> Engine:
+    if device not in _ENGINES:
+        _ENGINES[device] = Engine(device, arena_bytes)
+    return _ENGINES[device]
+
+
+class _Module:
+    """Minimal nn.Module-like shell (state-dict loading, eval/cuda no-ops) around engine weights."""
+    prefix = ""
+
+    def __init__(self, engine=None, device=0):
+        self.engine = engine or get_engine(device)
+        self.device = self.engine.device
+        self._built = False
+
+    def load_state_dict(self, sd, strict=True):
+        self.engine.load_state_dict({self.prefix + k: v for k, v in sd.items()})
+        self._build()
+        self._built = True
+        return [], []
+
+    def eval(self):
+        return self
+
+    def cuda(self, *a, **k):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def parameters(self):
+        return iter(())
+
+
+class UNetModel(_Module):
+    """ldm/modules/diffusionmodules/openaimodel.py:528-907 (constructor args :558-588, forward :860)."""
+    prefix = "model.diffusion_model."
+
+    def __init__(self, image_size=32, in_channels=9, model_channels=320, out_channels=4, num_res_blocks=2,
+                 attention_resolutions=(4, 2, 1), channel_mult=(1, 2, 4, 4), num_heads=8, use_spatial_transformer=True,
+                 transformer_depth=1, context_dim=768, use_checkpoint=False, legacy=False,
+                 add_conv_in_front_of_unet=False, engine=None, device=0, **unused):
+        super().__init__(engine, device)
+        cfg = (in_channels, out_channels, model_channels, num_res_blocks, tuple(attention_resolutions),
+               tuple(channel_mult), num_heads, context_dim, transformer_depth, use_spatial_transformer, legacy,
+               add_conv_in_front_of_unet)
+        if cfg != (9, 4, 320, 2, (4, 2, 1), (1, 2, 4, 4), 8, 768, 1, True, False, False):
+            raise NotImplementedError(f"reface_b200 implements the shipped REFace UNet config only, got {cfg}")
+        self.in_channels, self.out_channels, self.model_channels = in_channels, out_channels, model_channels
+        self.dtype = torch.float32
+
+    def _build(self):
+        self.engine.build_unet(self.prefix)
+
+    def forward(self, x, timesteps=None, context=None, y=None, return_features=False, **kwargs):
+        assert y is None, "must specify y if and only if the model is class-conditional"   # openaimodel.py:870-872
+        if return_features:
+            raise NotImplementedError("return_features is a training-time option")
+        return self.engine.unet_forward(x, timesteps, context)
+
+    __call__ = forward
+
+
+class _Posterior:
+    """DiagonalGaussianDistribution (ldm/modules/distributions/distributions.py:24-61) over engine outputs."""
+
+    def __init__(self, engine, img):
+        self.engine, self.img = engine, img
+        self._moments = None
+
+    def _m(self):
+        if self._moments is None:
+            _, mean, logvar = self.engine.vae_encode(self.img, None, return_moments=True)
+            self._moments = (mean, logvar)
+        return self._moments
+
+    @property
+    def mean(self):
+        return self._m()[0]
+
+    @property
+    def logvar(self):
+        return self._m()[1]
+
+    def sample(self, noise=None):
+        if noise is None:
+            b, _, h, w = self.img.shape
+            noise = torch.randn(b, 4, h // 8, w // 8, device=self.engine.device)
+        z = self.engine.vae_encode(self.img, noise)
+        return z / 0.18215           # unscaled, as the reference's posterior.sample(); scale_factor applied by the caller
+
+    def mode(self):
+        return self.mean
+
+
+class AutoencoderKL(_Module):
+    """ldm/models/autoencoder.py:285-333: encode(x) -> posterior, decode(z) -> image."""
+    prefix = "first_stage_model."
+
+    def __init__(self, ddconfig=None, lossconfig=None, embed_dim=4, engine=None, device=0, **unused):
+        super().__init__(engine, device)
+        self.embed_dim = embed_dim
+
+    def _build(self):
+        self.engine.build_vae(self.prefix)
+
+    def encode(self, x):
+        return _Posterior(self.engine, x)
+
+    def decode(self, z):
+        return self.engine.vae_decode(z * 0.18215)   # engine entry point takes the scaled latent (ddpm.py:1284)
+
+
+class FrozenCLIPEmbedder(_Module):
+    """ldm/modules/encoders/modules.py:211-264: encode(image[B,3,224,224]) -> [B,1,768]."""
+    prefix = "cond_stage_model."
+
+    def __init__(self, version="openai/clip-vit-large-patch14", engine=None, device=0, **unused):
+        super().__init__(engine, device)
+
+    def _build(self):
+        self.engine.build_clip(self.prefix)
+
+    def encode(self, image):
+        return self.engine.clip_encode(image)
+
+    forward = __call__ = encode
+
+
+class LatentDiffusion:
+    """The slice of ldm/models/diffusion/ddpm.py:LatentDiffusion that the inference scripts touch
+    (scripts/inference_test_bench.py:408-493, ldm/models/diffusion/ddim.py:100,113-119,207,345)."""
+
+    def __init__(self, state_dict=None, engine=None, device=0, scale_factor=0.18215, linear_start=0.00085,
+                 linear_end=0.012, timesteps=1000, clip_weight=1.0, ID_weight=10.0, Landmarks_weight=0.05, **unused):
+        self.engine = engine or get_engine(device)
+        self.device = self.engine.device
+        self.scale_factor = scale_factor
+        self.num_timesteps = timesteps
+        sch = ddim_schedule(50, 0.0, linear_start, linear_end, timesteps)
+        ac = sch["alphas_cumprod"]
+        self.betas = torch.tensor(sch["betas"], device=self.device)
+        self.alphas_cumprod = torch.tensor(ac, device=self.device)
+        self.alphas_cumprod_prev = torch.tensor(np.append(np.float32(1.0), ac[:-1]), device=self.device)
+        self.linear_start, self.linear_end = linear_start, linear_end
+        self.clip_weight, self.ID_weight, self.Landmarks_weight = clip_weight, ID_weight, Landmarks_weight
+        self.stack_feat = self.land_mark_id_seperate_layers = self.sep_head_att = False
+        self.Landmark_cond = True
+        self.learnable_vector = None
+        self._landmark_bias = None
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # -- weights
+    def load_state_dict(self, sd, strict=False):
+        e = self.engine
+        e.load_state_dict(sd)
+        e.build_unet()
+        e.build_vae()
+        e.build_clip()
+        e.build_arcface()
+        self.learnable_vector = sd["learnable_vector"].to(self.device, torch.float32)
+        self._landmark_bias = sd["landmark_proj_out.bias"].to(self.device, torch.float32)
+        return [], []
+
+    def eval(self):
+        return self
+
+    def cuda(self):
+        return self
+
+    @contextlib.contextmanager
+    def ema_scope(self, context=None):       # use_ema: false (project_ffhq.yaml:19) -> no-op (ddpm.py:309-322)
+        yield None
+
+    # -- hot path
+    def apply_model(self, x_noisy, t, cond, return_ids=False):             # ddpm.py:1519-1617, 2244-2246
+        if isinstance(cond, dict):
+            cond = torch.cat(cond["c_crossattn"], 1)
+        elif isinstance(cond, (list, tuple)):
+            cond = torch.cat(list(cond), 1)
+        return self.engine.unet_forward(x_noisy, t, cond)
+
+    def encode_first_stage(self, x):                                       # ddpm.py:1402-1439
+        return _Posterior(self.engine, x)
+
+    def get_first_stage_encoding(self, posterior, noise=None):             # ddpm.py:850-857
+        if isinstance(posterior, _Posterior):
+            return self.scale_factor * posterior.sample(noise)
+        return self.scale_factor * posterior
+
+    def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):   # ddpm.py:1277-1337
+        return self.engine.vae_decode(z)
+
+    def get_learned_conditioning(self, c):                                 # ddpm.py:859-870
+        return self.engine.clip_encode(c)
+
+    def get_landmarks(self, x):
+        """ddpm.py:1068-1099.  dlib is outside the boundary: without a detector every image
+        takes the reference's no-face branch (zeros(136) -> landmark_proj_out), i.e. the projection bias."""
+        return self._landmark_bias[None].repeat(x.shape[0], 1)
+
+    def conditioning_with_feat(self, x, landmarks=None, is_train=False, tar=None, tar_mask=None, landmarks136=None):
+        """ddpm.py:872-1045 for the shipped config (Source+Target CLIP, ArcFace ID, landmarks, weight_division).
+        `landmarks136` (raw 68x2 dlib points) may be given instead of the projected `landmarks`."""
+        e = self.engine
+        b = x.shape[0]
+        c_src = e.clip_encode(x)
+        c_tgt = e.clip_encode(e.target_clip_input(tar))
+        idf = e.arcface_embed(x)
+        if landmarks136 is None:
+            landmarks136 = torch.zeros(b, 136, device=self.device)
+            # a caller-supplied projected landmark vector other than the no-face bias cannot be inverted
+            if landmarks is not None and not torch.allclose(landmarks.reshape(b, -1).to(self.device), self._landmark_bias[None].expand(b, -1)):
+                raise NotImplementedError("pass raw landmarks via landmarks136=...")
+        return e.condition_fuse(c_src, c_tgt, idf, landmarks136, self.clip_weight, self.ID_weight, self.Landmarks_weight)
+
+
+class DDIMSampler:
+    """ldm/models/diffusion/ddim.py:96-251: same constructor and `sample` signature; the 50-step loop runs inside
+    one C-ABI call (rfb_ddim_sample)."""
+
+    def __init__(self, model, schedule="linear", **kwargs):
+        self.model = model
+        self.ddpm_num_timesteps = model.num_timesteps
+        self.schedule = schedule
+
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0.0, verbose=True):
+        assert ddim_discretize == "uniform"
+        sch = ddim_schedule(ddim_num_steps, ddim_eta, self.model.linear_start, self.model.linear_end,
+                            self.ddpm_num_timesteps)
+        self._sch = sch
+        self.ddim_timesteps = sch["timesteps"]
+        dev = self.model.device
+        self.ddim_alphas = torch.tensor(sch["a_t"], device=dev)
+        self.ddim_alphas_prev = sch["a_prev"]
+        self.ddim_sigmas = torch.tensor(sch["sigma"], device=dev)
+        self.ddim_sqrt_one_minus_alphas = torch.tensor(sch["sqrt_one_minus_a"], device=dev)
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None, img_callback=None,
+               quantize_x0=False, eta=0.0, mask=None, x0=None, temperature=1.0, noise_dropout=0.0, score_corrector=None,
+               corrector_kwargs=None, verbose=True, x_T=None, log_every_t=100, unconditional_guidance_scale=1.0,
+               unconditional_conditioning=None, src_im=None, tar=None, **kwargs):
+        if conditioning is not None and not isinstance(conditioning, dict) and conditioning.shape[0] != batch_size:
+            print(f"Warning: Got {conditioning.shape[0]} conditionings but batch-size is {batch_size}")   # ddim.py:172-173
+        if "test_model_kwargs" in kwargs:
+            tk = kwargs["test_model_kwargs"]
+            z_inpaint, m = tk["inpaint_image"], tk["inpaint_mask"]
+        elif "rest" in kwargs:
+            rest = kwargs["rest"]
+            z_inpaint, m = rest[:, :4], rest[:, 4:5]
+        else:
+            raise Exception("kwargs must contain either 'test_model_kwargs' or 'rest' key")           # ddim.py:333-334
+        for name, v in dict(mask=mask, score_corrector=score_corrector, callback=callback, img_callback=img_callback).items():
+            if v is not None:
+                raise NotImplementedError(f"{name} is not supported by the fused DDIM loop")
+        if quantize_x0 or noise_dropout > 0.0:
+            raise NotImplementedError("quantize_x0 / noise_dropout are not supported")
+        self.make_schedule(S, ddim_eta=eta, verbose=verbose)
+        C, H, W = shape
+        eng = self.model.engine
+        dev = self.model.device
+        if x_T is None:
+            x_T = torch.randn(batch_size, C, H, W, device=dev)                                        # ddim.py:210-213
+        n = len(self.ddim_timesteps)
+        noise = None
+        if eta > 0:
+            noise = torch.randn(n, batch_size, C, H, W, device=dev) * temperature                       # ddim.py:371
+        x0_, ix, ip = eng.ddim_sample(x_T, z_inpaint, m, conditioning, unconditional_conditioning, S,
+                                      unconditional_guidance_scale, eta=eta, log_every_t=log_every_t, noise=noise,
+                                      schedule=self._sch)
+        inter = {"x_inter": [x_T] + list(ix), "pred_x0": [x_T] + list(ip)}                             # ddim.py:221,247-249
+        return x0_, inter
+
+
+def swap_faces(model: LatentDiffusion, ref_img, tar_img, inpaint_img, mask_lat, landmarks136, x_T, enc_noise, S=50,
+               scale=3.5, log_every_t=100):
+    """The per-batch body of scripts/inference_test_bench.py:438-495 through the drop-in classes."""
+    b = ref_img.shape[0]
+    uc = model.learnable_vector.repeat(b, 1, 1)                                                      # :441
+    c = model.conditioning_with_feat(ref_img, tar=tar_img, landmarks136=landmarks136)                 # :447-448
+    z_inpaint = model.get_first_stage_encoding(model.encode_first_stage(inpaint_img), noise=enc_noise)   # :462-463
+    sampler = DDIMSampler(model)
+    samples, _ = sampler.sample(S=S, conditioning=c, batch_size=b, shape=[4, x_T.shape[2], x_T.shape[3]], verbose=False,
+                                unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0, x_T=x_T,
+                                log_every_t=log_every_t,
+                                test_model_kwargs={"inpaint_image": z_inpaint, "inpaint_mask": mask_lat})   # :469-479
+    x = model.decode_first_stage(samples)                                                              # :493
+    return dict(c=c, z_inpaint=z_inpaint, samples=samples, image=torch.clamp((x + 1.0) / 2.0, 0.0, 1.0))

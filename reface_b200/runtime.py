@@ -32,6 +32,7 @@ SIGNATURES = {
     "rfb_set_option": (_i, [_vp, C.c_char_p, _ll]),
     "rfb_launch_count": (_ll, [_vp]),
     "rfb_arena_peak": (_sz, [_vp]),
+    "rfb_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
     "rfb_unet_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "rfb_concat9": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "rfb_cfg_ddim_update": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp]),
@@ -168,6 +169,12 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.lib.rfb_launch_count(self.h))
+
+    def profile_read(self):
+        """(ms, algorithmic_flops, n_launches) of the tensor-core launches since option 'profile' was set."""
+        ms, fl, n = C.c_double(), C.c_double(), _ll()
+        self._ck(self.lib.rfb_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(n)))
+        return ms.value, fl.value, n.value
 
     @property
     def arena_peak(self):

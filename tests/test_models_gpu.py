@@ -1,0 +1,110 @@
+"""GPU: VAE, CLIP, ArcFace, conditioning fusion and the whole swap path through the C ABI vs the reference
+goldens / the oracle.  Tolerances are the stated fp16 tolerances (relative to the reference's max magnitude)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _g(name):
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, name + ".npz")).items()}
+
+
+def rel(a, b):
+    return float((a.cpu() - b).abs().max() / b.abs().max())
+
+
+@pytest.fixture(scope="module")
+def vae_engine(engine, vae_sd):
+    engine.load_state_dict(vae_sd)
+    engine.build_vae()
+    return engine
+
+
+def test_vae_encode_decode_vs_reference_golden(vae_engine):
+    g = _g("vae_64")
+    z, mean, logvar = vae_engine.vae_encode(g["x"], g["noise"], return_moments=True)
+    print("vae mean", rel(mean, g["mean"]), "logvar", rel(logvar, g["logvar"]), "z", rel(z, g["z"]))
+    assert rel(mean, g["mean"]) < 2e-2 and rel(logvar, g["logvar"]) < 2e-2 and rel(z, g["z"]) < 2e-2
+    img = vae_engine.vae_decode(g["zdec"])
+    print("vae decode", rel(img, g["img"]))
+    assert rel(img, g["img"]) < 2e-2
+
+
+def test_vae_512_vs_oracle(vae_engine, oracle, vae_sd):
+    gen = torch.Generator().manual_seed(3)
+    z = torch.randn(1, 4, 32, 32, generator=gen) * 0.18215 * 3
+    with torch.no_grad():
+        ref = oracle.vae_decode(oracle.Params(vae_sd, oracle.PFX_VAE), z)
+    img = vae_engine.vae_decode(z)
+    print("vae decode 256", rel(img, ref))
+    assert rel(img, ref) < 2e-2
+    x = torch.rand(1, 3, 256, 256, generator=gen) * 2 - 1
+    noise = torch.randn(1, 4, 32, 32, generator=gen)
+    with torch.no_grad():
+        zr = oracle.vae_encode(oracle.Params(vae_sd, oracle.PFX_VAE), x, noise)
+    zz = vae_engine.vae_encode(x, noise)
+    print("vae encode 256", rel(zz, zr))
+    assert rel(zz, zr) < 2e-2
+
+
+@pytest.fixture(scope="module")
+def cond_engine(engine, clip_sd, arc_sd, fusion_sd):
+    for sd in (clip_sd, arc_sd, fusion_sd):
+        engine.load_state_dict(sd)
+    engine.build_clip()
+    engine.build_arcface()
+    return engine
+
+
+def test_clip_vs_reference_golden(cond_engine):
+    g = _g("clip_B1")
+    img = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(int(g["img_seed"])))
+    out = cond_engine.clip_encode(img)
+    print("clip", rel(out, g["out"]))
+    assert rel(out, g["out"]) < 3e-2
+
+
+def test_arcface_and_fusion_vs_reference_golden(cond_engine):
+    g = _g("cond_B2")
+    ref_img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(int(g["ref_seed"])))
+    idf = cond_engine.arcface_embed(ref_img)
+    print("arcface", rel(idf, g["id_feat"]))
+    assert rel(idf, g["id_feat"]) < 3e-2
+    c_src = cond_engine.clip_encode(ref_img)
+    c_tgt = cond_engine.clip_encode(cond_engine.target_clip_input(g["tar"]))
+    c = cond_engine.condition_fuse(c_src, c_tgt, idf, torch.zeros(2, 136))
+    print("cond", rel(c, g["c"]))
+    assert rel(c, g["c"]) < 3e-2
+
+
+def test_target_clip_input_matches_oracle(cond_engine, oracle):
+    tar = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(9)) * 2 - 1
+    out = cond_engine.target_clip_input(tar).cpu()
+    assert float((out - oracle.target_clip_input(tar)).abs().max()) < 1e-4
+
+
+def test_full_swap_path_vs_oracle(engine, oracle, unet_sd, vae_sd, clip_sd, arc_sd, fusion_sd):
+    """Whole path (config[0] shape: 256x256, 5 DDIM steps, B=1, CFG 3.5) through the drop-in classes vs the oracle.
+    Stated tolerance per decoded pixel (image in [0,1]): max-abs 0.08, mean-abs 0.01 (fp16 operands over
+    5 x 2 UNet calls + VAE; fp32 latents/statistics)."""
+    from reface_b200.ldm_api import LatentDiffusion, swap_faces
+    sd = {}
+    for d in (unet_sd, vae_sd, clip_sd, arc_sd, fusion_sd):
+        sd.update(d)
+    model = LatentDiffusion(sd, engine=engine)
+    inp = oracle.synthetic_inputs(1, 256, seed=5)
+    with torch.no_grad():
+        ref = oracle.swap_pipeline(sd, S=5, scale=3.5, **inp)
+    out = swap_faces(model, S=5, scale=3.5, **{k: v.cuda() for k, v in inp.items()})
+    for k in ("c", "z_inpaint", "samples"):
+        print(k, rel(out[k], ref[k]))
+    d = (out["image"].cpu() - ref["image"]).abs()
+    print("image max", float(d.max()), "mean", float(d.mean()))
+    assert rel(out["c"], ref["c"]) < 3e-2 and rel(out["z_inpaint"], ref["z_inpaint"]) < 2e-2
+    assert float(d.max()) < 0.08 and float(d.mean()) < 0.01
