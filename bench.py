@@ -70,7 +70,8 @@ def cpu_baseline(args, steps, warmup):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import reface_oracle as O
     torch.set_grad_enabled(False)
-    cores = os.cpu_count() or 1
+    ncpu = os.cpu_count() or 1
+    cores = min(ncpu, int(os.environ.get("RFB_CPU_THREADS", 32)))   # torch CPU ops stop scaling (and regress) beyond ~32 threads
     torch.set_num_threads(cores)
     H, S = args.size, args.ddim_steps
     L = H // 8
@@ -229,7 +230,7 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline(args, 2, 1)[0]
+                line["cpu_baseline"] = cpu_baseline(args, 1, 1)[0]
             except Exception as e:  # the GPU number stands on its own
                 line["cpu_baseline"] = dict(error=repr(e))
         print(json.dumps(line))

@@ -160,11 +160,12 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[(long long)n * 2 * C + i], sh[i]);
 }
-// Phase 2: y = (x-mean)*rstd*gamma+beta [* sigmoid]  (one thread per 8 channels of one pixel)
+// Phase 2: y = x*a[n,c] + b[n,c] [* sigmoid] with a = rstd*gamma, b = beta - mean*rstd*gamma staged in smem.
+// blockDim = (C/8)*R like phase 1: a thread keeps its 8 channels (a/b in registers) and walks over pixels.
 __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ y,
-                                int N, int HW, int C, int G, float eps, int silu) {
-  extern __shared__ float sh[];  // per-block cache of mean/rstd for one sample: [2*G]
+                                int N, int HW, int C, int G, float eps, int silu, int slab) {
+  extern __shared__ float sh[];  // [2*G] mean/rstd
   const int n = blockIdx.y;
   const int cpg = C / G;
   for (int gidx = threadIdx.x; gidx < G; gidx += blockDim.x) {
@@ -181,11 +182,20 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
   }
   __syncthreads();
   const int cv = C >> 3;
-  const long long total = (long long)HW * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cv);
-    const long long p = i / cv;
-    const long long off = ((long long)n * HW + p) * C + c8 * 8;
+  const int R = blockDim.x / cv;
+  const int cq = threadIdx.x % cv, pr = threadIdx.x / cv;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cq * 8 + j;
+    const int gi = c / cpg;
+    a[j] = sh[2 * gi + 1] * __ldg(gamma + c);
+    b[j] = __ldg(beta + c) - sh[2 * gi] * a[j];
+  }
+  const int p0 = blockIdx.x * slab;
+  const int p1 = min(HW, p0 + slab);
+  for (int p = p0 + pr; p < p1; p += R) {
+    const long long off = ((long long)n * HW + p) * C + cq * 8;
     const uint4 u = *reinterpret_cast<const uint4*>(x + off);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     float v[8];
@@ -197,9 +207,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c8 * 8 + j;
-      const int gi = c / cpg;
-      float t = (v[j] - sh[2 * gi]) * sh[2 * gi + 1] * __ldg(gamma + c) + __ldg(beta + c);
+      float t = v[j] * a[j] + b[j];
       if (silu) t = t / (1.0f + __expf(-t));
       v[j] = t;
     }
@@ -257,21 +265,20 @@ __global__ void softmax_rows_kernel(__half* __restrict__ x, long long rows, int 
   __half* p = x + row * ld;
   float mx = -INFINITY;
   for (int i = threadIdx.x; i < L; i += blockDim.x) mx = fmaxf(mx, __half2float(p[i]));
+  const int nw = blockDim.x >> 5;
   mx = warp_max(mx);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();
-  mx = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
-  mx = warp_max(mx);
-  mx = __shfl_sync(0xffffffffu, mx, 0);
+  mx = -INFINITY;
+  for (int w = 0; w < nw; ++w) mx = fmaxf(mx, red[w]);  // every thread reduces the per-warp partials
   __syncthreads();
   float s = 0.f;
   for (int i = threadIdx.x; i < L; i += blockDim.x) s += __expf(__half2float(p[i]) - mx);
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
-  s = warp_sum(s);
-  s = __shfl_sync(0xffffffffu, s, 0);
+  s = 0.f;
+  for (int w = 0; w < nw; ++w) s += red[w];
   const float inv = 1.0f / s;
   for (int i = threadIdx.x; i < ld; i += blockDim.x)
     p[i] = (i < L) ? __float2half_rn(__expf(__half2float(p[i]) - mx) * inv) : __float2half_rn(0.f);
@@ -296,29 +303,46 @@ __global__ void transpose_v_kernel(const __half* __restrict__ v, __half* __restr
 }
 
 // ------------------------------------------------------------------ small-M linear (fp32 in, fp32 weights)
-// out[r, o] = act(bias[o] + sum_k act_in(x[r, k]) * W[o, k]) for r < R <= 16; one warp per output o.
+// out[r, o] = act_out(bias[o] + sum_k act_in(x[r, k]) * W[o, k]) (+ res[r, o]) for r < R <= RMAX.
+// One warp per output column; x is staged (activated once) through shared memory in 512-wide K chunks,
+// weights are streamed with 16-byte loads.  K % 4 == 0.
 template <int RMAX>
 __global__ void linear_small_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                     const float* __restrict__ bias, float* __restrict__ out, int R, int K, int O,
                                     long long ldx, long long ldo, int act_in, int act_out,
                                     const float* __restrict__ res) {
-  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (o >= O) return;
-  const int lane = threadIdx.x & 31;
+  constexpr int KC = 512;
+  __shared__ __align__(16) float xs[RMAX][KC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + warp;
   float acc[RMAX];
 #pragma unroll
   for (int r = 0; r < RMAX; ++r) acc[r] = 0.f;
-  const float* w = W + (long long)o * K;
-  for (int k = lane; k < K; k += 32) {
-    const float wv = __ldg(w + k);
-#pragma unroll
-    for (int r = 0; r < RMAX; ++r)
-      if (r < R) {
-        float xv = x[r * ldx + k];
-        if (act_in == 1) xv = xv / (1.0f + __expf(-xv));
-        acc[r] += xv * wv;
+  const float* w = W + (long long)min(o, O - 1) * K;
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    const int kc = min(KC, K - k0);
+    for (int idx = threadIdx.x; idx < R * KC; idx += blockDim.x) {
+      const int r = idx / KC, kk = idx % KC;
+      float v = 0.f;
+      if (kk < kc) {
+        v = x[r * ldx + k0 + kk];
+        if (act_in == 1) v = v / (1.0f + __expf(-v));
       }
+      xs[r][kk] = v;
+    }
+    __syncthreads();
+    for (int kk = lane * 4; kk < kc; kk += 128) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k0 + kk));
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r)
+        if (r < R) {
+          const float4 xv = *reinterpret_cast<const float4*>(&xs[r][kk]);
+          acc[r] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+        }
+    }
+    __syncthreads();
   }
+  if (o >= O) return;
 #pragma unroll
   for (int r = 0; r < RMAX; ++r) {
     if (r < R) {

@@ -131,7 +131,7 @@ Lin32 lin32(Ctx& c, const std::string& wname, const std::string& bname) {
 }
 
 // ------------------------------------------------------------------------------------------ TMA descriptors
-static CUtensorMap make_tmap(Ctx& c, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+CUtensorMap make_tmap(Ctx& c, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
                              const uint32_t* box) {
   CUtensorMap m;
   uint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -309,6 +309,7 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
 // [ref: ldm/modules/attention.py:204-220]
 void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads, int d, __half* out, long long ldo,
                float scale, int q_off, int k_off, int v_off) {
+  if (c.attn_flash && attention_flash(c, qkv, ldq, N, L, heads, d, out, ldo, scale, q_off, k_off, v_off)) return;
   const size_t mk = c.mark();
   const int Z = N * heads;
   const int Lp = round_up(L, 8);
@@ -378,9 +379,11 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
   dim3 g1((unsigned)((HW + slab - 1) / slab), (unsigned)x.n);
   gn_stats_kernel<<<g1, cv * R, 2 * C * sizeof(float), c.stream>>>(x.p, stats, HW, C, slab);
   LAUNCH_CHECK(c);
-  dim3 g2((unsigned)grid_for((long long)HW * cv, 256, 148 * 8), (unsigned)x.n);
-  gn_apply_kernel<<<g2, 256, 2 * 32 * sizeof(float), c.stream>>>(x.p, stats, gamma, beta, y.p, x.n, HW, C, 32, eps,
-                                                               silu ? 1 : 0);
+  const int want2 = std::max(1, (8 * c.num_sms) / std::max(1, x.n));
+  const int slab2 = std::max(R, (HW + want2 - 1) / want2);
+  dim3 g2((unsigned)((HW + slab2 - 1) / slab2), (unsigned)x.n);
+  gn_apply_kernel<<<g2, cv * R, 2 * 32 * sizeof(float), c.stream>>>(x.p, stats, gamma, beta, y.p, x.n, HW, C, 32, eps,
+                                                                  silu ? 1 : 0, slab2);
   LAUNCH_CHECK(c);
   c.release(mk);
   return y;

@@ -122,6 +122,13 @@ LinW pack_geglu(Ctx& c, const std::string& wname, const std::string& bname, int 
 Lin32 lin32(Ctx& c, const std::string& wname, const std::string& bname);
 int pick_bn(Ctx& c, long long M, int N, bool geglu);
 
+// TMA descriptor (fp16, 128-byte swizzle, zero fill out of bounds); dims/box innermost first, strides in bytes
+CUtensorMap make_tmap(Ctx& c, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                      const uint32_t* box);
+// fused flash-style attention (tcgen05, S and O tiles in TMEM); returns false when the shape is not covered
+bool attention_flash(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads, int d, __half* out,
+                     long long ldo, float scale, int q_off, int k_off, int v_off);
+
 // ---- op launchers (all asynchronous on c.stream)
 void gemm(Ctx& c, const __half* A, long long lda, long long M, int K, const __half* W, int kp, int N, __half* out,
           long long ldo, const Epi& e, int force_bn = 0, int kalg = 0);

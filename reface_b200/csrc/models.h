@@ -51,8 +51,13 @@ struct DdimSchedule {
 };
 
 UNet* build_unet(Ctx& c, const std::string& pfx, const UNetCfg& cfg);
+struct UNetAux {                        // optional step-invariant inputs of a forward pass
+  int uniform_t = 0;                    // all N samples share t[0] (DDIM loop)
+  std::vector<const float*> crossvec;   // per SpatialTransformer (execution order): to_out(to_v(ctx)) [N, C]
+};
+std::vector<const float*> unet_cross_vectors(Ctx& c, UNet& u, const float* ctx, int N, int T);
 void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const float* ctx, int N, int L, int T,
-                  float* eps);
+                  float* eps, const UNetAux* aux = nullptr);
 Tens cross_attention_general(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T, int N);
 void ddim_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, const float* mask, const float* cond,
                  const float* uncond, int B, int L, int T, const DdimSchedule& s, float scale, const float* noise,

@@ -150,13 +150,13 @@ UNet* build_unet(Ctx& c, const std::string& pfx, const UNetCfg& cfg) {
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-static Tens run_res(Ctx& c, const ResW& r, const Tens& x, const float* emb, int N) {
-  // emb_out = Linear(SiLU(emb))  [openaimodel.py:264]
-  float* eo = c.alloc_t<float>((size_t)N * r.cout);
-  linear_small(c, emb, 1280, N, r.emb, eo, r.cout, /*act_in=silu*/ 1, 0);
+static Tens run_res(Ctx& c, const ResW& r, const Tens& x, const float* emb, int emb_rows) {
+  // emb_out = Linear(SiLU(emb))  [openaimodel.py:264]; emb_rows == 1 when every sample shares the timestep
+  float* eo = c.alloc_t<float>((size_t)emb_rows * r.cout);
+  linear_small(c, emb, r.emb.in, emb_rows, r.emb, eo, r.cout, /*act_in=silu*/ 1, 0);
   Tens h = groupnorm(c, x, r.g1, r.b1, 1e-5f, true);
   Epi e1;
-  e1.rowvec = eo, e1.ldv = r.cout;
+  e1.rowvec = eo, e1.ldv = emb_rows == 1 ? 0 : r.cout;
   Tens h1 = conv3x3_t(c, h, r.c1, e1);
   Tens h2 = groupnorm(c, h1, r.g2, r.b2, 1e-5f, true);
   Tens skip = x;
@@ -166,7 +166,17 @@ static Tens run_res(Ctx& c, const ResW& r, const Tens& x, const float* emb, int 
   return conv3x3_t(c, h2, r.c2, e2);
 }
 
-static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T, int N) {
+// attn2 with a single context token: softmax over one key is exactly 1, so the block adds
+// to_out(to_v(ctx[n])) to every token (attention.py:206-221); the vector depends on the context only.
+static float* cross_vec(Ctx& c, const STW& s, const float* ctx, int N) {
+  float* v = c.alloc_t<float>((size_t)N * s.c);
+  float* vec = c.alloc_t<float>((size_t)N * s.c);
+  linear_small(c, ctx, s.ctx_dim, N, s.v2, v, s.c, 0, 0);
+  linear_small(c, v, s.c, N, s.o2, vec, s.c, 0, 0);
+  return vec;
+}
+
+static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T, int N, const float* vec_pre) {
   const int C = s.c;
   Tens xn = groupnorm(c, x, s.gn_g, s.gn_b, 1e-6f, false);
   Tens h = conv3x3_t(c, xn, s.proj_in, Epi(), 1, 0, 0, 0, 0);
@@ -178,12 +188,8 @@ static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T,
   attention(c, qkv.p, 3 * C, N, L, s.heads, s.d, a.p, C, 1.0f / sqrtf((float)s.d), 0, C, 2 * C);
   Tens h1;
   if (T == 1) {
-    // --- attn2 with a single context token: softmax over one key is exactly 1, so the block adds
-    // to_out(to_v(ctx[n])) to every token (attention.py:206-221).  Folded into attn1's out-projection epilogue.
-    float* v = c.alloc_t<float>((size_t)N * C);
-    float* vec = c.alloc_t<float>((size_t)N * C);
-    linear_small(c, ctx, s.ctx_dim, N, s.v2, v, C, 0, 0);
-    linear_small(c, v, C, N, s.o2, vec, C, 0, 0);
+    // --- attn2 (degenerate, see cross_vec) folded into attn1's out-projection epilogue
+    const float* vec = vec_pre ? vec_pre : cross_vec(c, s, ctx, N);
     Epi e;
     e.res = h.p, e.ldr = C, e.rowvec = vec, e.ldv = C, e.rows_per_vec = L;
     h1 = linear_t(c, a, s.o1, e);
@@ -214,11 +220,24 @@ Tens cross_attention_general(Ctx& c, const STW& s, const Tens& x, const float* c
   throw std::runtime_error("cross-attention with context length > 1 is not implemented yet (shipped config uses T=1)");
 }
 
-static Tens run_ops(Ctx& c, const std::vector<UOp>& ops, Tens h, const float* emb, const float* ctx, int T, int N) {
+struct RunState {
+  const float* emb;
+  int emb_rows;
+  const float* ctx;
+  int T, N;
+  const UNetAux* aux;
+  int st_idx;
+};
+
+static Tens run_ops(Ctx& c, const std::vector<UOp>& ops, Tens h, RunState& rs) {
   for (const UOp& op : ops) {
     switch (op.kind) {
-      case OP_RES: h = run_res(c, op.res, h, emb, N); break;
-      case OP_ATTN: h = run_st(c, op.st, h, ctx, T, N); break;
+      case OP_RES: h = run_res(c, op.res, h, rs.emb, rs.emb_rows); break;
+      case OP_ATTN: {
+        const float* pre = (rs.aux && rs.st_idx < (int)rs.aux->crossvec.size()) ? rs.aux->crossvec[rs.st_idx] : nullptr;
+        h = run_st(c, op.st, h, rs.ctx, rs.T, rs.N, pre);
+        ++rs.st_idx;
+      } break;
       case OP_DOWN: h = conv3x3_t(c, h, op.conv, Epi(), 2, 1, 1, 1, 1); break;
       case OP_UP: h = conv3x3_t(c, upsample2x(c, h), op.conv, Epi()); break;
       case OP_CONV_IN: h = conv3x3_t(c, h, op.conv, Epi()); break;
@@ -228,27 +247,43 @@ static Tens run_ops(Ctx& c, const std::vector<UOp>& ops, Tens h, const float* em
 }
 
 // x9: [N,9,L,L] fp32 NCHW, t: [N] int64, ctx: [N,T,768] fp32 (all device) -> eps [N,4,L,L] fp32 NCHW
+std::vector<const float*> unet_cross_vectors(Ctx& c, UNet& u, const float* ctx, int N, int T) {
+  std::vector<const float*> out;
+  if (T != 1) return out;
+  auto visit = [&](const std::vector<UOp>& ops) {
+    for (const UOp& op : ops)
+      if (op.kind == OP_ATTN) out.push_back(cross_vec(c, op.st, ctx, N));
+  };
+  for (auto& ops : u.inp) visit(ops);
+  visit(u.mid);
+  for (auto& ops : u.out) visit(ops);
+  return out;
+}
+
 void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const float* ctx, int N, int L, int T,
-                  float* eps) {
+                  float* eps, const UNetAux* aux) {
   const size_t mk = c.mark();
   const int mc = u.cfg.model_channels;
-  float* temb = c.alloc_t<float>((size_t)N * mc);
-  float* e1 = c.alloc_t<float>((size_t)N * 4 * mc);
-  float* emb = c.alloc_t<float>((size_t)N * 4 * mc);
-  timestep_embedding(c, t, temb, N, mc);
-  linear_small(c, temb, mc, N, u.te0, e1, 4 * mc, 0, /*silu*/ 1);
-  linear_small(c, e1, 4 * mc, N, u.te2, emb, 4 * mc, 0, 0);
+  // time embedding MLP (openaimodel.py:874-875); one row is enough when all samples share the timestep
+  const int er = (aux && aux->uniform_t) ? 1 : N;
+  float* temb = c.alloc_t<float>((size_t)er * mc);
+  float* e1 = c.alloc_t<float>((size_t)er * 4 * mc);
+  float* emb = c.alloc_t<float>((size_t)er * 4 * mc);
+  timestep_embedding(c, t, temb, er, mc);
+  linear_small(c, temb, mc, er, u.te0, e1, 4 * mc, 0, /*silu*/ 1);
+  linear_small(c, e1, 4 * mc, er, u.te2, emb, 4 * mc, 0, 0);
+  RunState rs{emb, er, ctx, T, N, aux, 0};
   Tens h = from_nchw_f32(c, x9, N, u.cfg.in_channels, L, L, u.cfg.in_channels);
   std::vector<Tens> hs;
   for (auto& ops : u.inp) {
-    h = run_ops(c, ops, h, emb, ctx, T, N);
+    h = run_ops(c, ops, h, rs);
     hs.push_back(h);
   }
-  h = run_ops(c, u.mid, h, emb, ctx, T, N);
+  h = run_ops(c, u.mid, h, rs);
   for (auto& ops : u.out) {
     Tens cat = concat_c(c, h, hs.back());
     hs.pop_back();
-    h = run_ops(c, ops, cat, emb, ctx, T, N);
+    h = run_ops(c, ops, cat, rs);
   }
   Tens hn = groupnorm(c, h, u.out_g, u.out_b, 1e-5f, true);
   Epi e;
@@ -288,11 +323,16 @@ void ddim_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, cons
     CUDA_OK(cudaMemcpyAsync(ctx, cond, cb, cudaMemcpyDeviceToDevice, c.stream));
   }
   CUDA_OK(cudaMemcpyAsync(xa, x_T, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  // step-invariant terms, computed once per sampling run: the cross-attention vectors depend on
+  // the context only; every sample shares the step's timestep, so one time-embedding row serves the batch.
+  UNetAux aux;
+  aux.uniform_t = 1;
+  aux.crossvec = unet_cross_vectors(c, u, ctx, N, T);
   int n_inter = 0;
   for (int i = 0; i < s.n; ++i) {
     const int index = s.n - 1 - i;
     concat9(c, xa, z_inpaint, mask, x9, B, (int)HW, dup);
-    unet_forward(c, u, x9, ts + (size_t)index * N, ctx, N, L, T, eps);
+    unet_forward(c, u, x9, ts + (size_t)index * N, ctx, N, L, T, eps, &aux);
     cfg_ddim_update(c, xa, eps, noise ? noise + (size_t)i * cnt : nullptr, xb, p0, cnt, scale, s.a_t[index],
                     s.a_prev[index], s.sigma[index], s.sqrt_one_minus_a[index], cfg ? 1 : 0);
     std::swap(xa, xb);

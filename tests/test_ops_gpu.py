@@ -98,10 +98,16 @@ def test_layernorm(engine, rows, C):
 
 @pytest.mark.parametrize("N,L,heads,d", [(2, 256, 8, 40), (1, 1024, 8, 80), (2, 64, 8, 160), (1, 257, 16, 64),
                                          (1, 256, 1, 512), (2, 16, 8, 40), (1, 4096, 8, 40)])
-def test_attention(engine, N, L, heads, d):
+@pytest.mark.parametrize("flash", [0, 1])
+def test_attention(engine, N, L, heads, d, flash):
+    """flash=1: fused tcgen05 kernel where the shape allows (d in {40,80}, L % 128 == 0); flash=0: S/P materialised."""
     C = heads * d
     qkv = h(rn(N, L, 3 * C, seed=1))
-    y = engine.op_attention(qkv, heads)
+    engine.set_option("attn_flash", flash)
+    try:
+        y = engine.op_attention(qkv, heads)
+    finally:
+        engine.set_option("attn_flash", 1)
     q, k, v = qkv.chunk(3, dim=-1)
     sp = lambda t: t.reshape(N, L, heads, d).transpose(1, 2)
     ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(N, L, C)
