@@ -139,6 +139,7 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "gemm_smem_budget") c.gemm_smem_budget = (int)value;
   else if (k == "attn_flash") c.attn_flash = (int)value;
   else if (k == "profile") c.profile = (int)value;
+  else if (k == "gemm_persistent") c.gemm_persistent = (int)value;
   else return -1;
   return 0;
 }

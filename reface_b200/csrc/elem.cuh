@@ -148,17 +148,53 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
       }
     }
   }
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
-  if (pr < R) {
+  // deterministic in-block reduction over the R pixel rows (fixed order, no atomics): results must not depend
+  // on the batch size or on scheduling (multi-GPU shards have to reproduce the single-GPU bits)
+  float* shp = sh + (size_t)pr * 2 * C + (size_t)cq * 16;  // sh: [R][2*C]
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[2 * (cq * 8 + j)], s[j]);
-      atomicAdd(&sh[2 * (cq * 8 + j) + 1], ss[j]);
-    }
+  for (int j = 0; j < 8; ++j) {
+    shp[2 * j] = s[j];
+    shp[2 * j + 1] = ss[j];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[(long long)n * 2 * C + i], sh[i]);
+  // partial[n][slab][2*C]
+  float* dst = stats + ((long long)n * gridDim.x + blockIdx.x) * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float a = 0.f;
+    for (int rr = 0; rr < R; ++rr) a += sh[(size_t)rr * 2 * C + i];
+    dst[i] = a;
+  }
+}
+// Phase 1b: fold the per-slab partials in a fixed order -> mean / rstd per (n, group): out[n][G][2]
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int nslab, int HW, int C,
+                                   int G, float eps) {
+  const int n = blockIdx.x;
+  const int cpg = C / G;
+  // 8 threads per group (blockDim = 8*G): thread t folds slabs t, t+8, ...; the 8 partials are then combined by a
+  // fixed shuffle tree -> bitwise reproducible
+  const int gi = threadIdx.x >> 3, t = threadIdx.x & 7;
+  float s = 0.f, ss = 0.f;
+  if (gi < G) {
+    for (int sl = t; sl < nslab; sl += 8) {
+      const float* p = partial + ((long long)n * nslab + sl) * 2 * C;
+      for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+        s += p[2 * c];
+        ss += p[2 * c + 1];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (gi < G && t == 0) {
+    const float cnt = (float)cpg * (float)HW;
+    const float mean = s / cnt;
+    const float var = fmaxf(ss / cnt - mean * mean, 0.f);
+    out[((long long)n * G + gi) * 2] = mean;
+    out[((long long)n * G + gi) * 2 + 1] = rsqrtf(var + eps);
+  }
 }
 // Phase 2: y = x*a[n,c] + b[n,c] [* sigmoid] with a = rstd*gamma, b = beta - mean*rstd*gamma staged in smem.
 // blockDim = (C/8)*R like phase 1: a thread keeps its 8 channels (a/b in registers) and walks over pixels.
@@ -168,18 +204,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
   extern __shared__ float sh[];  // [2*G] mean/rstd
   const int n = blockIdx.y;
   const int cpg = C / G;
-  for (int gidx = threadIdx.x; gidx < G; gidx += blockDim.x) {
-    float s = 0.f, ss = 0.f;
-    for (int c = gidx * cpg; c < (gidx + 1) * cpg; ++c) {
-      s += stats[((long long)n * C + c) * 2];
-      ss += stats[((long long)n * C + c) * 2 + 1];
-    }
-    const float cnt = (float)cpg * (float)HW;
-    const float mean = s / cnt;
-    const float var = fmaxf(ss / cnt - mean * mean, 0.f);
-    sh[2 * gidx] = mean;
-    sh[2 * gidx + 1] = rsqrtf(var + eps);
-  }
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = stats[(long long)n * 2 * G + i];  // mean, rstd
   __syncthreads();
   const int cv = C >> 3;
   const int R = blockDim.x / cv;

@@ -7,7 +7,7 @@
 #include <cstring>
 
 #include "elem.cuh"
-#include "gemm_tc.cuh"
+#include "gemm_persist.cuh"
 
 namespace rfb {
 
@@ -194,7 +194,31 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     rec.kind = 0;
     CUDA_OK(cudaEventRecord(rec.a, c.stream));
   }
-  gemm_tc_kernel<<<grid, GEMM_THREADS, smem, c.stream>>>(tmA, tmB, g);
+  if (c.gemm_persistent) {
+    // persistent, double-buffered-accumulator kernel: one CTA per SM, deep smem ring
+    static bool attr2 = false;
+    if (!attr2) {
+      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr2 = true;
+    }
+    int ps = c.force_stages ? c.force_stages : std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+    g.stages = ps;
+    const size_t psmem = gemmp_smem_bytes(ps, g.BN);
+    RFB_CHECK(psmem <= 227 * 1024, "GEMM smem over budget");
+    const int m_tiles = (int)grid.x, n_tiles = (int)grid.y;
+    const int total = m_tiles * n_tiles * (int)grid.z;
+    const int ctas = std::min(total, c.num_sms);
+    if (g.geglu)
+      gemm_persist_kernel<EPI_GEGLU><<<ctas, GEMMP_THREADS, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
+    else if (g.act == 0 && g.out32 == nullptr && g.alpha == 1.0f)
+      gemm_persist_kernel<EPI_FAST><<<ctas, GEMMP_THREADS, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
+    else
+      gemm_persist_kernel<EPI_GENERIC><<<ctas, GEMMP_THREADS, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
+  } else {
+    gemm_tc_kernel<<<grid, GEMM_THREADS, smem, c.stream>>>(tmA, tmB, g);
+  }
   LAUNCH_CHECK(c);
   if (c.profile) {
     CUDA_OK(cudaEventRecord(rec.b, c.stream));
@@ -371,13 +395,16 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
   const size_t mk = c.mark();
   const int HW = x.h * x.w, C = x.c, cv = C / 8;
   RFB_CHECK(cv <= 1024, "GroupNorm: too many channels");
-  float* stats = c.alloc_t<float>((size_t)x.n * C * 2);
-  CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)x.n * C * 2 * sizeof(float), c.stream));
   const int R = std::max(1, 512 / cv);
-  const int want_blocks = std::max(1, (4 * c.num_sms) / std::max(1, x.n));
-  int slab = std::max(R, (HW + want_blocks - 1) / want_blocks);
-  dim3 g1((unsigned)((HW + slab - 1) / slab), (unsigned)x.n);
-  gn_stats_kernel<<<g1, cv * R, 2 * C * sizeof(float), c.stream>>>(x.p, stats, HW, C, slab);
+  // the slab partition depends on the tensor shape only (never on the batch size): bitwise batch-independence
+  const int slab = std::max(R, (HW + 63) / 64);
+  const int nslab = (HW + slab - 1) / slab;
+  float* partial = c.alloc_t<float>((size_t)x.n * nslab * C * 2);
+  float* stats = c.alloc_t<float>((size_t)x.n * 32 * 2);
+  dim3 g1((unsigned)nslab, (unsigned)x.n);
+  gn_stats_kernel<<<g1, cv * R, (size_t)R * 2 * C * sizeof(float), c.stream>>>(x.p, partial, HW, C, slab);
+  LAUNCH_CHECK(c);
+  gn_finalize_kernel<<<(unsigned)x.n, 8 * 32, 0, c.stream>>>(partial, stats, nslab, HW, C, 32, eps);
   LAUNCH_CHECK(c);
   const int want2 = std::max(1, (8 * c.num_sms) / std::max(1, x.n));
   const int slab2 = std::max(R, (HW + want2 - 1) / want2);
