@@ -123,8 +123,9 @@ __global__ void concat_c_kernel(const __half* __restrict__ a, const __half* __re
 // ------------------------------------------------------------------ GroupNorm (fp32 statistics)
 // Phase 1: per-(n, channel) sum / sum of squares over a slab of pixels -> atomics into stats[n][C][2].
 // blockDim = (C/8) * R; thread (pr, cq) owns 8 channels and pixel rows pr, pr+R, ...
-__global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ stats, int HW, int C, int slab) {
-  extern __shared__ float sh[];  // [2*C]
+__global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ stats, int HW, int C, int slab,
+                                int G) {
+  extern __shared__ float sh[];  // [R][2*C] + [2*C]
   const int cv = C >> 3;
   const int R = blockDim.x / cv;
   const int cq = threadIdx.x % cv, pr = threadIdx.x / cv;
@@ -157,12 +158,20 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
     shp[2 * j + 1] = ss[j];
   }
   __syncthreads();
-  // partial[n][slab][2*C]
-  float* dst = stats + ((long long)n * gridDim.x + blockIdx.x) * 2 * C;
+  float* chs = sh + (size_t)R * 2 * C;  // [2*C] per-channel sums of this slab
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     float a = 0.f;
     for (int rr = 0; rr < R; ++rr) a += sh[(size_t)rr * 2 * C + i];
-    dst[i] = a;
+    chs[i] = a;
+  }
+  __syncthreads();
+  // partial[n][slab][G][2]: channels of a group folded in channel order
+  const int cpg = C / G;
+  if (threadIdx.x < 2 * G) {
+    const int gi = threadIdx.x >> 1, which = threadIdx.x & 1;
+    float a = 0.f;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) a += chs[2 * c + which];
+    stats[((long long)n * gridDim.x + blockIdx.x) * 2 * G + threadIdx.x] = a;
   }
 }
 // Phase 1b: fold the per-slab partials in a fixed order -> mean / rstd per (n, group): out[n][G][2]
@@ -176,11 +185,9 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __r
   float s = 0.f, ss = 0.f;
   if (gi < G) {
     for (int sl = t; sl < nslab; sl += 8) {
-      const float* p = partial + ((long long)n * nslab + sl) * 2 * C;
-      for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
-        s += p[2 * c];
-        ss += p[2 * c + 1];
-      }
+      const float2 v = *reinterpret_cast<const float2*>(partial + (((long long)n * nslab + sl) * G + gi) * 2);
+      s += v.x;
+      ss += v.y;
     }
   }
 #pragma unroll

@@ -399,10 +399,10 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
   // the slab partition depends on the tensor shape only (never on the batch size): bitwise batch-independence
   const int slab = std::max(R, (HW + 63) / 64);
   const int nslab = (HW + slab - 1) / slab;
-  float* partial = c.alloc_t<float>((size_t)x.n * nslab * C * 2);
+  float* partial = c.alloc_t<float>((size_t)x.n * nslab * 32 * 2);
   float* stats = c.alloc_t<float>((size_t)x.n * 32 * 2);
   dim3 g1((unsigned)nslab, (unsigned)x.n);
-  gn_stats_kernel<<<g1, cv * R, (size_t)R * 2 * C * sizeof(float), c.stream>>>(x.p, partial, HW, C, slab);
+  gn_stats_kernel<<<g1, cv * R, (size_t)(R + 1) * 2 * C * sizeof(float), c.stream>>>(x.p, partial, HW, C, slab, 32);
   LAUNCH_CHECK(c);
   gn_finalize_kernel<<<(unsigned)x.n, 8 * 32, 0, c.stream>>>(partial, stats, nslab, HW, C, 32, eps);
   LAUNCH_CHECK(c);

@@ -17,7 +17,7 @@ struct ResW {
   ConvW c1, c2, skipw;
   Lin32 emb;
   bool skip = false;
-  int cin = 0, cout = 0;
+  int cin = 0, cout = 0, emb_off = 0;  // emb_off: column of this block in the concatenated emb_layers output
 };
 struct STW {
   const float *gn_g = nullptr, *gn_b = nullptr, *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr,
@@ -39,7 +39,7 @@ struct UNet {
   std::string pfx;
   std::vector<std::vector<UOp>> inp, out;
   std::vector<UOp> mid;
-  Lin32 te0, te2;
+  Lin32 te0, te2, emb_cat;
   const float *out_g = nullptr, *out_b = nullptr;
   ConvW out_conv;
 };

@@ -143,6 +143,30 @@ UNet* build_unet(Ctx& c, const std::string& pfx, const UNetCfg& cfg) {
       ++idx;
     }
   }
+  // all 22 ResBlock emb_layers (Linear(1280 -> Cout) on SiLU(emb)) share their input: concatenate them so that
+  // one launch per forward produces every block's time-embedding row
+  {
+    std::vector<ResW*> rs;
+    auto visit = [&](std::vector<UOp>& ops) {
+      for (UOp& op : ops)
+        if (op.kind == OP_RES) rs.push_back(&op.res);
+    };
+    for (auto& ops : u->inp) visit(ops);
+    visit(u->mid);
+    for (auto& ops : u->out) visit(ops);
+    int total = 0;
+    for (ResW* r : rs) r->emb_off = total, total += r->emb.out;
+    const int in = rs.empty() ? 0 : rs[0]->emb.in;
+    float* w = (float*)c.dmalloc((size_t)total * in * sizeof(float));
+    float* b = (float*)c.dmalloc((size_t)total * sizeof(float));
+    for (ResW* r : rs) {
+      CUDA_OK(cudaMemcpyAsync(w + (size_t)r->emb_off * in, r->emb.w, (size_t)r->emb.out * in * sizeof(float),
+                              cudaMemcpyDeviceToDevice, c.stream));
+      CUDA_OK(cudaMemcpyAsync(b + r->emb_off, r->emb.b, (size_t)r->emb.out * sizeof(float), cudaMemcpyDeviceToDevice,
+                              c.stream));
+    }
+    u->emb_cat.w = w, u->emb_cat.b = b, u->emb_cat.in = in, u->emb_cat.out = total;
+  }
   u->out_g = c.pf(pfx + "out.0.weight"), u->out_b = c.pf(pfx + "out.0.bias");
   u->out_conv = pack_conv(c, pfx + "out.2.weight", pfx + "out.2.bias");
   CUDA_OK(cudaStreamSynchronize(c.stream));
@@ -150,13 +174,12 @@ UNet* build_unet(Ctx& c, const std::string& pfx, const UNetCfg& cfg) {
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-static Tens run_res(Ctx& c, const ResW& r, const Tens& x, const float* emb, int emb_rows) {
-  // emb_out = Linear(SiLU(emb))  [openaimodel.py:264]; emb_rows == 1 when every sample shares the timestep
-  float* eo = c.alloc_t<float>((size_t)emb_rows * r.cout);
-  linear_small(c, emb, r.emb.in, emb_rows, r.emb, eo, r.cout, /*act_in=silu*/ 1, 0);
+static Tens run_res(Ctx& c, const ResW& r, const Tens& x, const float* emb_all, int emb_rows, int emb_ld) {
+  // emb_out = Linear(SiLU(emb)) [openaimodel.py:264] was computed for all blocks at once (emb_all: [rows, emb_ld]);
+  // emb_rows == 1 when every sample shares the timestep
   Tens h = groupnorm(c, x, r.g1, r.b1, 1e-5f, true);
   Epi e1;
-  e1.rowvec = eo, e1.ldv = emb_rows == 1 ? 0 : r.cout;
+  e1.rowvec = emb_all + r.emb_off, e1.ldv = emb_rows == 1 ? 0 : emb_ld;
   Tens h1 = conv3x3_t(c, h, r.c1, e1);
   Tens h2 = groupnorm(c, h1, r.g2, r.b2, 1e-5f, true);
   Tens skip = x;
@@ -221,8 +244,8 @@ Tens cross_attention_general(Ctx& c, const STW& s, const Tens& x, const float* c
 }
 
 struct RunState {
-  const float* emb;
-  int emb_rows;
+  const float* emb;  // every ResBlock's emb_layers output: [emb_rows, emb_ld]
+  int emb_rows, emb_ld;
   const float* ctx;
   int T, N;
   const UNetAux* aux;
@@ -232,7 +255,7 @@ struct RunState {
 static Tens run_ops(Ctx& c, const std::vector<UOp>& ops, Tens h, RunState& rs) {
   for (const UOp& op : ops) {
     switch (op.kind) {
-      case OP_RES: h = run_res(c, op.res, h, rs.emb, rs.emb_rows); break;
+      case OP_RES: h = run_res(c, op.res, h, rs.emb, rs.emb_rows, rs.emb_ld); break;
       case OP_ATTN: {
         const float* pre = (rs.aux && rs.st_idx < (int)rs.aux->crossvec.size()) ? rs.aux->crossvec[rs.st_idx] : nullptr;
         h = run_st(c, op.st, h, rs.ctx, rs.T, rs.N, pre);
@@ -272,7 +295,9 @@ void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const fl
   timestep_embedding(c, t, temb, er, mc);
   linear_small(c, temb, mc, er, u.te0, e1, 4 * mc, 0, /*silu*/ 1);
   linear_small(c, e1, 4 * mc, er, u.te2, emb, 4 * mc, 0, 0);
-  RunState rs{emb, er, ctx, T, N, aux, 0};
+  float* emb_all = c.alloc_t<float>((size_t)er * u.emb_cat.out);
+  linear_small(c, emb, 4 * mc, er, u.emb_cat, emb_all, u.emb_cat.out, /*act_in=silu*/ 1, 0);
+  RunState rs{emb_all, er, u.emb_cat.out, ctx, T, N, aux, 0};
   Tens h = from_nchw_f32(c, x9, N, u.cfg.in_channels, L, L, u.cfg.in_channels);
   std::vector<Tens> hs;
   for (auto& ops : u.inp) {
