@@ -152,8 +152,8 @@ def main():
         flat = synth.random_flat(dev, seed=0)
     else:
         flat = torch.empty(synth.flat_layout()[1], dtype=torch.float32, device=dev)
-    if world > 1:
-        dist.broadcast(flat, 0)
+    from reface_b200 import shard
+    shard.broadcast_checkpoint(flat, 0)
     eng = Engine(local)
     model = LatentDiffusion(synth.state_dict_from_flat(flat), engine=eng)
     del flat
