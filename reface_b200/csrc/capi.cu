@@ -140,6 +140,7 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "attn_flash") c.attn_flash = (int)value;
   else if (k == "profile") c.profile = (int)value;
   else if (k == "gemm_persistent") c.gemm_persistent = (int)value;
+  else if (k == "gemm_pair") c.gemm_pair = (int)value;
   else return -1;
   return 0;
 }

@@ -7,7 +7,7 @@
 #include <cstring>
 
 #include "elem.cuh"
-#include "gemm_persist.cuh"
+#include "gemm_pair.cuh"
 
 namespace rfb {
 
@@ -168,7 +168,9 @@ int pick_bn(Ctx& c, long long M, int N, bool geglu) {
   return best;
 }
 
-static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, dim3 grid, double kalg) {
+// Bplain/kp/nrows_w: the plain 2-D weight operand (lets the 2-CTA kernel rebuild the B map with a half-height box)
+static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, dim3 grid, double kalg,
+                        const __half* Bplain = nullptr, int kp = 0, int nrows_w = 0) {
   const int stage_bytes = GEMM_A_STAGE_BYTES + g.BN * 128;
   int stages = c.force_stages ? c.force_stages : std::max(2, std::min(6, c.gemm_smem_budget / stage_bytes));
   stages = std::min(stages, std::max(1, g.nk));
@@ -194,7 +196,46 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     rec.kind = 0;
     CUDA_OK(cudaEventRecord(rec.a, c.stream));
   }
-  if (c.gemm_persistent) {
+  const bool pair_ok = c.gemm_pair && c.gemm_persistent && Bplain != nullptr && grid.z == 1 && grid.x >= 2 &&
+                       (g.a_mode == A_PLAIN || g.a_mode == A_CONV3) && g.b_mode == B_PLAIN &&
+                       (long long)grid.x * grid.y >= c.num_sms / 2;
+  if (pair_ok) {
+    // 2-CTA pairs (cta_group::2): each CTA loads its 128 A rows and half of the B tile
+    static bool attr3 = false;
+    if (!attr3) {
+      CUDA_OK(cudaFuncSetAttribute(gemm_pair_kernel<EPI_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CUDA_OK(cudaFuncSetAttribute(gemm_pair_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CUDA_OK(cudaFuncSetAttribute(gemm_pair_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr3 = true;
+    }
+    const int sb2 = GEMM_A_STAGE_BYTES + (g.BN / 2) * 128;
+    g.stages = c.force_stages ? c.force_stages : std::max(2, std::min(8, (200 * 1024) / sb2));
+    const size_t psmem = gemm2_smem_bytes(g.stages, g.BN);
+    RFB_CHECK(psmem <= 227 * 1024, "GEMM smem over budget");
+    const uint64_t db[2] = {(uint64_t)kp, (uint64_t)nrows_w};
+    const uint64_t sb[1] = {(uint64_t)kp * 2};
+    const uint32_t bb[2] = {64, (uint32_t)(g.BN / 2)};
+    CUtensorMap tmB2 = make_tmap(c, Bplain, 2, db, sb, bb);
+    const int m_pairs = ((int)grid.x + 1) / 2, n_tiles = (int)grid.y;
+    const int total_pairs = m_pairs * n_tiles;
+    const int pairs = std::min(total_pairs, c.num_sms / 2);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(GEMMP_THREADS);
+    cfg.dynamicSmemBytes = psmem;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    if (g.geglu)
+      CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI_GEGLU>, tmA, tmB2, g, m_pairs, n_tiles, total_pairs));
+    else if (g.act == 0 && g.out32 == nullptr && g.alpha == 1.0f)
+      CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI_FAST>, tmA, tmB2, g, m_pairs, n_tiles, total_pairs));
+    else
+      CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI_GENERIC>, tmA, tmB2, g, m_pairs, n_tiles, total_pairs));
+  } else if (c.gemm_persistent) {
     // persistent, double-buffered-accumulator kernel: one CTA per SM, deep smem ring
     static bool attr2 = false;
     if (!attr2) {
@@ -251,7 +292,7 @@ void gemm(Ctx& c, const __half* A, long long lda, long long M, int K, const __ha
   CUtensorMap tmA = make_tmap(c, A, 2, da, sa, ba);
   CUtensorMap tmB = make_tmap(c, W, 2, db, sb, bb);
   dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + g.BN - 1) / g.BN), 1);
-  launch_gemm(c, tmA, tmB, g, grid, (double)(kalg > 0 ? kalg : K));
+  launch_gemm(c, tmA, tmB, g, grid, (double)(kalg > 0 ? kalg : K), W, kp, nrows_w);
 }
 
 Tens linear_t(Ctx& c, const Tens& x, const LinW& w, Epi e) {
@@ -309,7 +350,7 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
     CUtensorMap tmA = make_tmap(c, x.p, 4, da, sa, ba);
     CUtensorMap tmB = make_tmap(c, w.w, 2, db, sb, bb);
     dim3 grid((unsigned)((M + 127) / 128), (unsigned)((w.cout + g.BN - 1) / g.BN), 1);
-    launch_gemm(c, tmA, tmB, g, grid, 9.0 * w.cin);
+    launch_gemm(c, tmA, tmB, g, grid, 9.0 * w.cin, w.w, w.kp, round_up(w.cout, 32));
     return y;
   }
   // generic path: explicit im2col then a plain GEMM

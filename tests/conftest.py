@@ -50,6 +50,9 @@ def engine():
     from reface_b200.runtime import Engine
     assert torch.cuda.is_available(), "gpu tests need a GPU"
     eng = Engine(0, arena_bytes=24 << 30)
+    for k, v in os.environ.items():          # e.g. RFB_GEMM_PAIR=0 to A/B a kernel generation
+        if k.startswith("RFB_") and k != "RFB_CPU_THREADS":
+            eng.set_option(k[4:].lower(), int(v))
     yield eng
     eng.close()
 
