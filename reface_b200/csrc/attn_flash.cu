@@ -40,7 +40,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   using Cfg = FlashCfg<DP>;
   constexpr int NC = Cfg::NC;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index via shuffle = provably warp-uniform: TMA / MMA operands stay in uniform registers (no R2UR per issue)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();  // 128-byte swizzle atoms need a 1024-byte aligned tile base
   const uint32_t sQ = base;
@@ -80,56 +81,65 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
       mbar_expect_tx(b_q, Cfg::Q_BYTES);
       for (int c = 0; c < NC; ++c) tma_load_4d(sQ + c * Cfg::CHUNK, &tmQ, b_q, c * 64, head, qt * 128, n);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-        mbar_wait(b_ke + 8 * s, ph ^ 1u);
+    }
+    __syncwarp();
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+      mbar_wait(b_ke + 8 * s, ph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(b_kf + 8 * s, Cfg::KV_BYTES);
         for (int c = 0; c < NC; ++c)
           tma_load_4d(sK + s * Cfg::KV_BYTES + c * Cfg::CHUNK, &tmK, b_kf + 8 * s, c * 64, head, j * 128, n);
-        mbar_wait(b_ve + 8 * s, ph ^ 1u);
+      }
+      __syncwarp();
+      mbar_wait(b_ve + 8 * s, ph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(b_vf + 8 * s, Cfg::KV_BYTES);
         for (int c = 0; c < NC; ++c)
           tma_load_4d(sV + s * Cfg::KV_BYTES + c * Cfg::CHUNK, &tmV, b_vf + 8 * s, c * 64, head, j * 128, n);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = idesc_f16(128, 128);
-      const uint32_t idesc_o = idesc_f16(128, DP, 0, 1);  // B (= V) is MN-major
-      mbar_wait(b_q, 0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-        // ---- S = Q K^T
-        mbar_wait(b_kf + 8 * s, ph);
-        if (j > 0) mbar_wait(b_sfree, (uint32_t)(j - 1) & 1u);
-        tc_fence_after();
-        {
-          int first = 1;
+    const uint32_t idesc_s = idesc_f16(128, 128);
+    const uint32_t idesc_o = idesc_f16(128, DP, 0, 1);  // B (= V) is MN-major
+    mbar_wait(b_q, 0);
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+      // ---- S = Q K^T
+      mbar_wait(b_kf + 8 * s, ph);
+      if (j > 0) mbar_wait(b_sfree, (uint32_t)(j - 1) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        int first = 1;
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            const int ksteps = (c == NC - 1) ? ((DP - c * 64) + 15) / 16 : 4;
-            const uint64_t da = smem_desc_k_sw128(sQ + c * Cfg::CHUNK);
-            const uint64_t db = smem_desc_k_sw128(sK + s * Cfg::KV_BYTES + c * Cfg::CHUNK);
-            for (int k = 0; k < ksteps; ++k) {
-              mma_f16_ss(tS, da + 2u * k, db + 2u * k, idesc_s, first ? 0u : 1u);
-              first = 0;
-            }
+        for (int c = 0; c < NC; ++c) {
+          const int ksteps = (c == NC - 1) ? ((DP - c * 64) + 15) / 16 : 4;
+          const uint64_t da = smem_desc_k_sw128(sQ + c * Cfg::CHUNK);
+          const uint64_t db = smem_desc_k_sw128(sK + s * Cfg::KV_BYTES + c * Cfg::CHUNK);
+#pragma unroll
+          for (int k = 0; k < ksteps; ++k) {
+            mma_f16_ss(tS, da + 2u * k, db + 2u * k, idesc_s, first ? 0u : 1u);
+            first = 0;
           }
         }
         mma_commit(b_ke + 8 * s);
         mma_commit(b_sfull);
-        // ---- O_j = P V
-        mbar_wait(b_vf + 8 * s, ph);
-        mbar_wait(b_pfull, (uint32_t)j & 1u);
-        tc_fence_after();
+      }
+      __syncwarp();
+      // ---- O_j = P V
+      mbar_wait(b_vf + 8 * s, ph);
+      mbar_wait(b_pfull, (uint32_t)j & 1u);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t da = smem_desc_k_sw128(sP + (k >> 2) * Cfg::CHUNK) + 2u * (k & 3);
@@ -140,6 +150,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mma_commit(b_ve + 8 * s);
         mma_commit(b_ofull);
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ softmax / accumulate warps

@@ -141,10 +141,20 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "profile") c.profile = (int)value;
   else if (k == "gemm_persistent") c.gemm_persistent = (int)value;
   else if (k == "gemm_pair") c.gemm_pair = (int)value;
+  else if (k == "gemm_kmerge") c.gemm_kmerge = (int)value;
+  else if (k == "gemm_debug") c.gemm_debug = (int)value;
   else return -1;
   return 0;
 }
 long long rfb_launch_count(rfb_ctx* h) { return h ? h->c.launches : 0; }
+int rfb_debug_read(rfb_ctx* h, unsigned long long* out, int n) {
+  API_BEGIN(h)
+  RFB_CHECK(c.dbg_buf, "option gemm_debug was never enabled");
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(out, c.dbg_buf, (size_t)std::min(n, c.num_sms * 8) * sizeof(unsigned long long),
+                     cudaMemcpyDeviceToHost));
+  API_END
+}
 int rfb_profile_read(rfb_ctx* h, double* ms, double* flops, long long* n) {
   API_BEGIN(h)
   CUDA_OK(cudaDeviceSynchronize());

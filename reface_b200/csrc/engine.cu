@@ -208,14 +208,22 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
       CUDA_OK(cudaFuncSetAttribute(gemm_pair_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr3 = true;
     }
-    const int sb2 = GEMM_A_STAGE_BYTES + (g.BN / 2) * 128;
+    g.kmerge = (c.gemm_kmerge >= 2 && g.nk >= 4) ? 2 : 1;
+    const int sb2 = g.kmerge * (GEMM_A_STAGE_BYTES + (g.BN / 2) * 128);
     g.stages = c.force_stages ? c.force_stages : std::max(2, std::min(8, (200 * 1024) / sb2));
-    const size_t psmem = gemm2_smem_bytes(g.stages, g.BN);
+    const size_t psmem = gemm2_smem_bytes(g.stages, g.BN, g.kmerge);
     RFB_CHECK(psmem <= 227 * 1024, "GEMM smem over budget");
     const uint64_t db[2] = {(uint64_t)kp, (uint64_t)nrows_w};
     const uint64_t sb[1] = {(uint64_t)kp * 2};
     const uint32_t bb[2] = {64, (uint32_t)(g.BN / 2)};
     CUtensorMap tmB2 = make_tmap(c, Bplain, 2, db, sb, bb);
+    g.dbg = nullptr;
+    if (c.gemm_debug) {
+      // raw cudaMalloc on purpose: Ctx::owned is rolled back by the single-op test entry points
+      if (!c.dbg_buf) CUDA_OK(cudaMalloc((void**)&c.dbg_buf, (size_t)c.num_sms * 8 * sizeof(unsigned long long)));
+      CUDA_OK(cudaMemsetAsync(c.dbg_buf, 0, (size_t)c.num_sms * 8 * sizeof(unsigned long long), c.stream));
+      g.dbg = c.dbg_buf;
+    }
     const int m_pairs = ((int)grid.x + 1) / 2, n_tiles = (int)grid.y;
     const int total_pairs = m_pairs * n_tiles;
     const int pairs = std::min(total_pairs, c.num_sms / 2);

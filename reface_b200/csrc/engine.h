@@ -73,9 +73,11 @@ struct Ctx {
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
   long long launches = 0;     // kernels launched by this library (reported by bench)
   int gemm_smem_budget = 110 * 1024;  // per-CTA smem target (2 CTAs/SM)
-  int force_bn = 0, force_stages = 0, attn_flash = 1, gemm_persistent = 1, gemm_pair = 1;
+  int force_bn = 0, force_stages = 0, attn_flash = 1, gemm_persistent = 1, gemm_pair = 1, gemm_kmerge = 1;
   // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline)
   int profile = 0;
+  int gemm_debug = 0;                       // per-CTA clock64 counters of the last 2-CTA GEMM launch
+  unsigned long long* dbg_buf = nullptr;    // [num_sms * 8]
   struct ProfRec { cudaEvent_t a, b; double flops; int kind; };
   std::vector<ProfRec> prof;
   UNet* unet = nullptr;

@@ -16,8 +16,10 @@
 
 namespace rfb {
 
-__host__ __device__ inline size_t gemm2_smem_bytes(int stages, int BN) {
-  return 1024 + (size_t)stages * (GEMM_A_STAGE_BYTES + (size_t)(BN / 2) * 128) + 16 * stages + 128;
+// kmerge: 64-wide k-blocks per pipeline stage (2 halves the mbarrier waits / commits the single MMA-issuing thread
+// has to execute per MMA)
+__host__ __device__ inline size_t gemm2_smem_bytes(int stages, int BN, int kmerge) {
+  return 1024 + (size_t)stages * kmerge * (GEMM_A_STAGE_BYTES + (size_t)(BN / 2) * 128) + 16 * stages + 128;
 }
 
 template <int MODE>
@@ -25,7 +27,10 @@ __global__ void __launch_bounds__(GEMMP_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g,
                  const int m_pairs, const int n_tiles, const int total_pairs) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5;
+  // warp index via shuffle: tells the compiler it is warp-uniform, so descriptors / coordinates of the TMA and MMA
+  // roles live in uniform registers (a lane-0-only loop forced ELECT + 4-6 R2UR.BROADCAST before EVERY UTCHMMA and
+  // cost ~130 cycles per MMA issue)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int S = g.stages;
   const int BN = g.BN;
@@ -33,8 +38,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const bool leader = rank == 0;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;
-  const uint32_t sB = base + (uint32_t)S * GEMM_A_STAGE_BYTES;
-  const uint32_t b_stage_bytes = (uint32_t)(BN / 2) * 128u;
+  const int KM = g.kmerge;
+  const uint32_t a_stage_bytes = (uint32_t)KM * GEMM_A_STAGE_BYTES;
+  const uint32_t b_sub_bytes = (uint32_t)(BN / 2) * 128u;
+  const uint32_t b_stage_bytes = (uint32_t)KM * b_sub_bytes;
+  const uint32_t sB = base + (uint32_t)S * a_stage_bytes;
   const uint32_t bars = sB + (uint32_t)S * b_stage_bytes;  // full[S], empty[S]
   const uint32_t bar_accf = bars + 16u * S;
   const uint32_t bar_acce = bar_accf + 16u;
@@ -67,10 +75,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int per_z = m_pairs * n_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer (both CTAs)
-      const uint32_t tx = 2u * (GEMM_A_STAGE_BYTES + b_stage_bytes);
-      uint32_t it = 0;
+    {
+      // ------------------------------------------------------------ TMA producer (both CTAs; whole warp runs the
+      // loop with warp-uniform state, one elected lane issues)
+      uint32_t it = 0, st = 0, sp = 0;
+      long long t_empty = 0;
       for (int pt = pair_id; pt < total_pairs; pt += num_pairs) {
         const int z = pt / per_z;
         const int rem = pt - z * per_z;
@@ -90,49 +99,78 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         const int m0 = m_tile * GEMM_BM;
         const int n0 = n_tile * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < g.nk; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)S;
-          const uint32_t ph = (it / (uint32_t)S) & 1u;
+        for (int kb0 = 0; kb0 < g.nk; kb0 += KM, ++it) {
+          const uint32_t s = st, ph = sp;  // running stage / phase (no runtime division in the hot loop)
+          if (++st == (uint32_t)S) st = 0, sp ^= 1u;
+          const int nv = min(KM, g.nk - kb0);
+          const long long t0 = g.dbg ? clock64() : 0;
           mbar_wait(bars + 8u * (S + s), ph ^ 1u);
+          if (g.dbg) t_empty += clock64() - t0;
           const uint32_t full = bars + 8u * s;
-          if (leader) mbar_expect_tx(full, tx);
-          const uint32_t dA = sA + s * GEMM_A_STAGE_BYTES;
-          const uint32_t dB = sB + s * b_stage_bytes;
-          if (g.a_mode == A_PLAIN) {
-            tma_load_2d_2sm(dA, &tmA, full, kb * GEMM_BK, m0);
-          } else {
-            const int tap = kb / g.cblocks;
-            const int cb = kb - tap * g.cblocks;
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            tma_load_4d_2sm(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(full, 2u * (uint32_t)nv * (GEMM_A_STAGE_BYTES + b_sub_bytes));
+            for (int j = 0; j < nv; ++j) {
+              const int kb = kb0 + j;
+              const uint32_t dA = sA + s * a_stage_bytes + (uint32_t)j * GEMM_A_STAGE_BYTES;
+              const uint32_t dB = sB + s * b_stage_bytes + (uint32_t)j * b_sub_bytes;
+              if (g.a_mode == A_PLAIN) {
+                tma_load_2d_2sm(dA, &tmA, full, kb * GEMM_BK, m0);
+              } else {
+                const int tap = kb / g.cblocks;
+                const int cb = kb - tap * g.cblocks;
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                tma_load_4d_2sm(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn);
+              }
+              tma_load_2d_2sm(dB, &tmB, full, kb * GEMM_BK, n0);
+            }
           }
-          tma_load_2d_2sm(dB, &tmB, full, kb * GEMM_BK, n0);
+          __syncwarp();
         }
       }
+      if (g.dbg && lane == 0) g.dbg[(size_t)blockIdx.x * 8 + 3] = (unsigned long long)t_empty;
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (leader) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA; converged warp, the
+      // elected lane issues tcgen05.mma / commit with operands held in uniform registers)
       const uint32_t idesc = idesc_f16(256, (uint32_t)BN);
-      uint32_t it = 0, ti = 0;
+      uint32_t it = 0, ti = 0, st = 0, sp = 0;
+      long long t_full = 0, t_acc = 0;
+      const long long t_begin = clock64();
       for (int pt = pair_id; pt < total_pairs; pt += num_pairs, ++ti) {
         const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+        long long t0 = g.dbg ? clock64() : 0;
         mbar_wait(bar_acce + 8u * as, aph ^ 1u);
+        if (g.dbg) t_acc += clock64() - t0;
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * 256u;
-        for (int kb = 0; kb < g.nk; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)S;
-          const uint32_t ph = (it / (uint32_t)S) & 1u;
+        for (int kb0 = 0; kb0 < g.nk; kb0 += KM, ++it) {
+          const uint32_t s = st, ph = sp;  // running stage / phase (no runtime division in the hot loop)
+          if (++st == (uint32_t)S) st = 0, sp ^= 1u;
+          const int nv = min(KM, g.nk - kb0);
+          t0 = g.dbg ? clock64() : 0;
           mbar_wait(bars + 8u * s, ph);
+          if (g.dbg) t_full += clock64() - t0;
           tc_fence_after();
-          const uint64_t da = smem_desc_k_sw128(sA + s * GEMM_A_STAGE_BYTES);
-          const uint64_t db = smem_desc_k_sw128(sB + s * b_stage_bytes);
+          const bool last = kb0 + KM >= g.nk;
+          if (elect_one()) {
+            for (int j = 0; j < nv; ++j) {
+              const uint64_t da = smem_desc_k_sw128(sA + s * a_stage_bytes + (uint32_t)j * GEMM_A_STAGE_BYTES);
+              const uint64_t db = smem_desc_k_sw128(sB + s * b_stage_bytes + (uint32_t)j * b_sub_bytes);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            mma_f16_ss_2cta(tacc, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
-          mma_commit_2cta_mc(bars + 8u * (S + s), 3);  // smem slot free in both CTAs
+              for (int k = 0; k < GEMM_BK / 16; ++k)
+                mma_f16_ss_2cta(tacc, da + 2u * k, db + 2u * k, idesc, (uint32_t)(((kb0 + j) | k) != 0));
+            }
+            mma_commit_2cta_mc(bars + 8u * (S + s), 3);               // smem slot free in both CTAs
+            if (last) mma_commit_2cta_mc(bar_accf + 8u * as, 3);      // accumulators ready in both CTAs
+          }
+          __syncwarp();
         }
-        mma_commit_2cta_mc(bar_accf + 8u * as, 3);  // accumulators ready in both CTAs
+      }
+      if (g.dbg && lane == 0) {
+        unsigned long long* d = g.dbg + (size_t)blockIdx.x * 8;
+        d[0] = (unsigned long long)(clock64() - t_begin), d[1] = (unsigned long long)t_full;
+        d[2] = (unsigned long long)t_acc, d[6] = it, d[7] = ti;
       }
     }
   } else {
@@ -145,6 +183,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ncols = (MODE == EPI_GEGLU) ? halfN : BN;
     const int NO = (MODE == EPI_GEGLU) ? (g.N >> 1) : g.N;
     uint32_t ti = 0;
+    long long t_wait = 0;
+    const long long t_ebegin = clock64();
     for (int pt = pair_id; pt < total_pairs; pt += num_pairs, ++ti) {
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
       const int z = pt / per_z;
@@ -155,7 +195,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = m < g.M;
       const long long zoff = (long long)(z / g.zdiv) * g.zs_outer + (long long)(z % g.zdiv) * g.zs_inner;
       const float* rv = (g.rowvec && row_ok) ? g.rowvec + (m / g.rows_per_vec) * g.ldv : nullptr;
+      const long long tw0 = g.dbg ? clock64() : 0;
       mbar_wait(bar_accf + 8u * as, aph);
+      if (g.dbg) t_wait += clock64() - tw0;
       tc_fence_after();
       const uint32_t trow = tmem_base + as * 256u + ((uint32_t)(q * 32) << 16);
       for (int c0 = half * 32; c0 < ncols; c0 += 64) {
@@ -264,6 +306,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (leader) mbar_arrive(bar_acce + 8u * as);
         else mbar_arrive_remote(bar_acce + 8u * as, 0);
       }
+    }
+    if (g.dbg && warp == 2 && lane == 0) {
+      g.dbg[(size_t)blockIdx.x * 8 + 4] = (unsigned long long)t_wait;
+      g.dbg[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - t_ebegin);
     }
   }
   tc_fence_before();

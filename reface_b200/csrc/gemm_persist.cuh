@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(GEMMP_THREADS, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g,
                     const int m_tiles, const int n_tiles, const int total_tiles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform (see gemm_pair.cuh)
   const int lane = threadIdx.x & 31;
   const int S = g.stages;
   const int BN = g.BN;
@@ -78,10 +78,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int per_z = m_tiles * n_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer
+    {
+      // ------------------------------------------------------------ TMA producer (converged warp, elected issue)
       const uint32_t tx = GEMM_A_STAGE_BYTES + b_stage_bytes;
-      uint32_t it = 0;
+      uint32_t st = 0, sp = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int z = tile / per_z;
         const int rem = tile - z * per_z;
@@ -99,56 +99,62 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         const int m0 = m_tile * GEMM_BM, n0 = n_tile * BN;
-        for (int kb = 0; kb < g.nk; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)S;
-          const uint32_t ph = (it / (uint32_t)S) & 1u;
+        for (int kb = 0; kb < g.nk; ++kb) {
+          const uint32_t s = st, ph = sp;
+          if (++st == (uint32_t)S) st = 0, sp ^= 1u;
           mbar_wait(bars + 8u * (S + s), ph ^ 1u);
           const uint32_t full = bars + 8u * s;
-          mbar_expect_tx(full, tx);
-          const uint32_t dA = sA + s * GEMM_A_STAGE_BYTES;
-          const uint32_t dB = sB + s * b_stage_bytes;
-          switch (g.a_mode) {
-            case A_PLAIN: tma_load_2d(dA, &tmA, full, kb * GEMM_BK, m0); break;
-            case A_CONV3: {
-              const int tap = kb / g.cblocks;
-              const int cb = kb - tap * g.cblocks;
-              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-              tma_load_4d(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn);
-            } break;
-            case A_BATCH3: tma_load_3d(dA, &tmA, full, kb * GEMM_BK, m0, z); break;
-            default: tma_load_4d(dA, &tmA, full, kb * GEMM_BK, z % g.heads, m0, z / g.heads); break;
+          if (elect_one()) {
+            mbar_expect_tx(full, tx);
+            const uint32_t dA = sA + s * GEMM_A_STAGE_BYTES;
+            const uint32_t dB = sB + s * b_stage_bytes;
+            switch (g.a_mode) {
+              case A_PLAIN: tma_load_2d(dA, &tmA, full, kb * GEMM_BK, m0); break;
+              case A_CONV3: {
+                const int tap = kb / g.cblocks;
+                const int cb = kb - tap * g.cblocks;
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                tma_load_4d(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn);
+              } break;
+              case A_BATCH3: tma_load_3d(dA, &tmA, full, kb * GEMM_BK, m0, z); break;
+              default: tma_load_4d(dA, &tmA, full, kb * GEMM_BK, z % g.heads, m0, z / g.heads); break;
+            }
+            switch (g.b_mode) {
+              case B_PLAIN: tma_load_2d(dB, &tmB, full, kb * GEMM_BK, n0); break;
+              case B_BATCH3: tma_load_3d(dB, &tmB, full, kb * GEMM_BK, n0, z); break;
+              default: tma_load_4d(dB, &tmB, full, kb * GEMM_BK, z % g.heads, n0, z / g.heads); break;
+            }
           }
-          switch (g.b_mode) {
-            case B_PLAIN: tma_load_2d(dB, &tmB, full, kb * GEMM_BK, n0); break;
-            case B_BATCH3: tma_load_3d(dB, &tmB, full, kb * GEMM_BK, n0, z); break;
-            default: tma_load_4d(dB, &tmB, full, kb * GEMM_BK, z % g.heads, n0, z / g.heads); break;
-          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
+    {
+      // ------------------------------------------------------------ MMA issuer (converged warp, elected issue)
       const uint32_t idesc = idesc_f16(GEMM_BM, (uint32_t)BN);
-      uint32_t it = 0, ti = 0;
+      uint32_t ti = 0, st = 0, sp = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
         mbar_wait(bar_acce + 8u * as, aph ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * 256u;
-        for (int kb = 0; kb < g.nk; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)S;
-          const uint32_t ph = (it / (uint32_t)S) & 1u;
+        for (int kb = 0; kb < g.nk; ++kb) {
+          const uint32_t s = st, ph = sp;
+          if (++st == (uint32_t)S) st = 0, sp ^= 1u;
           mbar_wait(bars + 8u * s, ph);
           tc_fence_after();
-          const uint64_t da = smem_desc_k_sw128(sA + s * GEMM_A_STAGE_BYTES);
-          const uint64_t db = smem_desc_k_sw128(sB + s * b_stage_bytes);
+          if (elect_one()) {
+            const uint64_t da = smem_desc_k_sw128(sA + s * GEMM_A_STAGE_BYTES);
+            const uint64_t db = smem_desc_k_sw128(sB + s * b_stage_bytes);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            mma_f16_ss(tacc, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
-          mma_commit(bars + 8u * (S + s));
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              mma_f16_ss(tacc, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+            mma_commit(bars + 8u * (S + s));
+            if (kb == g.nk - 1) mma_commit(bar_accf + 8u * as);
+          }
+          __syncwarp();
         }
-        mma_commit(bar_accf + 8u * as);
       }
     }
   } else {

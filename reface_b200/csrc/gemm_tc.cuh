@@ -18,7 +18,7 @@ enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_QGELU = 3, ACT_PRELU = 
 
 struct GemmArgs {
   int M, N, nk;  // rows (per batch z), valid output columns (of the B tensor), number of 64-wide k blocks
-  int BN, stages, tmem_cols;
+  int BN, stages, tmem_cols, kmerge;
   int a_mode, b_mode;
   // A_CONV3 geometry: tile = bimg images x bh rows x bw cols (=128 output pixels), K = taps x cblocks x 64
   int cblocks, bw, bh, bimg, tiles_w, tiles_h;
@@ -40,6 +40,10 @@ struct GemmArgs {
   // batch (blockIdx.z) offsets in elements for out/res: (z / zdiv) * zs_outer + (z % zdiv) * zs_inner
   long long zs_outer, zs_inner;
   int zdiv;
+  // optional instrumentation (option "gemm_debug"): per CTA 8 x u64 clock64 totals
+  // [0] MMA thread total, [1] waiting on full[], [2] waiting on acc_empty[], [3] producer waiting on empty[],
+  // [4] epilogue warp2 waiting on acc_full[], [5] epilogue warp2 total, [6] k-stages issued, [7] tiles
+  unsigned long long* dbg;
 };
 
 static constexpr int GEMM_THREADS = 192;

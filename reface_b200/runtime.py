@@ -33,6 +33,7 @@ SIGNATURES = {
     "rfb_launch_count": (_ll, [_vp]),
     "rfb_arena_peak": (_sz, [_vp]),
     "rfb_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
+    "rfb_debug_read": (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
     "rfb_unet_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "rfb_concat9": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "rfb_cfg_ddim_update": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp]),
