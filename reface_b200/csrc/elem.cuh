@@ -136,8 +136,9 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict_
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
   if (pr < R) {
+#pragma unroll 4
     for (int p = p0 + pr; p < p1; p += R) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + ((long long)n * HW + p) * C + cq * 8);
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((long long)n * HW + p) * C + cq * 8));
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -226,9 +227,10 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
   }
   const int p0 = blockIdx.x * slab;
   const int p1 = min(HW, p0 + slab);
+#pragma unroll 4
   for (int p = p0 + pr; p < p1; p += R) {
     const long long off = ((long long)n * HW + p) * C + cq * 8;
-    const uint4 u = *reinterpret_cast<const uint4*>(x + off);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + off));
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     float v[8];
 #pragma unroll

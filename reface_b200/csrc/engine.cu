@@ -210,7 +210,7 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     }
     g.kmerge = (c.gemm_kmerge >= 2 && g.nk >= 4) ? 2 : 1;
     const int sb2 = g.kmerge * (GEMM_A_STAGE_BYTES + (g.BN / 2) * 128);
-    g.stages = c.force_stages ? c.force_stages : std::max(2, std::min(8, (200 * 1024) / sb2));
+    g.stages = c.force_stages ? c.force_stages : std::max(2, std::min(8, (186 * 1024) / sb2));  // ~37 KB: epilogue staging
     const size_t psmem = gemm2_smem_bytes(g.stages, g.BN, g.kmerge);
     RFB_CHECK(psmem <= 227 * 1024, "GEMM smem over budget");
     const uint64_t db[2] = {(uint64_t)kp, (uint64_t)nrows_w};
@@ -252,7 +252,7 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
       CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr2 = true;
     }
-    int ps = c.force_stages ? c.force_stages : std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+    int ps = c.force_stages ? c.force_stages : std::max(2, std::min(8, (186 * 1024) / stage_bytes));
     g.stages = ps;
     const size_t psmem = gemmp_smem_bytes(ps, g.BN);
     RFB_CHECK(psmem <= 227 * 1024, "GEMM smem over budget");

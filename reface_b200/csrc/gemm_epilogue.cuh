@@ -1,0 +1,279 @@
+// Epilogue of the persistent GEMM kernels: TMEM accumulators -> fused bias / time-embedding row / GEGLU / activation /
+// residual -> fp16 rows in HBM, with COALESCED global traffic and the global-load latencies taken off the critical path.
+//
+// tcgen05.ld 32x32b hands every thread one accumulator ROW, so a direct store makes each warp instruction touch
+// 32 different 128-byte lines (measured: ~2500 cycles of LSU time per 128x160 tile, and the same again for the
+// residual read; the K=320 GEMMs of the UNet were epilogue-bound at 2.2-2.7x their HBM time).  Each epilogue warp owns
+// two 4 KB shared-memory staging tiles (32 rows x 128 B, XOR-swizzled in 16-byte units) and a 512 B bias strip:
+//   prefetch (BEFORE the accumulators are ready): residual rows of the warp's <=2 column chunks -> staging tiles with
+//            8 lanes per row (4 lines per instruction instead of 32); bias columns -> smem strip
+//   drain    : tcgen05.ld -> + bias (smem broadcast) [+ row vector] [GEGLU / activation] + staged residual ->
+//              fp16 row back into the staging tile -> coalesced 16-byte stores
+// (clock64 profile of the first version: 30 % of the epilogue time was the exposed residual-load latency, 37-49 % the
+// per-chunk bias loads + math; the accumulator loads themselves were ~1 %.)
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace rfb {
+
+static constexpr int EPI_STAGE_BYTES = 4096;               // one staging tile
+static constexpr int EPI_WARP_BYTES = 4096 + 512;          // staging tile + bias strip per epilogue warp
+
+enum EpiMode { EPI_FAST = 0, EPI_GEGLU = 1, EPI_GENERIC = 2 };
+
+// exact-erf GELU with a cheap erf (Abramowitz-Stegun 7.1.26, |err| < 1.5e-7: far below the fp16 output ulp)
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erf_abs = 1.0f - p * t * __expf(-z * z);
+  const float erf = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf);
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32f(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+
+struct EpiTile {  // warp-uniform description of one output tile for one epilogue warp
+  int ncols, NO, ocol_tile, halfN;
+  long long m_base, zoff;
+  bool vec_ok;
+};
+
+template <int MODE>
+__device__ __forceinline__ EpiTile epi_tile_info(const GemmArgs& g, int q, int m_tile, int n_tile, int z) {
+  EpiTile t;
+  t.halfN = g.BN >> 1;
+  t.ncols = (MODE == EPI_GEGLU) ? t.halfN : g.BN;
+  t.NO = (MODE == EPI_GEGLU) ? (g.N >> 1) : g.N;
+  t.ocol_tile = (MODE == EPI_GEGLU) ? n_tile * t.halfN : n_tile * g.BN;
+  t.m_base = (long long)m_tile * GEMM_BM + q * 32;
+  t.zoff = (long long)(z / g.zdiv) * g.zs_outer + (long long)(z % g.zdiv) * g.zs_inner;
+  t.vec_ok = g.out != nullptr && (t.NO & 7) == 0 && (g.ldo & 7) == 0 && (t.zoff & 7) == 0 &&
+             (!g.res || (g.ldr & 7) == 0);
+  return t;
+}
+
+// Phase A -- runs while the MMAs of this tile are still in flight.
+//   wbuf: this warp's smem region (two staging tiles, then the bias strip)
+template <int MODE>
+__device__ __forceinline__ void epilogue_prefetch(const GemmArgs& g, const EpiTile& t, uint32_t wbuf, int lane, int half,
+                                                  int n_tile) {
+  const uint32_t bias_s = wbuf + EPI_STAGE_BYTES;
+#pragma unroll
+  for (int ci = 0; ci < 2; ++ci) {
+    const int c0 = half * 64 + ci * 128;
+    if (c0 >= t.ncols) break;
+    const int ocol0 = t.ocol_tile + c0;
+    const int cvalid = min(64, min(t.ncols - c0, t.NO - ocol0));
+    if (cvalid <= 0) continue;
+    if (g.bias) {
+      if (MODE == EPI_GEGLU) {
+        // value bias at [0,64), gate bias at [64,128) of this chunk's half of the strip is too small: GEGLU reads
+        // its two biases directly (they are contiguous, 16-byte loads), see epilogue_drain
+      } else {
+        // 64 floats of this chunk -> strip[ci*64 ..]
+        for (int j = lane; j < 64; j += 32) {
+          const int col = ocol0 + j;
+          sts32f(bias_s + (uint32_t)(ci * 64 + j) * 4u, col < g.N ? __ldg(g.bias + col) : 0.f);
+        }
+      }
+    }
+    if (g.res && t.vec_ok) {
+      // first chunk: residual rows straight into the (idle) staging tile; second chunk: pull its lines into L2
+      // now, the staging tile is refilled when chunk 0 has been stored (see epilogue_drain)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3), unit = lane & 7;
+        const long long gm = t.m_base + row;
+        const bool ok = gm < g.M && unit * 8 < cvalid;
+        const __half* src = g.res + t.zoff + gm * g.ldr + ocol0 + unit * 8;
+        if (ci == 0) {
+          uint4 val = make_uint4(0u, 0u, 0u, 0u);
+          if (ok) val = __ldg(reinterpret_cast<const uint4*>(src));
+          sts128(wbuf + (uint32_t)row * 128u + (uint32_t)((unit ^ (row & 7)) << 4), val);
+        } else if (ok && unit == 0) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Phase B -- drains this warp's 32 accumulator rows (TMEM lanes q*32..q*32+31).
+//   trow : TMEM address of (lane quadrant, accumulator stage, column 0)
+template <int MODE>
+__device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile& t, uint32_t trow, uint32_t wbuf, int lane,
+                                               int half, int n_tile) {
+  const int BN = g.BN;
+  const long long m = t.m_base + lane;  // the row this thread owns next to TMEM
+  const bool row_ok = m < g.M;
+  const float* rv = (g.rowvec && row_ok) ? g.rowvec + (m / g.rows_per_vec) * g.ldv : nullptr;
+  const uint32_t bias_s = wbuf + EPI_STAGE_BYTES;
+  const int sw = lane & 7;
+
+#pragma unroll
+  for (int ci = 0; ci < 2; ++ci) {
+    const int c0 = half * 64 + ci * 128;
+    if (c0 >= t.ncols) break;
+    const int ocol0 = t.ocol_tile + c0;
+    const int cvalid = min(64, min(t.ncols - c0, t.NO - ocol0));  // warp-uniform
+    if (cvalid <= 0) continue;
+    const uint32_t stage = wbuf;
+    const uint32_t my_row = stage + (uint32_t)lane * 128u;  // row-per-thread view of the staging tile
+    if (ci == 1 && g.res && t.vec_ok) {
+      __syncwarp();  // chunk 0's rows have been read out of the staging tile
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3), unit = lane & 7;
+        const long long gm = t.m_base + row;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (gm < g.M && unit * 8 < cvalid)
+          val = __ldg(reinterpret_cast<const uint4*>(g.res + t.zoff + gm * g.ldr + ocol0 + unit * 8));
+        sts128(stage + (uint32_t)row * 128u + (uint32_t)((unit ^ (row & 7)) << 4), val);
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h * 32 >= cvalid) break;  // warp-uniform
+      const int cc = c0 + h * 32;   // column inside the tile
+      const int oc = ocol0 + h * 32;
+      uint32_t acc[32];
+      float v[32];
+      tmem_ld32(trow + (uint32_t)cc, acc);
+      if (MODE == EPI_GEGLU) {
+        uint32_t gat[32];
+        tmem_ld32(trow + (uint32_t)(t.halfN + cc), gat);
+        const float4* bx = reinterpret_cast<const float4*>(g.bias + n_tile * BN + cc);
+        const float4* bg = reinterpret_cast<const float4*>(g.bias + n_tile * BN + t.halfN + cc);
+        float4 b1[8], b2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b1[j] = __ldg(bx + j), b2[j] = __ldg(bg + j);  // in flight with the TMEM loads
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[4 * j + 0] = (__uint_as_float(acc[4 * j + 0]) + b1[j].x) * gelu_erf_fast(__uint_as_float(gat[4 * j + 0]) + b2[j].x);
+          v[4 * j + 1] = (__uint_as_float(acc[4 * j + 1]) + b1[j].y) * gelu_erf_fast(__uint_as_float(gat[4 * j + 1]) + b2[j].y);
+          v[4 * j + 2] = (__uint_as_float(acc[4 * j + 2]) + b1[j].z) * gelu_erf_fast(__uint_as_float(gat[4 * j + 2]) + b2[j].z);
+          v[4 * j + 3] = (__uint_as_float(acc[4 * j + 3]) + b1[j].w) * gelu_erf_fast(__uint_as_float(gat[4 * j + 3]) + b2[j].w);
+        }
+      } else {
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+        if (MODE == EPI_GENERIC) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= g.alpha;
+        }
+        if (g.bias) {  // staged by epilogue_prefetch (zeros beyond N)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = lds128f(bias_s + (uint32_t)(ci * 64 + h * 32 + 4 * j) * 4u);
+            v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+          }
+        }
+        if (rv) {
+          if (oc + 32 <= g.N && (g.ldv & 3) == 0) {
+            const float4* r4 = reinterpret_cast<const float4*>(rv + oc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(r4 + j);
+              v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (oc + j < g.N) v[j] += __ldg(rv + oc + j);
+          }
+        }
+        if (MODE == EPI_GENERIC && g.act) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = oc + j;
+            v[j] = apply_act(v[j], g.act, (g.act == ACT_PRELU && col < g.N) ? __ldg(g.act_param + col) : 0.f);
+          }
+        }
+      }
+      if (t.vec_ok) {
+        // own row: add the staged residual, then overwrite the same 16-byte units with the fp16 result
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const uint32_t a = my_row + (uint32_t)(((h * 4 + u4) ^ sw) << 4);
+          if (g.res) {
+            const uint4 u = lds128(a);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_h2(w[e]);
+              v[u4 * 8 + 2 * e] += f.x;
+              v[u4 * 8 + 2 * e + 1] += f.y;
+            }
+          }
+          uint4 o;
+          o.x = pack_h2(v[u4 * 8 + 0], v[u4 * 8 + 1]);
+          o.y = pack_h2(v[u4 * 8 + 2], v[u4 * 8 + 3]);
+          o.z = pack_h2(v[u4 * 8 + 4], v[u4 * 8 + 5]);
+          o.w = pack_h2(v[u4 * 8 + 6], v[u4 * 8 + 7]);
+          sts128(a, o);
+        }
+      } else if (row_ok) {
+        // scalar fallback (odd widths / strides, fp32 strided outputs)
+        if (g.res) {
+          const __half* rp = g.res + t.zoff + m * g.ldr + oc;
+          for (int j = 0; j < 32; ++j)
+            if (oc + j < t.NO) v[j] += __half2float(rp[j]);
+        }
+        if (g.out) {
+          __half* op = g.out + t.zoff + m * g.ldo + oc;
+          for (int j = 0; j < 32; ++j)
+            if (oc + j < t.NO) op[j] = __float2half_rn(v[j]);
+        }
+        if (MODE == EPI_GENERIC && g.out32) {
+          float* op = g.out32 + (m / g.o32_rpn) * g.o32_sn + (m % g.o32_rpn) * g.o32_sp;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (oc + j < t.NO) op[(long long)(oc + j) * g.o32_sc] = v[j];
+        }
+      }
+    }
+    // staging tile -> HBM, coalesced: 8 lanes x 16 B per row, 4 rows per instruction
+    if (t.vec_ok) {
+      __syncwarp();
+      uint4 val[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3), unit = lane & 7;
+        val[i] = lds128(stage + (uint32_t)row * 128u + (uint32_t)((unit ^ (row & 7)) << 4));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3), unit = lane & 7;
+        const long long gm = t.m_base + row;
+        if (gm < g.M && unit * 8 < cvalid)
+          *reinterpret_cast<uint4*>(g.out + t.zoff + gm * g.ldo + ocol0 + unit * 8) = val[i];
+      }
+    }
+  }
+  __syncwarp();  // staging tiles / bias strip may be refilled by the next tile's prefetch
+}
+
+}  // namespace rfb

@@ -1,9 +1,8 @@
-// 2-CTA (tcgen05 cta_group::2) persistent GEMM / implicit-GEMM convolution.
+// 2-CTA (tcgen05 cta_group::2) persistent GEMM / implicit-GEMM convolution -- the main tensor-core kernel.
 //
-// Why: the 1-CTA persistent kernel is bound by L2 -> SM operand traffic (ncu: 1.7 GB through the crossbar for a
-// 121 GFLOP conv = ~7.2 KB/cycle, the chip's L2 fabric limit; tensor pipe 45 % active).  A CTA PAIR (cluster of 2
-// on one TPC) computes a 256 x BN tile with one UMMA (M=256): each CTA loads its own 128 A rows and only HALF of
-// the B tile (BN/2 rows); the tensor cores read both halves across the pair.  Bytes per FLOP drop by 27-33 %.
+// A CTA PAIR (cluster of 2 on one TPC) computes a 256 x BN tile with one UMMA (M=256): each CTA loads its own 128 A
+// rows and only HALF of the B tile (BN/2 rows); the tensor cores read both halves across the pair, so operand bytes
+// per FLOP drop by 27-33 % versus the 1-CTA kernel (which ncu showed pinned at the ~6-7 KB/cycle L2->SM fabric limit).
 //
 // Protocol (per CTA: warp0 TMA producer, warp1 TMEM owner + MMA issuer (leader only), warps2-9 epilogue):
 //   full[s]      leader's barrier only (count 1): leader posts expect_tx for BOTH CTAs' bytes; both CTAs' TMA loads
@@ -11,15 +10,16 @@
 //   empty[s]     one per CTA: released by the leader's tcgen05.commit (multicast to both CTAs)
 //   acc_full[a]  one per CTA: multicast commit after the last k-block of a tile
 //   acc_empty[a] leader's barrier (count 2 x 8 epilogue warps): the peer's warps arrive remotely (mapa)
+// TMA / MMA roles are converged warps with one elected issuing lane (operands in uniform registers, see
+// gemm_persist.cuh).  kmerge = number of 64-wide k-blocks per pipeline stage.
 #pragma once
 #include "gemm_persist.cuh"
 
 namespace rfb {
 
-// kmerge: 64-wide k-blocks per pipeline stage (2 halves the mbarrier waits / commits the single MMA-issuing thread
-// has to execute per MMA)
 __host__ __device__ inline size_t gemm2_smem_bytes(int stages, int BN, int kmerge) {
-  return 1024 + (size_t)stages * kmerge * (GEMM_A_STAGE_BYTES + (size_t)(BN / 2) * 128) + 16 * stages + 128;
+  return 2048 + (size_t)stages * kmerge * (GEMM_A_STAGE_BYTES + (size_t)(BN / 2) * 128) + 16 * stages + 128 +
+         (size_t)GEMMP_EPI_WARPS * EPI_WARP_BYTES;
 }
 
 template <int MODE>
@@ -27,9 +27,6 @@ __global__ void __launch_bounds__(GEMMP_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g,
                  const int m_pairs, const int n_tiles, const int total_pairs) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // warp index via shuffle: tells the compiler it is warp-uniform, so descriptors / coordinates of the TMA and MMA
-  // roles live in uniform registers (a lane-0-only loop forced ELECT + 4-6 R2UR.BROADCAST before EVERY UTCHMMA and
-  // cost ~130 cycles per MMA issue)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int S = g.stages;
@@ -47,6 +44,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t bar_accf = bars + 16u * S;
   const uint32_t bar_acce = bar_accf + 16u;
   const uint32_t tptr = bar_acce + 16u;
+  const uint32_t epi_stage = (tptr + 16u + 1023u) & ~1023u;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
@@ -75,64 +73,60 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int per_z = m_pairs * n_tiles;
 
   if (warp == 0) {
-    {
-      // ------------------------------------------------------------ TMA producer (both CTAs; whole warp runs the
-      // loop with warp-uniform state, one elected lane issues)
-      uint32_t it = 0, st = 0, sp = 0;
-      long long t_empty = 0;
-      for (int pt = pair_id; pt < total_pairs; pt += num_pairs) {
-        const int z = pt / per_z;
-        const int rem = pt - z * per_z;
-        const int mp = rem / n_tiles, n_tile = rem - mp * n_tiles;
-        const int m_tile = 2 * mp + (int)rank;
-        int cw = 0, ch = 0, cn = 0;
-        if (g.a_mode == A_CONV3) {
-          if (g.bimg > 1) {
-            cn = m_tile * g.bimg;
-          } else {
-            const int per_img = g.tiles_w * g.tiles_h;
-            cn = m_tile / per_img;
-            const int r2 = m_tile - cn * per_img;
-            ch = (r2 / g.tiles_w) * g.bh;
-            cw = (r2 % g.tiles_w) * g.bw;
-          }
-        }
-        const int m0 = m_tile * GEMM_BM;
-        const int n0 = n_tile * BN + (int)rank * (BN / 2);
-        for (int kb0 = 0; kb0 < g.nk; kb0 += KM, ++it) {
-          const uint32_t s = st, ph = sp;  // running stage / phase (no runtime division in the hot loop)
-          if (++st == (uint32_t)S) st = 0, sp ^= 1u;
-          const int nv = min(KM, g.nk - kb0);
-          const long long t0 = g.dbg ? clock64() : 0;
-          mbar_wait(bars + 8u * (S + s), ph ^ 1u);
-          if (g.dbg) t_empty += clock64() - t0;
-          const uint32_t full = bars + 8u * s;
-          if (elect_one()) {
-            if (leader) mbar_expect_tx(full, 2u * (uint32_t)nv * (GEMM_A_STAGE_BYTES + b_sub_bytes));
-            for (int j = 0; j < nv; ++j) {
-              const int kb = kb0 + j;
-              const uint32_t dA = sA + s * a_stage_bytes + (uint32_t)j * GEMM_A_STAGE_BYTES;
-              const uint32_t dB = sB + s * b_stage_bytes + (uint32_t)j * b_sub_bytes;
-              if (g.a_mode == A_PLAIN) {
-                tma_load_2d_2sm(dA, &tmA, full, kb * GEMM_BK, m0);
-              } else {
-                const int tap = kb / g.cblocks;
-                const int cb = kb - tap * g.cblocks;
-                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                tma_load_4d_2sm(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn);
-              }
-              tma_load_2d_2sm(dB, &tmB, full, kb * GEMM_BK, n0);
-            }
-          }
-          __syncwarp();
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    uint32_t st = 0, sp = 0;
+    long long t_empty = 0;
+    for (int pt = pair_id; pt < total_pairs; pt += num_pairs) {
+      const int z = pt / per_z;
+      const int rem = pt - z * per_z;
+      const int mp = rem / n_tiles, n_tile = rem - mp * n_tiles;
+      const int m_tile = 2 * mp + (int)rank;
+      int cw = 0, ch = 0, cn = 0;
+      if (g.a_mode == A_CONV3) {
+        if (g.bimg > 1) {
+          cn = m_tile * g.bimg;
+        } else {
+          const int per_img = g.tiles_w * g.tiles_h;
+          cn = m_tile / per_img;
+          const int r2 = m_tile - cn * per_img;
+          ch = (r2 / g.tiles_w) * g.bh;
+          cw = (r2 % g.tiles_w) * g.bw;
         }
       }
-      if (g.dbg && lane == 0) g.dbg[(size_t)blockIdx.x * 8 + 3] = (unsigned long long)t_empty;
+      const int m0 = m_tile * GEMM_BM;
+      const int n0 = n_tile * BN + (int)rank * (BN / 2);
+      for (int kb0 = 0; kb0 < g.nk; kb0 += KM) {
+        const uint32_t s = st, ph = sp;  // running stage / phase (no runtime division in the hot loop)
+        if (++st == (uint32_t)S) st = 0, sp ^= 1u;
+        const int nv = min(KM, g.nk - kb0);
+        const long long t0 = g.dbg ? clock64() : 0;
+        mbar_wait(bars + 8u * (S + s), ph ^ 1u);
+        if (g.dbg) t_empty += clock64() - t0;
+        const uint32_t full = bars + 8u * s;
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(full, 2u * (uint32_t)nv * (GEMM_A_STAGE_BYTES + b_sub_bytes));
+          for (int j = 0; j < nv; ++j) {
+            const int kb = kb0 + j;
+            const uint32_t dA = sA + s * a_stage_bytes + (uint32_t)j * GEMM_A_STAGE_BYTES;
+            const uint32_t dB = sB + s * b_stage_bytes + (uint32_t)j * b_sub_bytes;
+            if (g.a_mode == A_PLAIN) {
+              tma_load_2d_2sm(dA, &tmA, full, kb * GEMM_BK, m0);
+            } else {
+              const int tap = kb / g.cblocks;
+              const int cb = kb - tap * g.cblocks;
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              tma_load_4d_2sm(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn);
+            }
+            tma_load_2d_2sm(dB, &tmB, full, kb * GEMM_BK, n0);
+          }
+        }
+        __syncwarp();
+      }
     }
+    if (g.dbg && lane == 0) g.dbg[(size_t)blockIdx.x * 8 + 3] = (unsigned long long)t_empty;
   } else if (warp == 1) {
     if (leader) {
-      // ------------------------------------------------------------ MMA issuer (leader CTA; converged warp, the
-      // elected lane issues tcgen05.mma / commit with operands held in uniform registers)
+      // ------------------------------------------------------------ MMA issuer (leader CTA)
       const uint32_t idesc = idesc_f16(256, (uint32_t)BN);
       uint32_t it = 0, ti = 0, st = 0, sp = 0;
       long long t_full = 0, t_acc = 0;
@@ -145,7 +139,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * 256u;
         for (int kb0 = 0; kb0 < g.nk; kb0 += KM, ++it) {
-          const uint32_t s = st, ph = sp;  // running stage / phase (no runtime division in the hot loop)
+          const uint32_t s = st, ph = sp;
           if (++st == (uint32_t)S) st = 0, sp ^= 1u;
           const int nv = min(KM, g.nk - kb0);
           t0 = g.dbg ? clock64() : 0;
@@ -161,8 +155,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int k = 0; k < GEMM_BK / 16; ++k)
                 mma_f16_ss_2cta(tacc, da + 2u * k, db + 2u * k, idesc, (uint32_t)(((kb0 + j) | k) != 0));
             }
-            mma_commit_2cta_mc(bars + 8u * (S + s), 3);               // smem slot free in both CTAs
-            if (last) mma_commit_2cta_mc(bar_accf + 8u * as, 3);      // accumulators ready in both CTAs
+            mma_commit_2cta_mc(bars + 8u * (S + s), 3);           // smem slot free in both CTAs
+            if (last) mma_commit_2cta_mc(bar_accf + 8u * as, 3);  // accumulators ready in both CTAs
           }
           __syncwarp();
         }
@@ -178,12 +172,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int e = warp - 2;
     const int q = warp & 3;
     const int half = e >> 2;
-    const int r = q * 32 + lane;
-    const int halfN = BN >> 1;
-    const int ncols = (MODE == EPI_GEGLU) ? halfN : BN;
-    const int NO = (MODE == EPI_GEGLU) ? (g.N >> 1) : g.N;
+    const uint32_t stage = epi_stage + (uint32_t)e * EPI_WARP_BYTES;  // this warp's staging tile + bias strip
     uint32_t ti = 0;
-    long long t_wait = 0;
+    long long t_wait = 0, t_pre = 0;
     const long long t_ebegin = clock64();
     for (int pt = pair_id; pt < total_pairs; pt += num_pairs, ++ti) {
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
@@ -191,115 +182,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int rem = pt - z * per_z;
       const int mp = rem / n_tiles, n_tile = rem - mp * n_tiles;
       const int m_tile = 2 * mp + (int)rank;
-      const long long m = (long long)m_tile * GEMM_BM + r;
-      const bool row_ok = m < g.M;
-      const long long zoff = (long long)(z / g.zdiv) * g.zs_outer + (long long)(z % g.zdiv) * g.zs_inner;
-      const float* rv = (g.rowvec && row_ok) ? g.rowvec + (m / g.rows_per_vec) * g.ldv : nullptr;
+      const EpiTile et = epi_tile_info<MODE>(g, q, m_tile, n_tile, z);
+      const long long tp0 = g.dbg ? clock64() : 0;
+      epilogue_prefetch<MODE>(g, et, stage, lane, half, n_tile);  // bias / residual while the MMAs still run
       const long long tw0 = g.dbg ? clock64() : 0;
       mbar_wait(bar_accf + 8u * as, aph);
-      if (g.dbg) t_wait += clock64() - tw0;
+      if (g.dbg) t_wait += clock64() - tw0, t_pre += tw0 - tp0;
       tc_fence_after();
       const uint32_t trow = tmem_base + as * 256u + ((uint32_t)(q * 32) << 16);
-      for (int c0 = half * 32; c0 < ncols; c0 += 64) {
-        const int ocol0 = ((MODE == EPI_GEGLU) ? n_tile * halfN : n_tile * BN) + c0;
-        uint32_t acc[32];
-        float v[32];
-        tmem_ld32(trow + (uint32_t)c0, acc);
-        if (MODE == EPI_GEGLU) {
-          uint32_t gat[32];
-          tmem_ld32(trow + (uint32_t)(halfN + c0), gat);
-          tmem_ld_wait();
-          const float4* bx = reinterpret_cast<const float4*>(g.bias + n_tile * BN + c0);
-          const float4* bg = reinterpret_cast<const float4*>(g.bias + n_tile * BN + halfN + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b1 = __ldg(bx + j), b2 = __ldg(bg + j);
-            v[4 * j + 0] = (__uint_as_float(acc[4 * j + 0]) + b1.x) * gelu_erf_fast(__uint_as_float(gat[4 * j + 0]) + b2.x);
-            v[4 * j + 1] = (__uint_as_float(acc[4 * j + 1]) + b1.y) * gelu_erf_fast(__uint_as_float(gat[4 * j + 1]) + b2.y);
-            v[4 * j + 2] = (__uint_as_float(acc[4 * j + 2]) + b1.z) * gelu_erf_fast(__uint_as_float(gat[4 * j + 2]) + b2.z);
-            v[4 * j + 3] = (__uint_as_float(acc[4 * j + 3]) + b1.w) * gelu_erf_fast(__uint_as_float(gat[4 * j + 3]) + b2.w);
-          }
-        } else {
-          tmem_ld_wait();
-          const bool fullc = (ocol0 + 32 <= NO);
-          if (MODE == EPI_FAST && fullc) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-            if (g.bias) {
-              const float4* b4 = reinterpret_cast<const float4*>(g.bias + ocol0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b = __ldg(b4 + j);
-                v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
-              }
-            }
-            if (rv) {
-              const float4* r4 = reinterpret_cast<const float4*>(rv + ocol0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b = __ldg(r4 + j);
-                v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = ocol0 + j;
-              float x = __uint_as_float(acc[j]) * g.alpha;
-              if (col < g.N) {
-                if (g.bias) x += __ldg(g.bias + col);
-                if (rv) x += __ldg(rv + col);
-                if (g.act) x = apply_act(x, g.act, g.act == ACT_PRELU ? __ldg(g.act_param + col) : 0.f);
-              }
-              v[j] = x;
-            }
-          }
-        }
-        if (!row_ok) continue;
-        const bool fullc = (ocol0 + 32 <= NO);
-        if (g.res) {
-          const __half* rp = g.res + zoff + m * g.ldr + ocol0;
-          if (fullc) {
-#pragma unroll
-            for (int grp = 0; grp < 4; ++grp) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rp + grp * 8);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 f = unpack_h2(w[t]);
-                v[grp * 8 + 2 * t] += f.x;
-                v[grp * 8 + 2 * t + 1] += f.y;
-              }
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (ocol0 + j < NO) v[j] += __half2float(rp[j]);
-          }
-        }
-        if (g.out) {
-          __half* op = g.out + zoff + m * g.ldo + ocol0;
-          if (fullc) {
-#pragma unroll
-            for (int grp = 0; grp < 4; ++grp) {
-              uint4 u;
-              u.x = pack_h2(v[grp * 8 + 0], v[grp * 8 + 1]);
-              u.y = pack_h2(v[grp * 8 + 2], v[grp * 8 + 3]);
-              u.z = pack_h2(v[grp * 8 + 4], v[grp * 8 + 5]);
-              u.w = pack_h2(v[grp * 8 + 6], v[grp * 8 + 7]);
-              *reinterpret_cast<uint4*>(op + grp * 8) = u;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (ocol0 + j < NO) op[j] = __float2half_rn(v[j]);
-          }
-        }
-        if (MODE == EPI_GENERIC && g.out32) {
-          float* op = g.out32 + (m / g.o32_rpn) * g.o32_sn + (m % g.o32_rpn) * g.o32_sp;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (ocol0 + j < NO) op[(long long)(ocol0 + j) * g.o32_sc] = v[j];
-        }
-      }
+      epilogue_drain<MODE>(g, et, trow, stage, lane, half, n_tile);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -310,6 +201,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (g.dbg && warp == 2 && lane == 0) {
       g.dbg[(size_t)blockIdx.x * 8 + 4] = (unsigned long long)t_wait;
       g.dbg[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - t_ebegin);
+      if (!leader) g.dbg[(size_t)blockIdx.x * 8 + 0] = (unsigned long long)t_pre;  // peer's MMA slots are free
     }
   }
   tc_fence_before();
