@@ -67,8 +67,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(b_ve + 8 * i, 1);
     }
     mbar_init(b_sfull, 1);
-    mbar_init(b_sfree, 128);
-    mbar_init(b_pfull, 128);
+    mbar_init(b_sfree, 4);  // one arrival per softmax warp
+    mbar_init(b_pfull, 4);
     mbar_init(b_ofull, 1);
     fence_mbar_init();
   }
@@ -164,59 +164,65 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(b_sfull, (uint32_t)j & 1u);
       tc_fence_after();
-      // pass 1: row max
-      float mx = m;
+      // pass 1: row max of the raw scores (scale > 0 is applied once afterwards); two TMEM loads per wait
+      float mraw = -INFINITY;
 #pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t sv[32];
-        tmem_ld32(tS + lane_off + c0, sv);
+      for (int c0 = 0; c0 < 128; c0 += 64) {
+        uint32_t s0[32], s1[32];
+        tmem_ld32(tS + lane_off + c0, s0);
+        tmem_ld32(tS + lane_off + c0 + 32, s1);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]) * scale_log2e);
+        for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
       }
+      const float mx = fmaxf(m, mraw * scale_log2e);
       const float alpha = fast_exp2(m - mx);  // exp2(-inf) = 0 on the first tile
       m = mx;
       float rs = 0.f;
       // pass 2: p = exp2(s - m) -> fp16 -> swizzled smem (A operand of the P.V MMA)
 #pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t sv[32];
-        tmem_ld32(tS + lane_off + c0, sv);
+      for (int c0 = 0; c0 < 128; c0 += 64) {
+        uint32_t sv[64];
+        tmem_ld32(tS + lane_off + c0, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_ld32(tS + lane_off + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
         tmem_ld_wait();
-        if (c0 == 96) {  // S fully consumed: let the MMA warp overwrite it with the next tile's scores
+        if (c0 == 64) {  // S fully consumed: let the MMA warp overwrite it with the next tile's scores
           tc_fence_before();
-          mbar_arrive(b_sfree);
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_exp2(__uint_as_float(sv[2 * i]) * scale_log2e - mx);
-          const float p1 = fast_exp2(__uint_as_float(sv[2 * i + 1]) * scale_log2e - mx);
-          rs += p0 + p1;
-          pk[i] = pack_h2(p0, p1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_sfree);
         }
         const uint32_t chunk_base = sP + (c0 >> 6) * Cfg::CHUNK + (uint32_t)r * 128u;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t unit = (uint32_t)(((c0 & 63) >> 3) + u) ^ (uint32_t)(r & 7);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(chunk_base + unit * 16u), "r"(pk[4 * u]),
-                       "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+        for (int u = 0; u < 8; ++u) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[8 * u + 2 * i]), scale_log2e, -mx));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[8 * u + 2 * i + 1]), scale_log2e, -mx));
+            rs += p0 + p1;
+            pk[i] = pack_h2(p0, p1);
+          }
+          const uint32_t unit = (uint32_t)u ^ (uint32_t)(r & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(chunk_base + unit * 16u), "r"(pk[0]), "r"(pk[1]),
+                       "r"(pk[2]), "r"(pk[3])
                        : "memory");
         }
       }
       l = l * alpha + rs;
       fence_proxy_async_smem();
-      mbar_arrive(b_pfull);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_pfull);
       // O_acc = alpha * O_acc + O_j
       mbar_wait(b_ofull, (uint32_t)j & 1u);
       tc_fence_after();
+      {
+        uint32_t ov[DP];
 #pragma unroll
-      for (int c0 = 0; c0 < DP; c0 += 16) {
-        uint32_t ov[16];
-        tmem_ld16(tO + lane_off + c0, ov);
+        for (int c0 = 0; c0 < DP; c0 += 16)
+          tmem_ld16(tO + lane_off + c0, *reinterpret_cast<uint32_t(*)[16]>(&ov[c0]));
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) oacc[c0 + i] = oacc[c0 + i] * alpha + __uint_as_float(ov[i]);
+        for (int i = 0; i < DP; ++i) oacc[i] = fmaf(oacc[i], alpha, __uint_as_float(ov[i]));
       }
       tc_fence_before();
     }

@@ -143,6 +143,8 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "gemm_pair") c.gemm_pair = (int)value;
   else if (k == "gemm_kmerge") c.gemm_kmerge = (int)value;
   else if (k == "gemm_debug") c.gemm_debug = (int)value;
+  else if (k == "gemm_pair_min_nk") c.gemm_pair_min_nk = (int)value;
+  else if (k == "gemm_epi3_max_nk") c.gemm_epi3_max_nk = (int)value;
   else return -1;
   return 0;
 }

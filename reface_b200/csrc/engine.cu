@@ -197,7 +197,7 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     CUDA_OK(cudaEventRecord(rec.a, c.stream));
   }
   const bool pair_ok = c.gemm_pair && c.gemm_persistent && Bplain != nullptr && grid.z == 1 && grid.x >= 2 &&
-                       (g.a_mode == A_PLAIN || g.a_mode == A_CONV3) && g.b_mode == B_PLAIN &&
+                       (g.a_mode == A_PLAIN || g.a_mode == A_CONV3) && g.b_mode == B_PLAIN && g.nk >= c.gemm_pair_min_nk &&
                        (long long)grid.x * grid.y >= c.num_sms / 2;
   if (pair_ok) {
     // 2-CTA pairs (cta_group::2): each CTA loads its 128 A rows and half of the B tile
@@ -247,24 +247,34 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     // persistent, double-buffered-accumulator kernel: one CTA per SM, deep smem ring
     static bool attr2 = false;
     if (!attr2) {
-      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      const int mx = 227 * 1024;
+      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_FAST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GEGLU, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GENERIC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_FAST, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GEGLU, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
       attr2 = true;
     }
-    int ps = c.force_stages ? c.force_stages : std::max(2, std::min(8, (186 * 1024) / stage_bytes));
+    // short-K GEMMs are epilogue-bound: 3 epilogue warps per lane quadrant (448 threads) instead of 2
+    const int np = (g.nk <= c.gemm_epi3_max_nk && g.BN > 64 && g.act == 0 && g.out32 == nullptr && g.alpha == 1.0f) ? 3 : 2;
+    const int budget = (227 - 3) * 1024 - 4 * np * EPI_WARP_BYTES;
+    int ps = c.force_stages ? c.force_stages : std::max(2, std::min(8, budget / stage_bytes));
     g.stages = ps;
-    const size_t psmem = gemmp_smem_bytes(ps, g.BN);
+    const size_t psmem = gemmp_smem_bytes(ps, g.BN, np);
     RFB_CHECK(psmem <= 227 * 1024, "GEMM smem over budget");
     const int m_tiles = (int)grid.x, n_tiles = (int)grid.y;
     const int total = m_tiles * n_tiles * (int)grid.z;
     const int ctas = std::min(total, c.num_sms);
-    if (g.geglu)
-      gemm_persist_kernel<EPI_GEGLU><<<ctas, GEMMP_THREADS, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
-    else if (g.act == 0 && g.out32 == nullptr && g.alpha == 1.0f)
-      gemm_persist_kernel<EPI_FAST><<<ctas, GEMMP_THREADS, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
-    else
-      gemm_persist_kernel<EPI_GENERIC><<<ctas, GEMMP_THREADS, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
+    const int thr = 64 + np * 128;
+    if (g.geglu) {
+      if (np == 3) gemm_persist_kernel<EPI_GEGLU, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
+      else gemm_persist_kernel<EPI_GEGLU, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
+    } else if (g.act == 0 && g.out32 == nullptr && g.alpha == 1.0f) {
+      if (np == 3) gemm_persist_kernel<EPI_FAST, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
+      else gemm_persist_kernel<EPI_FAST, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
+    } else {
+      gemm_persist_kernel<EPI_GENERIC, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
+    }
   } else {
     gemm_tc_kernel<<<grid, GEMM_THREADS, smem, c.stream>>>(tmA, tmB, g);
   }

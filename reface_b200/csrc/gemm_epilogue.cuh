@@ -71,30 +71,45 @@ __device__ __forceinline__ EpiTile epi_tile_info(const GemmArgs& g, int q, int m
   return t;
 }
 
+// One tile AHEAD: this warp's bias columns into 4 registers per lane (2 chunks x 2 floats) and the residual lines of
+// the tile into L2 -- issued before the current tile is drained, so the latencies are off the critical path.
+template <int MODE, int NP>
+__device__ __forceinline__ void epilogue_lookahead(const GemmArgs& g, const EpiTile& t, int lane, int half,
+                                                   float (&nb)[4]) {
+#pragma unroll
+  for (int ci = 0; ci < 2; ++ci) {
+    const int c0 = half * 64 + ci * (NP * 64);  // `half` = part index of this warp inside its lane quadrant
+    nb[2 * ci] = nb[2 * ci + 1] = 0.f;
+    if (c0 >= t.ncols) continue;
+    const int ocol0 = t.ocol_tile + c0;
+    if (g.bias && MODE != EPI_GEGLU) {
+      const int c1 = ocol0 + lane, c2 = ocol0 + 32 + lane;
+      if (c1 < g.N && lane < t.ncols - c0) nb[2 * ci] = __ldg(g.bias + c1);
+      if (c2 < g.N && 32 + lane < t.ncols - c0) nb[2 * ci + 1] = __ldg(g.bias + c2);
+    }
+    if (g.res && t.vec_ok && ocol0 < t.NO) {
+      const long long gm = t.m_base + lane;
+      if (gm < g.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.res + t.zoff + gm * g.ldr + ocol0));
+    }
+  }
+}
+
 // Phase A -- runs while the MMAs of this tile are still in flight.
-//   wbuf: this warp's smem region (two staging tiles, then the bias strip)
-template <int MODE>
+//   wbuf: this warp's smem region (staging tile, then the bias strip); nb: bias values from epilogue_lookahead
+template <int MODE, int NP>
 __device__ __forceinline__ void epilogue_prefetch(const GemmArgs& g, const EpiTile& t, uint32_t wbuf, int lane, int half,
-                                                  int n_tile) {
+                                                  int n_tile, const float (&nb)[4]) {
   const uint32_t bias_s = wbuf + EPI_STAGE_BYTES;
 #pragma unroll
   for (int ci = 0; ci < 2; ++ci) {
-    const int c0 = half * 64 + ci * 128;
+    const int c0 = half * 64 + ci * (NP * 64);  // `half` = part index of this warp inside its lane quadrant
     if (c0 >= t.ncols) break;
     const int ocol0 = t.ocol_tile + c0;
     const int cvalid = min(64, min(t.ncols - c0, t.NO - ocol0));
     if (cvalid <= 0) continue;
-    if (g.bias) {
-      if (MODE == EPI_GEGLU) {
-        // value bias at [0,64), gate bias at [64,128) of this chunk's half of the strip is too small: GEGLU reads
-        // its two biases directly (they are contiguous, 16-byte loads), see epilogue_drain
-      } else {
-        // 64 floats of this chunk -> strip[ci*64 ..]
-        for (int j = lane; j < 64; j += 32) {
-          const int col = ocol0 + j;
-          sts32f(bias_s + (uint32_t)(ci * 64 + j) * 4u, col < g.N ? __ldg(g.bias + col) : 0.f);
-        }
-      }
+    if (g.bias && MODE != EPI_GEGLU) {  // GEGLU reads its two bias vectors directly in epilogue_drain
+      sts32f(bias_s + (uint32_t)(ci * 64 + lane) * 4u, nb[2 * ci]);
+      sts32f(bias_s + (uint32_t)(ci * 64 + 32 + lane) * 4u, nb[2 * ci + 1]);
     }
     if (g.res && t.vec_ok) {
       // first chunk: residual rows straight into the (idle) staging tile; second chunk: pull its lines into L2
@@ -120,7 +135,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmArgs& g, const EpiTi
 
 // Phase B -- drains this warp's 32 accumulator rows (TMEM lanes q*32..q*32+31).
 //   trow : TMEM address of (lane quadrant, accumulator stage, column 0)
-template <int MODE>
+template <int MODE, int NP>
 __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile& t, uint32_t trow, uint32_t wbuf, int lane,
                                                int half, int n_tile) {
   const int BN = g.BN;
@@ -132,7 +147,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile&
 
 #pragma unroll
   for (int ci = 0; ci < 2; ++ci) {
-    const int c0 = half * 64 + ci * 128;
+    const int c0 = half * 64 + ci * (NP * 64);  // `half` = part index of this warp inside its lane quadrant
     if (c0 >= t.ncols) break;
     const int ocol0 = t.ocol_tile + c0;
     const int cvalid = min(64, min(t.ncols - c0, t.NO - ocol0));  // warp-uniform

@@ -176,21 +176,37 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t ti = 0;
     long long t_wait = 0, t_pre = 0;
     const long long t_ebegin = clock64();
+    float nb[4] = {0.f, 0.f, 0.f, 0.f};
+    auto tile_info = [&](int pt, int& m_tile, int& n_tile, int& z) {
+      z = pt / per_z;
+      const int rem = pt - z * per_z;
+      const int mp = rem / n_tiles;
+      n_tile = rem - mp * n_tiles;
+      m_tile = 2 * mp + (int)rank;
+      return epi_tile_info<MODE>(g, q, m_tile, n_tile, z);
+    };
+    if (pair_id < total_pairs) {
+      int a, b, c2;
+      const EpiTile e0 = tile_info(pair_id, a, b, c2);
+      epilogue_lookahead<MODE, 2>(g, e0, lane, half, nb);
+    }
     for (int pt = pair_id; pt < total_pairs; pt += num_pairs, ++ti) {
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
-      const int z = pt / per_z;
-      const int rem = pt - z * per_z;
-      const int mp = rem / n_tiles, n_tile = rem - mp * n_tiles;
-      const int m_tile = 2 * mp + (int)rank;
-      const EpiTile et = epi_tile_info<MODE>(g, q, m_tile, n_tile, z);
+      int m_tile, n_tile, z;
+      const EpiTile et = tile_info(pt, m_tile, n_tile, z);
       const long long tp0 = g.dbg ? clock64() : 0;
-      epilogue_prefetch<MODE>(g, et, stage, lane, half, n_tile);  // bias / residual while the MMAs still run
+      epilogue_prefetch<MODE, 2>(g, et, stage, lane, half, n_tile, nb);  // bias / residual while the MMAs still run
+      if (pt + num_pairs < total_pairs) {  // next tile's bias -> registers, residual lines -> L2
+        int a, b, c2;
+        const EpiTile en = tile_info(pt + num_pairs, a, b, c2);
+        epilogue_lookahead<MODE, 2>(g, en, lane, half, nb);
+      }
       const long long tw0 = g.dbg ? clock64() : 0;
       mbar_wait(bar_accf + 8u * as, aph);
       if (g.dbg) t_wait += clock64() - tw0, t_pre += tw0 - tp0;
       tc_fence_after();
       const uint32_t trow = tmem_base + as * 256u + ((uint32_t)(q * 32) << 16);
-      epilogue_drain<MODE>(g, et, trow, stage, lane, half, n_tile);
+      epilogue_drain<MODE, 2>(g, et, trow, stage, lane, half, n_tile);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -18,13 +18,15 @@ namespace rfb {
 static constexpr int GEMMP_THREADS = 320;
 static constexpr int GEMMP_EPI_WARPS = 8;
 
-__host__ __device__ inline size_t gemmp_smem_bytes(int stages, int BN) {
+// NP = epilogue warps per TMEM lane quadrant (2 for MMA-bound shapes; 3 for short-K, epilogue-bound GEMMs whose
+// per-warp latency chains need more warps in flight)
+__host__ __device__ inline size_t gemmp_smem_bytes(int stages, int BN, int np = 2) {
   return 2048 + (size_t)stages * (GEMM_A_STAGE_BYTES + (size_t)BN * 128) + 16 * stages + 128 +
-         (size_t)GEMMP_EPI_WARPS * EPI_WARP_BYTES;
+         (size_t)(4 * np) * EPI_WARP_BYTES;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(GEMMP_THREADS, 1)
+template <int MODE, int NP>
+__global__ void __launch_bounds__(64 + NP * 128, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g,
                     const int m_tiles, const int n_tiles, const int total_tiles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -49,7 +51,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accf + 8u * i, 1);
-      mbar_init(bar_acce + 8u * i, GEMMP_EPI_WARPS);
+      mbar_init(bar_acce + 8u * i, 4 * NP);
     }
     fence_mbar_init();
   }
@@ -148,17 +150,32 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = e >> 2;  // which 64-column chunks this warp drains
     const uint32_t stage = epi_stage + (uint32_t)e * EPI_WARP_BYTES;  // this warp's staging tile + bias strip
     uint32_t ti = 0;
+    float nb[4] = {0.f, 0.f, 0.f, 0.f};
+    auto tile_info = [&](int tile, int& m_tile, int& n_tile, int& z) {
+      z = tile / per_z;
+      const int rem = tile - z * per_z;
+      m_tile = rem / n_tiles, n_tile = rem - m_tile * n_tiles;
+      return epi_tile_info<MODE>(g, q, m_tile, n_tile, z);
+    };
+    if ((int)blockIdx.x < total_tiles) {
+      int a, b, c2;
+      const EpiTile e0 = tile_info(blockIdx.x, a, b, c2);
+      epilogue_lookahead<MODE, NP>(g, e0, lane, half, nb);
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
-      const int z = tile / per_z;
-      const int rem = tile - z * per_z;
-      const int m_tile = rem / n_tiles, n_tile = rem - m_tile * n_tiles;
-      const EpiTile et = epi_tile_info<MODE>(g, q, m_tile, n_tile, z);
-      epilogue_prefetch<MODE>(g, et, stage, lane, half, n_tile);  // bias / residual while the MMAs still run
+      int m_tile, n_tile, z;
+      const EpiTile et = tile_info(tile, m_tile, n_tile, z);
+      epilogue_prefetch<MODE, NP>(g, et, stage, lane, half, n_tile, nb);  // bias / residual while the MMAs still run
+      if (tile + (int)gridDim.x < total_tiles) {  // next tile's bias -> registers, residual lines -> L2
+        int a, b, c2;
+        const EpiTile en = tile_info(tile + gridDim.x, a, b, c2);
+        epilogue_lookahead<MODE, NP>(g, en, lane, half, nb);
+      }
       mbar_wait(bar_accf + 8u * as, aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + as * 256u + ((uint32_t)(q * 32) << 16);
-      epilogue_drain<MODE>(g, et, trow, stage, lane, half, n_tile);
+      epilogue_drain<MODE, NP>(g, et, trow, stage, lane, half, n_tile);
       // this warp has finished reading the accumulator stage
       tc_fence_before();
       __syncwarp();
