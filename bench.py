@@ -35,6 +35,15 @@ def peaks():
     return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def traffic_from_profiles():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, averaged over the launches of
+    the committed `ncu --set full` capture (profiles/r01_traffic.json, written by scripts/ncu_summary.py)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("dram_bytes_per_launch")
+    return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -222,7 +231,8 @@ def main():
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches),
                 roofline=dict(bound="tensor", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s",
-                              frac=achieved / pk["tflops"], traffic=None, kernel="gemm_tc_kernel",
+                              frac=achieved / pk["tflops"], traffic=traffic_from_profiles(),
+                              kernel="gemm_persist_kernel (tcgen05 GEMM / implicit-GEMM conv) + attn_flash_kernel",
                               launches_per_step=int(g_n), kernel_ms_per_step=g_ms, alg_tflop_per_step=g_flops / 1e12,
                               share_of_step=g_ms / (ms / args.steps), peak_source=pk["source"] + ", sustained bf16",
                               whole_path_frac=(value / world) * fpf / (pk["tflops"] * 1e12) if fpf else None),
