@@ -108,6 +108,11 @@ int rfb_op_layernorm(rfb_ctx* ctx, const float* x, const float* gamma, const flo
 int rfb_op_attention(rfb_ctx* ctx, const float* qkv, int N, int L, int heads, int d, float scale, float* out,
                      void* stream);
 
+/* Kernel-only timing of the HBM-bound normalisation kernels (kind 0: GroupNorm(32)+SiLU as in ResBlock.in_layers,
+ * openaimodel.py:203-206; kind 1: LayerNorm as in BasicTransformerBlock, attention.py:232-234) on device-resident
+ * NHWC fp16 tensors [N,H,W,C]; CUDA events on `stream`. */
+int rfb_bench_norm(rfb_ctx* ctx, int kind, int N, int C, int H, int W, int iters, double* ms_per_launch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

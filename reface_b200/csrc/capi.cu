@@ -139,6 +139,8 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "gemm_smem_budget") c.gemm_smem_budget = (int)value;
   else if (k == "attn_flash") c.attn_flash = (int)value;
   else if (k == "profile") c.profile = (int)value;
+  else if (k == "gn_fused") c.gn_fused = (int)value;
+  else if (k == "ln_vec") c.ln_vec = (int)value;
   else if (k == "gemm_persistent") c.gemm_persistent = (int)value;
   else if (k == "gemm_pair") c.gemm_pair = (int)value;
   else if (k == "gemm_kmerge") c.gemm_kmerge = (int)value;
@@ -436,6 +438,37 @@ int rfb_op_attention(rfb_ctx* h, const float* qkv, int N, int L, int heads, int 
   attention(c, q16, 3 * C, N, L, heads, d, o16, C, scale, 0, C, 2 * C);
   f16_to_f32_kernel<<<grid_for(n_out), 256, 0, c.stream>>>(o16, out, n_out);
   CUDA_OK(cudaGetLastError());
+  c.release(mk);
+  API_END
+}
+
+/* Kernel-only timing of the HBM-bound normalisation ops on device-resident fp16 tensors (CUDA events on the
+ * launching stream, `iters` back-to-back launches after one warm-up); kind 0 = GroupNorm(32)+SiLU, 1 = LayerNorm. */
+int rfb_bench_norm(rfb_ctx* h, int kind, int N, int C, int H, int W, int iters, double* ms_per_launch, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  const size_t mk = c.mark();
+  Tens x = c.new_tens(N, H, W, C);
+  CUDA_OK(cudaMemsetAsync(x.p, 0x3c, (size_t)x.rows() * C * sizeof(__half), c.stream));  // 0x3c3c = 1.0586
+  float* gb = c.alloc_t<float>((size_t)2 * C);
+  CUDA_OK(cudaMemsetAsync(gb, 0, (size_t)2 * C * sizeof(float), c.stream));
+  cudaEvent_t a, b;
+  CUDA_OK(cudaEventCreate(&a));
+  CUDA_OK(cudaEventCreate(&b));
+  for (int it = -1; it < iters; ++it) {
+    if (it == 0) CUDA_OK(cudaEventRecord(a, c.stream));
+    const size_t m2 = c.mark();
+    if (kind == 0) groupnorm(c, x, gb, gb + C, 1e-5f, true);
+    else layernorm(c, x, gb, gb + C, 1e-5f);
+    c.release(m2);
+  }
+  CUDA_OK(cudaEventRecord(b, c.stream));
+  CUDA_OK(cudaEventSynchronize(b));
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, a, b));
+  CUDA_OK(cudaEventDestroy(a));
+  CUDA_OK(cudaEventDestroy(b));
+  *ms_per_launch = (double)ms / iters;
   c.release(mk);
   API_END
 }

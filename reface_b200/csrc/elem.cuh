@@ -254,6 +254,135 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
   }
 }
 
+// Single-launch GroupNorm: the GN_CLUSTER CTAs of one sample form a thread-block cluster.  Each CTA reduces its pixel
+// slab (fp32 sums, fixed order), the per-group partials are exchanged through distributed shared memory and folded in
+// rank order (bitwise reproducible and independent of the batch size), then the CTA normalises the slab it has just
+// read (second read served by L2).  HBM traffic: x once + y once; one launch instead of stats / finalize / apply.
+// blockDim = (C/8) * R as above; dynamic smem = ((R + 1) * 2C + 4G) floats.
+static constexpr int GN_CLUSTER = 8;
+__device__ __forceinline__ float dsmem_ld_f32(uint32_t saddr, uint32_t cta) {
+  float v;
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %1, %2;\n"
+      "ld.shared::cluster.f32 %0, [ra];\n"
+      "}\n"
+      : "=f"(v)
+      : "r"(saddr), "r"(cta)
+      : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(1024, 1)
+gn_fused_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                __half* __restrict__ y, int HW, int C, int G, float eps, int silu) {
+  extern __shared__ float sh[];
+  const int cv = C >> 3;
+  const int R = blockDim.x / cv;
+  const int cq = threadIdx.x % cv, pr = threadIdx.x / cv;
+  const int n = blockIdx.y;
+  const int S = gridDim.x;  // == cluster size
+  const int rank = blockIdx.x;
+  const int per = (HW + S - 1) / S;
+  const int p0 = rank * per;
+  const int p1 = min(HW, p0 + per);
+  float* chs = sh + (size_t)R * 2 * C;  // [2C]
+  float* part = chs + 2 * C;            // [2G] this CTA's per-group sums (read by the whole cluster)
+  float* stat = part + 2 * G;           // [2G] mean / rstd
+  const __half* xn = x + (long long)n * HW * C + cq * 8;
+  {
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+#pragma unroll 8
+    for (int p = p0 + pr; p < p1; p += R) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * C));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack_h2(w[t]);
+        s[2 * t] += f.x;
+        ss[2 * t] = fmaf(f.x, f.x, ss[2 * t]);
+        s[2 * t + 1] += f.y;
+        ss[2 * t + 1] = fmaf(f.y, f.y, ss[2 * t + 1]);
+      }
+    }
+    float* shp = sh + (size_t)pr * 2 * C + (size_t)cq * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      shp[2 * j] = s[j];
+      shp[2 * j + 1] = ss[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float a = 0.f;
+    for (int rr = 0; rr < R; ++rr) a += sh[(size_t)rr * 2 * C + i];
+    chs[i] = a;
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  if (threadIdx.x < 2 * G) {
+    const int gi = threadIdx.x >> 1, which = threadIdx.x & 1;
+    float a = 0.f;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) a += chs[2 * c + which];
+    part[threadIdx.x] = a;
+  }
+  cluster_sync_all();  // every CTA's partials are visible cluster-wide
+  if (threadIdx.x < 2 * G) {
+    const uint32_t a0 = smem_u32(part + threadIdx.x);
+    float a = 0.f;
+    for (int rk = 0; rk < S; ++rk) a += dsmem_ld_f32(a0, (uint32_t)rk);
+    chs[threadIdx.x] = a;  // chs is free again: group totals (sum, sum of squares interleaved)
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // done reading the peers' smem
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const float cnt = (float)cpg * (float)HW;
+    const float mean = chs[2 * threadIdx.x] / cnt;
+    const float var = fmaxf(chs[2 * threadIdx.x + 1] / cnt - mean * mean, 0.f);
+    stat[2 * threadIdx.x] = mean;
+    stat[2 * threadIdx.x + 1] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  {
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cq * 8 + j;
+      const int gi = c / cpg;
+      a[j] = stat[2 * gi + 1] * __ldg(gamma + c);
+      b[j] = __ldg(beta + c) - stat[2 * gi] * a[j];
+    }
+    __half* yn = y + (long long)n * HW * C + cq * 8;
+#pragma unroll 4
+    for (int p = p0 + pr; p < p1; p += R) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * C));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      float v[8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack_h2(w[t]);
+        v[2 * t] = f.x;
+        v[2 * t + 1] = f.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(v[j], a[j], b[j]);
+        if (silu) t = __fdividef(t, 1.0f + __expf(-t));
+        v[j] = t;
+      }
+      uint4 o;
+      o.x = pack_h2(v[0], v[1]);
+      o.y = pack_h2(v[2], v[3]);
+      o.z = pack_h2(v[4], v[5]);
+      o.w = pack_h2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(yn + (long long)p * C) = o;
+    }
+  }
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // peers may still be reading `part`
+}
+
 // ------------------------------------------------------------------ LayerNorm: one warp per row, C % 64 == 0, C <= 2048
 __global__ void layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, __half* __restrict__ y, long long rows, int C,
@@ -289,6 +418,67 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, const float* __re
       const float b = (v[k].y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
       yp[lane + 32 * k] = __floats2half2_rn(a, b);
     }
+}
+
+// Vectorised LayerNorm: LPR lanes share a row (32/LPR rows per warp), every lane keeps VPL 16-byte vectors of the row
+// in registers (C = 8 * LPR * VPL).  Global traffic is 16 B per lane and fully coalesced (a warp instruction covers
+// 32/LPR contiguous 128-byte-aligned row segments); same two-pass fp32 statistics as layernorm_kernel.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_vec_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     __half* __restrict__ y, long long rows, long long ldx, long long ldy, float eps) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int C = 8 * LPR * VPL;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row = ((long long)blockIdx.x * 8 + warp) * RPW + lane / LPR;
+  const int sub = lane % LPR;
+  const bool ok = row < rows;
+  const uint4* xp = reinterpret_cast<const uint4*>(x + (ok ? row : 0) * ldx);
+  uint4 u[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) u[k] = __ldg(xp + sub + LPR * k);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = unpack_h2(w[t]);
+      s += f.x + f.y;
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / (float)C);
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = unpack_h2(w[t]);
+      const float a = f.x - mean, b = f.y - mean;
+      ss = fmaf(a, a, ss);
+      ss = fmaf(b, b, ss);
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss * (1.0f / (float)C) + eps);
+  uint4* yp = reinterpret_cast<uint4*>(y + (ok ? row : 0) * ldy);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int c0 = 8 * (sub + LPR * k);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    const float2 f0 = unpack_h2(u[k].x), f1 = unpack_h2(u[k].y), f2 = unpack_h2(u[k].z), f3 = unpack_h2(u[k].w);
+    uint4 o;
+    o.x = pack_h2(fmaf((f0.x - mean) * rstd, g0.x, b0.x), fmaf((f0.y - mean) * rstd, g0.y, b0.y));
+    o.y = pack_h2(fmaf((f1.x - mean) * rstd, g0.z, b0.z), fmaf((f1.y - mean) * rstd, g0.w, b0.w));
+    o.z = pack_h2(fmaf((f2.x - mean) * rstd, g1.x, b1.x), fmaf((f2.y - mean) * rstd, g1.y, b1.y));
+    o.w = pack_h2(fmaf((f3.x - mean) * rstd, g1.z, b1.z), fmaf((f3.y - mean) * rstd, g1.w, b1.w));
+    if (ok) yp[sub + LPR * k] = o;
+  }
 }
 
 // ------------------------------------------------------------------ row softmax (materialised attention path)

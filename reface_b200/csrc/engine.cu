@@ -455,6 +455,29 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
   const int HW = x.h * x.w, C = x.c, cv = C / 8;
   RFB_CHECK(cv <= 1024, "GroupNorm: too many channels");
   const int R = std::max(1, 512 / cv);
+  if (c.gn_fused) {
+    // one launch: a cluster of GN_CLUSTER CTAs per sample (statistics exchanged through DSMEM), see elem.cuh
+    static bool attr = false;
+    if (!attr) {
+      CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)GN_CLUSTER, (unsigned)x.n);
+    cfg.blockDim = dim3((unsigned)(cv * R));
+    cfg.dynamicSmemBytes = ((size_t)(R + 1) * 2 * C + 4 * 32) * sizeof(float);
+    cfg.stream = c.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = GN_CLUSTER, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    RFB_CHECK(cfg.dynamicSmemBytes <= 96 * 1024, "GroupNorm: smem over budget");
+    CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const __half*)x.p, gamma, beta, y.p, HW, C, 32, eps,
+                               silu ? 1 : 0));
+    LAUNCH_CHECK(c);
+    return y;
+  }
   // the slab partition depends on the tensor shape only (never on the batch size): bitwise batch-independence
   const int slab = std::max(R, (HW + 63) / 64);
   const int nslab = (HW + slab - 1) / slab;
@@ -475,10 +498,36 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
   return y;
 }
 
+// 16-byte-vectorised LayerNorm where C = 8 * LPR * VPL fits (LPR lanes per row, VPL vectors per lane)
+template <int LPR, int VPL>
+static void launch_ln_vec(Ctx& c, const __half* x, const float* gamma, const float* beta, __half* y, long long rows,
+                          long long ldx, long long ldy, float eps) {
+  const long long rows_per_block = 8 * (32 / LPR);
+  layernorm_vec_kernel<LPR, VPL><<<(unsigned)((rows + rows_per_block - 1) / rows_per_block), 256, 0, c.stream>>>(
+      x, gamma, beta, y, rows, ldx, ldy, eps);
+  LAUNCH_CHECK(c);
+}
+bool layernorm_vec(Ctx& c, const __half* x, const float* gamma, const float* beta, __half* y, long long rows, int C,
+                   long long ldx, long long ldy, float eps) {
+  if ((C & 7) || (ldx & 7) || (ldy & 7)) return false;
+  const int nv = C >> 3;
+#define RFB_LN_CASE(LPR, VPL)                                                 \
+  if (nv == LPR * VPL) {                                                      \
+    launch_ln_vec<LPR, VPL>(c, x, gamma, beta, y, rows, ldx, ldy, eps);       \
+    return true;                                                              \
+  }
+  RFB_LN_CASE(32, 5) RFB_LN_CASE(32, 4) RFB_LN_CASE(32, 3) RFB_LN_CASE(32, 2) RFB_LN_CASE(32, 1)
+  RFB_LN_CASE(16, 5) RFB_LN_CASE(16, 3) RFB_LN_CASE(16, 1)
+  RFB_LN_CASE(8, 5) RFB_LN_CASE(8, 3) RFB_LN_CASE(8, 1)
+#undef RFB_LN_CASE
+  return false;
+}
+
 Tens layernorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps) {
   RFB_CHECK(x.c % 64 == 0 && x.c <= 2048, "LayerNorm: C must be a multiple of 64, <= 2048");
   Tens y = c.new_tens(x.n, x.h, x.w, x.c);
   const long long rows = x.rows();
+  if (c.ln_vec && layernorm_vec(c, x.p, gamma, beta, y.p, rows, x.c, x.c, x.c, eps)) return y;
   layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, c.stream>>>(x.p, gamma, beta, y.p, rows, x.c, x.c, x.c, eps);
   LAUNCH_CHECK(c);
   return y;

@@ -73,10 +73,12 @@ struct Ctx {
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
   long long launches = 0;     // kernels launched by this library (reported by bench)
   int gemm_smem_budget = 110 * 1024;  // per-CTA smem target (2 CTAs/SM)
-  int force_bn = 0, force_stages = 0, attn_flash = 1, gemm_persistent = 1, gemm_kmerge = 1;
+  int force_bn = 0, force_stages = 0, attn_flash = 2, gemm_persistent = 1, gemm_kmerge = 1;
   // 2-CTA (cta_group::2) kernel: correct and faster on isolated long-K GEMMs (1180 vs 1114 TFLOP/s) but measured
   // ~4 % slower over the whole UNet step than 1-CTA tiles (profiles/r01_gemm_sweep_v2.txt) -> opt-in
   int gemm_pair = 0;
+  int gn_fused = 1;  // single-launch cluster GroupNorm (0: stats / finalize / apply kernels)
+  int ln_vec = 1;    // 16-byte-vectorised LayerNorm (0: one warp per row, 4-byte loads)
   int gemm_epi3_max_nk = 10;  // K <= 640: 3 epilogue warps per TMEM lane quadrant
   int gemm_pair_min_nk = 12;  // CTA pairs only for K >= 768: short-K GEMMs are epilogue-bound and measured faster on 1-CTA tiles
   // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "rfb_op_groupnorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "rfb_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _vp, _vp]),
     "rfb_op_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "rfb_bench_norm": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_double), _vp]),
 }
 
 
@@ -316,6 +317,12 @@ class Engine:
         self._ck(self.lib.rfb_op_layernorm(self.h, _ptr(x), _ptr(gamma), _ptr(beta), rows, Cc, float(eps), _ptr(out),
                                            self._stream()))
         return out
+
+    def bench_norm(self, kind, N, Cc, H, W, iters=20):
+        """ms per launch of GroupNorm+SiLU (kind 0) / LayerNorm (kind 1) on a device-resident fp16 [N,H,W,C] tensor."""
+        ms = C.c_double(0.0)
+        self._ck(self.lib.rfb_bench_norm(self.h, int(kind), N, Cc, H, W, iters, C.byref(ms), self._stream()))
+        return ms.value
 
     def op_attention(self, qkv, heads, scale=None):
         qkv = self._in(qkv)

@@ -1,0 +1,44 @@
+"""A/B of engine options over the whole UNet forward (N=16, L=64 by default): builds the UNet once, then times
+REPS forwards per option set.  Usage: python scripts/unet_ab.py "attn_flash=1" "gn_fused=0" "attn_flash=1,gn_fused=0,ln_vec=0"
+(the empty set = current defaults is always run first and last)."""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from reface_b200 import synth
+from reface_b200.runtime import Engine
+
+N = int(os.environ.get("N", 16)); L = int(os.environ.get("L", 64)); REPS = int(os.environ.get("REPS", 5))
+DEFAULTS = {"attn_flash": 2, "gn_fused": 1, "ln_vec": 1, "gemm_pair": 0}
+dev = torch.device("cuda", 0)
+flat = synth.random_flat(dev, 0)
+sd = {k: v for k, v in synth.state_dict_from_flat(flat).items() if k.startswith("model.diffusion_model.")}
+eng = Engine(0)
+eng.load_state_dict(sd)
+eng.build_unet()
+x = torch.randn(N, 9, L, L, device=dev); t = torch.full((N,), 981, device=dev, dtype=torch.long)
+ctx = torch.randn(N, 1, 768, device=dev)
+base = None
+for spec in [""] + sys.argv[1:] + [""]:
+    opts = dict(DEFAULTS)
+    for kv in filter(None, spec.split(",")):
+        k, v = kv.split("=")
+        opts[k] = int(v)
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    eps = eng.unet_forward(x, t, ctx); torch.cuda.synchronize()
+    if base is None:
+        base = eps.clone()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(REPS):
+        eng.unet_forward(x, t, ctx)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / REPS
+    eng.set_option("profile", 1)
+    eng.unet_forward(x, t, ctx)
+    gms, gfl, gn = eng.profile_read()
+    eng.set_option("profile", 0)
+    d = float((eps - base).abs().max() / base.abs().max())
+    print(f"[{spec or 'defaults':40s}] unet forward N={N} L={L}: {ms:7.3f} ms  tensor-core launches {gn} = {gms:7.3f} ms "
+          f"({gfl/gms/1e9:6.1f} TFLOP/s)  other = {ms-gms:6.3f} ms  diff vs defaults {d:.2e}", flush=True)

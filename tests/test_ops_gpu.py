@@ -78,36 +78,57 @@ def test_conv_generic_im2col(engine, N, C, H, O, k, s, pad):
 
 
 @pytest.mark.parametrize("N,C,H,eps,silu", [(2, 320, 16, 1e-5, True), (2, 960, 8, 1e-5, True), (1, 128, 64, 1e-6, True),
-                                            (3, 1280, 4, 1e-6, False), (2, 2560, 8, 1e-5, True)])
-def test_groupnorm(engine, N, C, H, eps, silu):
+                                            (3, 1280, 4, 1e-6, False), (2, 2560, 8, 1e-5, True), (2, 1920, 2, 1e-5, True),
+                                            (1, 512, 32, 1e-6, False), (5, 640, 32, 1e-5, True)])
+@pytest.mark.parametrize("fused", [1, 0])
+def test_groupnorm(engine, N, C, H, eps, silu, fused):
+    """fused=1 (default): one launch, a cluster of 8 CTAs per sample exchanging statistics through DSMEM;
+    fused=0: the three-kernel stats / finalize / apply path."""
     x = h(rn(N, C, H, H, seed=1) * 2 + 0.5)
     gam, bet = 1 + 0.1 * rn(C, seed=2), 0.1 * rn(C, seed=3)
-    y = engine.op_groupnorm(x, gam, bet, eps, silu)
+    engine.set_option("gn_fused", fused)
+    try:
+        y = engine.op_groupnorm(x, gam, bet, eps, silu)
+    finally:
+        engine.set_option("gn_fused", 1)
     ref = F.group_norm(x, 32, gam, bet, eps)
     ref = F.silu(ref) if silu else ref
     assert float((y - ref).abs().max()) < 6e-3
 
 
 @pytest.mark.parametrize("rows,C", [(100, 320), (4096, 640), (17, 1280), (257, 1024), (5, 768)])
-def test_layernorm(engine, rows, C):
+@pytest.mark.parametrize("vec", [1, 0])
+def test_layernorm(engine, rows, C, vec):
+    """vec=1 (default): 16-byte vectorised kernel (several lanes per row); vec=0: one warp per row."""
     x = h(rn(rows, C, seed=1) * 3 + 1)
     gam, bet = 1 + 0.1 * rn(C, seed=2), 0.1 * rn(C, seed=3)
-    y = engine.op_layernorm(x, gam, bet)
+    engine.set_option("ln_vec", vec)
+    try:
+        y = engine.op_layernorm(x, gam, bet)
+    finally:
+        engine.set_option("ln_vec", 1)
     assert float((y - F.layer_norm(x, (C,), gam, bet)).abs().max()) < 6e-3
 
 
 @pytest.mark.parametrize("N,L,heads,d", [(2, 256, 8, 40), (1, 1024, 8, 80), (2, 64, 8, 160), (1, 257, 16, 64),
                                          (1, 256, 1, 512), (2, 16, 8, 40), (1, 4096, 8, 40)])
-@pytest.mark.parametrize("flash", [0, 1])
-def test_attention(engine, N, L, heads, d, flash):
-    """flash=1: fused tcgen05 kernel where the shape allows (d in {40,80}, L % 128 == 0); flash=0: S/P materialised."""
+@pytest.mark.parametrize("flash", [0, 1, 2])
+@pytest.mark.parametrize("gain", [1.0, 3.0])
+def test_attention(engine, N, L, heads, d, flash, gain):
+    """flash=2 (default): fused tcgen05 kernel, O accumulated in TMEM with lazy rescaling, where the shape allows
+    (d in {40,80}, L % 128 == 0); flash=1: first-generation fused kernel; flash=0: S/P materialised.
+    gain=3 makes the scores ~9x larger so that the running maximum moves by more than the lazy-rescale threshold."""
+    if flash == 0 and gain != 1.0:
+        pytest.skip("the materialised path stores the scores in fp16: only exercised at unit gain")
     C = heads * d
     qkv = h(rn(N, L, 3 * C, seed=1))
+    qkv[..., :2 * C] *= gain
+    qkv = h(qkv)
     engine.set_option("attn_flash", flash)
     try:
         y = engine.op_attention(qkv, heads)
     finally:
-        engine.set_option("attn_flash", 1)
+        engine.set_option("attn_flash", 2)
     q, k, v = qkv.chunk(3, dim=-1)
     sp = lambda t: t.reshape(N, L, heads, d).transpose(1, 2)
     ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(N, L, C)
