@@ -522,6 +522,7 @@ static void launch_flash(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, c
     CUDA_OK(cudaEventCreate(&rec.b));
     rec.flops = 4.0 * (double)L * (double)L * (double)d * (double)N * (double)heads;
     rec.kind = 1;
+    rec.M = L, rec.N = L, rec.K = d, rec.BN = DP, rec.z = N * heads;
     CUDA_OK(cudaEventRecord(rec.a, c.stream));
   }
   if (c.attn_flash >= 2)

@@ -1,5 +1,6 @@
 // extern "C" boundary (include/reface_b200.h).  Exceptions never cross it: every entry point returns an
 // error code and stores the message in the context.
+#include <cstdio>
 #include "../../include/reface_b200.h"
 
 #include <cudaTypedefs.h>
@@ -140,6 +141,7 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "attn_flash") c.attn_flash = (int)value;
   else if (k == "profile") c.profile = (int)value;
   else if (k == "gn_fused") c.gn_fused = (int)value;
+  else if (k == "gemm_wave_bn") c.gemm_wave_bn = (int)value;
   else if (k == "ln_vec") c.ln_vec = (int)value;
   else if (k == "gemm_persistent") c.gemm_persistent = (int)value;
   else if (k == "gemm_pair") c.gemm_pair = (int)value;
@@ -167,6 +169,9 @@ int rfb_profile_read(rfb_ctx* h, double* ms, double* flops, long long* n) {
     float e = 0;
     CUDA_OK(cudaEventElapsedTime(&e, r.a, r.b));
     tms += e, tf += r.flops;
+    if (c.profile >= 2)
+      printf("PROF kind=%d M=%d N=%d K=%d BN=%d z=%d mode=%d us=%.2f tflops=%.1f\n", r.kind, r.M, r.N, r.K, r.BN, r.z, r.mode,
+             e * 1e3, r.flops / (e * 1e-3) / 1e12);
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }

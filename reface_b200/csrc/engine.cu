@@ -145,10 +145,29 @@ CUtensorMap make_tmap(Ctx& c, const void* base, int rank, const uint64_t* dims, 
   return m;
 }
 
-int pick_bn(Ctx& c, long long M, int N, bool geglu) {
+int pick_bn(Ctx& c, long long M, int N, bool geglu, int K, bool allow16) {
   if (c.force_bn) return c.force_bn;
   if (geglu) return (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
   if (N <= 32) return 32;
+  if (c.gemm_wave_bn && K >= 1024) {
+    // Long-K GEMMs are MMA-bound: choose the tile width that minimises (waves over the SMs) x (time of one tile).
+    // One 128 x bn x 16 MMA takes max(bn/2, 32 + bn/4) cycles (tensor pipe vs. the 128 B/clk of smem operand reads);
+    // e.g. M=4096, N=1280: bn=256 -> 160 tiles = 2 waves of 128-cycle steps, bn=144 -> 288 tiles = 2 waves of 72.
+    // Widths that are only multiples of 16 need the vectorised epilogue (allow16).  The K order of every output
+    // element's accumulation does not depend on bn, so results stay bitwise independent of the batch size.
+    const long long mt = (M + GEMM_BM - 1) / GEMM_BM;
+    int best = 0;
+    double best_cost = 0;
+    for (int bn = 256; bn >= 32; bn -= 16) {
+      if ((bn & 31) && !allow16) continue;
+      const long long nt = (N + bn - 1) / bn;
+      const long long waves = (mt * nt + c.num_sms - 1) / c.num_sms;
+      const double step = std::max(bn / 2.0, 32.0 + bn / 4.0);
+      const double cost = (double)waves * (step * (K / 16.0) + 8.0 * bn + 1500.0);
+      if (!best || cost < best_cost) best = bn, best_cost = cost;
+    }
+    return best;
+  }
   static const int cand[] = {256, 224, 192, 160, 128, 96, 64, 32};
   int best = 32;
   long long best_cost = -1;
@@ -183,7 +202,8 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     attr_set = true;
   }
   RFB_CHECK(smem <= 227 * 1024, "GEMM smem over budget");
-  RFB_CHECK(g.BN % 32 == 0 && g.BN >= 32 && g.BN <= 256, "BN must be a multiple of 32 in [32,256]");
+  RFB_CHECK(g.BN % 16 == 0 && g.BN >= 32 && g.BN <= 256, "BN must be a multiple of 16 in [32,256]");
+  RFB_CHECK(g.BN % 32 == 0 || c.gemm_persistent, "tile widths that are not multiples of 32 need the persistent kernel");
   if (g.zdiv <= 0) g.zdiv = 1;
   if (g.rows_per_vec <= 0) g.rows_per_vec = 1;
   if (g.o32_rpn <= 0) g.o32_rpn = 1;
@@ -194,6 +214,8 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     CUDA_OK(cudaEventCreate(&rec.b));
     rec.flops = 2.0 * (double)g.M * (double)(g.geglu ? g.N : g.N) * kalg * (double)grid.z;
     rec.kind = 0;
+    rec.M = g.M, rec.N = g.N, rec.K = (int)kalg, rec.BN = g.BN, rec.z = (int)grid.z;
+    rec.mode = g.a_mode * 100 + (g.geglu ? 10 : 0) + (g.res ? 1 : 0) + (g.rowvec ? 2 : 0) + (g.out32 ? 4 : 0);
     CUDA_OK(cudaEventRecord(rec.a, c.stream));
   }
   const bool pair_ok = c.gemm_pair && c.gemm_persistent && Bplain != nullptr && grid.z == 1 && grid.x >= 2 &&
@@ -297,7 +319,8 @@ void gemm(Ctx& c, const __half* A, long long lda, long long M, int K, const __ha
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M = (int)M, g.N = N, g.nk = (K + 63) / 64;
-  g.BN = force_bn ? force_bn : pick_bn(c, M, N, e.geglu != 0);
+  const bool vec_epi = e.out32 == nullptr && (N & 7) == 0 && (ldo & 7) == 0 && (!e.res || (e.ldr & 7) == 0);
+  g.BN = force_bn ? force_bn : pick_bn(c, M, N, e.geglu != 0, K, vec_epi);
   g.a_mode = A_PLAIN, g.b_mode = B_PLAIN;
   fill_epi(g, e, out, ldo);
   const uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
@@ -352,7 +375,8 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.M = (int)M, g.N = w.cout, g.cblocks = w.cin / 64, g.nk = 9 * g.cblocks;
-    g.BN = pick_bn(c, M, w.cout, false);
+    g.BN = pick_bn(c, M, w.cout, false, 9 * w.cin,
+                   e.out32 == nullptr && (w.cout & 7) == 0 && (!e.res || (e.ldr & 7) == 0));
     g.a_mode = A_CONV3, g.b_mode = B_PLAIN;
     g.bw = std::min(x.w, 128);
     g.bh = std::min(x.h, 128 / g.bw);

@@ -77,15 +77,16 @@ struct Ctx {
   // 2-CTA (cta_group::2) kernel: correct and faster on isolated long-K GEMMs (1180 vs 1114 TFLOP/s) but measured
   // ~4 % slower over the whole UNet step than 1-CTA tiles (profiles/r01_gemm_sweep_v2.txt) -> opt-in
   int gemm_pair = 0;
+  int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)
   int gn_fused = 1;  // single-launch cluster GroupNorm (0: stats / finalize / apply kernels)
   int ln_vec = 1;    // 16-byte-vectorised LayerNorm (0: one warp per row, 4-byte loads)
   int gemm_epi3_max_nk = 10;  // K <= 640: 3 epilogue warps per TMEM lane quadrant
   int gemm_pair_min_nk = 12;  // CTA pairs only for K >= 768: short-K GEMMs are epilogue-bound and measured faster on 1-CTA tiles
   // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline)
-  int profile = 0;
+  int profile = 0;       // 1: time every tensor-core launch; 2: also print one line per launch in rfb_profile_read
   int gemm_debug = 0;                       // per-CTA clock64 counters of the last 2-CTA GEMM launch
   unsigned long long* dbg_buf = nullptr;    // [num_sms * 8]
-  struct ProfRec { cudaEvent_t a, b; double flops; int kind; };
+  struct ProfRec { cudaEvent_t a, b; double flops; int kind; int M = 0, N = 0, K = 0, BN = 0, mode = 0, z = 1; };
   std::vector<ProfRec> prof;
   UNet* unet = nullptr;
   VAE* vae = nullptr;
@@ -129,7 +130,7 @@ LinW pack_linear(Ctx& c, const std::string& wname, const std::string& bname);
 LinW pack_linear_rows(Ctx& c, const std::vector<std::string>& wnames);  // concatenated along out (fused QKV)
 LinW pack_geglu(Ctx& c, const std::string& wname, const std::string& bname, int BN);
 Lin32 lin32(Ctx& c, const std::string& wname, const std::string& bname);
-int pick_bn(Ctx& c, long long M, int N, bool geglu);
+int pick_bn(Ctx& c, long long M, int N, bool geglu, int K = 0, bool allow16 = false);
 
 // TMA descriptor (fp16, 128-byte swizzle, zero fill out of bounds); dims/box innermost first, strides in bytes
 CUtensorMap make_tmap(Ctx& c, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
