@@ -141,6 +141,11 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "attn_flash") c.attn_flash = (int)value;
   else if (k == "profile") c.profile = (int)value;
   else if (k == "gn_fused") c.gn_fused = (int)value;
+  else if (k == "gn_cluster") c.gn_cluster = (int)value;
+  else if (k == "gn_threads") c.gn_threads = (int)value;
+  else if (k == "attn_poly") c.attn_poly = (int)value;
+  else if (k == "attn_pad") c.attn_pad = (int)value;
+  else if (k == "attn_stagger") c.attn_stagger = (int)value;
   else if (k == "gemm_wave_bn") c.gemm_wave_bn = (int)value;
   else if (k == "ln_vec") c.ln_vec = (int)value;
   else if (k == "gemm_persistent") c.gemm_persistent = (int)value;
@@ -340,6 +345,19 @@ struct TempParams {  // registers temporaries under "__op." and frees everything
   }
 };
 
+// [rows, 3*heads*d] -> [rows, 3*heads*hs] with zero-filled head slices (test hook for the padded attention layout)
+__global__ void pad_heads_kernel(const __half* __restrict__ src, __half* __restrict__ dst, long long rows, int nh, int d,
+                                 int hs) {
+  const long long total = rows * nh * hs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % hs);
+    const long long t = i / hs;
+    const int h = (int)(t % nh);
+    const long long r = t / nh;
+    dst[i] = e < d ? src[(r * nh + h) * d + e] : __float2half_rn(0.f);
+  }
+}
+
 __global__ void f32_to_f16_kernel(const float* s, __half* d, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     d[i] = __float2half_rn(s[i]);
@@ -440,7 +458,15 @@ int rfb_op_attention(rfb_ctx* h, const float* qkv, int N, int L, int heads, int 
   __half* q16 = c.alloc_t<__half>(n_in);
   __half* o16 = c.alloc_t<__half>(n_out);
   f32_to_f16_kernel<<<grid_for(n_in), 256, 0, c.stream>>>(qkv, q16, n_in);
-  attention(c, q16, 3 * C, N, L, heads, d, o16, C, scale, 0, C, 2 * C);
+  if (c.attn_pad && d < 64) {
+    const int hs = 64;
+    __half* qp = c.alloc_t<__half>((size_t)N * L * 3 * heads * hs);
+    pad_heads_kernel<<<grid_for((long long)N * L * 3 * heads * hs), 256, 0, c.stream>>>(q16, qp, (long long)N * L, 3 * heads, d,
+                                                                                       hs);
+    attention(c, qp, 3 * heads * hs, N, L, heads, d, o16, C, scale, 0, heads * hs, 2 * heads * hs, hs);
+  } else {
+    attention(c, q16, 3 * C, N, L, heads, d, o16, C, scale, 0, C, 2 * C);
+  }
   f16_to_f32_kernel<<<grid_for(n_out), 256, 0, c.stream>>>(o16, out, n_out);
   CUDA_OK(cudaGetLastError());
   c.release(mk);

@@ -254,12 +254,11 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
   }
 }
 
-// Single-launch GroupNorm: the GN_CLUSTER CTAs of one sample form a thread-block cluster.  Each CTA reduces its pixel
+// Single-launch GroupNorm: the CTAs of one sample (gridDim.x = cluster size, 8 or 16) form a thread-block cluster.  Each CTA reduces its pixel
 // slab (fp32 sums, fixed order), the per-group partials are exchanged through distributed shared memory and folded in
 // rank order (bitwise reproducible and independent of the batch size), then the CTA normalises the slab it has just
 // read (second read served by L2).  HBM traffic: x once + y once; one launch instead of stats / finalize / apply.
 // blockDim = (C/8) * R as above; dynamic smem = ((R + 1) * 2C + 4G) floats.
-static constexpr int GN_CLUSTER = 8;
 __device__ __forceinline__ float dsmem_ld_f32(uint32_t saddr, uint32_t cta) {
   float v;
   asm volatile(
@@ -273,7 +272,7 @@ __device__ __forceinline__ float dsmem_ld_f32(uint32_t saddr, uint32_t cta) {
       : "memory");
   return v;
 }
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(512, 2)
 gn_fused_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                 __half* __restrict__ y, int HW, int C, int G, float eps, int silu) {
   extern __shared__ float sh[];
@@ -286,39 +285,49 @@ gn_fused_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, c
   const int per = (HW + S - 1) / S;
   const int p0 = rank * per;
   const int p1 = min(HW, p0 + per);
-  float* chs = sh + (size_t)R * 2 * C;  // [2C]
+  float* chs = sh + max(R * 2 * C, 2 * G * S);  // [2C], behind the reduction scratch / the gathered cluster partials
   float* part = chs + 2 * C;            // [2G] this CTA's per-group sums (read by the whole cluster)
   float* stat = part + 2 * G;           // [2G] mean / rstd
   const __half* xn = x + (long long)n * HW * C + cq * 8;
+  constexpr int UB = 4;  // 16-byte loads in flight per thread (two CTAs per SM: 64 registers)
   {
     float s[8], ss[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
-#pragma unroll 8
-    for (int p = p0 + pr; p < p1; p += R) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * C));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int pb = p0 + pr; pb < p1; pb += UB * R) {
+      uint4 u[UB];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = unpack_h2(w[t]);
-        s[2 * t] += f.x;
-        ss[2 * t] = fmaf(f.x, f.x, ss[2 * t]);
-        s[2 * t + 1] += f.y;
-        ss[2 * t + 1] = fmaf(f.y, f.y, ss[2 * t + 1]);
+      for (int k = 0; k < UB; ++k) {
+        const int p = pb + k * R;
+        u[k] = make_uint4(0u, 0u, 0u, 0u);  // zeros add nothing to either sum
+        if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * C));
+      }
+#pragma unroll
+      for (int k = 0; k < UB; ++k) {
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_h2(w[t]);
+          s[2 * t] += f.x;
+          ss[2 * t] = fmaf(f.x, f.x, ss[2 * t]);
+          s[2 * t + 1] += f.y;
+          ss[2 * t + 1] = fmaf(f.y, f.y, ss[2 * t + 1]);
+        }
       }
     }
-    float* shp = sh + (size_t)pr * 2 * C + (size_t)cq * 16;
+    // sh[pr][k][cq], k = 2 * j + (0: sum, 1: sum of squares): consecutive lanes -> consecutive banks
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      shp[2 * j] = s[j];
-      shp[2 * j + 1] = ss[j];
+      sh[((size_t)pr * 16 + 2 * j) * cv + cq] = s[j];
+      sh[((size_t)pr * 16 + 2 * j + 1) * cv + cq] = ss[j];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 16 * cv; i += blockDim.x) {
+    const int k = i / cv, c8 = i - k * cv;
     float a = 0.f;
-    for (int rr = 0; rr < R; ++rr) a += sh[(size_t)rr * 2 * C + i];
-    chs[i] = a;
+    for (int rr = 0; rr < R; ++rr) a += sh[((size_t)rr * 16 + k) * cv + c8];
+    chs[2 * (c8 * 8 + (k >> 1)) + (k & 1)] = a;
   }
   __syncthreads();
   const int cpg = C / G;
@@ -329,13 +338,16 @@ gn_fused_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, c
     part[threadIdx.x] = a;
   }
   cluster_sync_all();  // every CTA's partials are visible cluster-wide
-  if (threadIdx.x < 2 * G) {
-    const uint32_t a0 = smem_u32(part + threadIdx.x);
-    float a = 0.f;
-    for (int rk = 0; rk < S; ++rk) a += dsmem_ld_f32(a0, (uint32_t)rk);
-    chs[threadIdx.x] = a;  // chs is free again: group totals (sum, sum of squares interleaved)
-  }
+  // gather all S x 2G partials with independent remote loads (sh is free again), then fold them in rank order
+  for (int i = threadIdx.x; i < 2 * G * S; i += blockDim.x)
+    sh[i] = dsmem_ld_f32(smem_u32(part + (i % (2 * G))), (uint32_t)(i / (2 * G)));
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // done reading the peers' smem
+  __syncthreads();
+  if (threadIdx.x < 2 * G) {
+    float a = 0.f;
+    for (int rk = 0; rk < S; ++rk) a += sh[rk * 2 * G + threadIdx.x];
+    chs[threadIdx.x] = a;  // group totals (sum, sum of squares interleaved)
+  }
   __syncthreads();
   if (threadIdx.x < G) {
     const float cnt = (float)cpg * (float)HW;
@@ -355,29 +367,32 @@ gn_fused_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, c
       b[j] = __ldg(beta + c) - stat[2 * gi] * a[j];
     }
     __half* yn = y + (long long)n * HW * C + cq * 8;
-#pragma unroll 4
-    for (int p = p0 + pr; p < p1; p += R) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * C));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-      float v[8];
+    for (int pb = p0 + pr; pb < p1; pb += UB * R) {
+      uint4 u[UB];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = unpack_h2(w[t]);
-        v[2 * t] = f.x;
-        v[2 * t + 1] = f.y;
+      for (int k = 0; k < UB; ++k) {
+        const int p = pb + k * R;
+        if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * C));
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = fmaf(v[j], a[j], b[j]);
-        if (silu) t = __fdividef(t, 1.0f + __expf(-t));
-        v[j] = t;
+      for (int k = 0; k < UB; ++k) {
+        const int p = pb + k * R;
+        if (p < p1) {
+          const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_h2(w[t]);
+            float v0 = fmaf(f.x, a[2 * t], b[2 * t]), v1 = fmaf(f.y, a[2 * t + 1], b[2 * t + 1]);
+            if (silu) {
+              v0 = __fdividef(v0, 1.0f + __expf(-v0));
+              v1 = __fdividef(v1, 1.0f + __expf(-v1));
+            }
+            o[t] = pack_h2(v0, v1);
+          }
+          *reinterpret_cast<uint4*>(yn + (long long)p * C) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
       }
-      uint4 o;
-      o.x = pack_h2(v[0], v[1]);
-      o.y = pack_h2(v[2], v[3]);
-      o.z = pack_h2(v[4], v[5]);
-      o.w = pack_h2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(yn + (long long)p * C) = o;
     }
   }
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // peers may still be reading `part`
@@ -510,14 +525,14 @@ __global__ void softmax_rows_kernel(__half* __restrict__ x, long long rows, int 
 
 // V section of a fused [N, L, ldq] projection -> Vt [N*heads, d, Lp] (keys contiguous), zero padded to Lp
 __global__ void transpose_v_kernel(const __half* __restrict__ v, __half* __restrict__ vt, int N, int L, int heads, int d,
-                                   long long ldq, int Lp) {
+                                   long long ldq, int Lp, int hs) {
   __shared__ __half tile[32][33];
   const int z = blockIdx.z;  // n*heads + h
   const int n = z / heads, h = z % heads;
   const int l0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int l = l0 + i, dd = d0 + threadIdx.x;
-    tile[i][threadIdx.x] = (l < L && dd < d) ? v[((long long)n * L + l) * ldq + h * d + dd] : __float2half_rn(0.f);
+    tile[i][threadIdx.x] = (l < L && dd < d) ? v[((long long)n * L + l) * ldq + h * hs + dd] : __float2half_rn(0.f);
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {

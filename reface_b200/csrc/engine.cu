@@ -415,8 +415,9 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
 // S = scale * Q K^T (fp16, [N*heads, L, Lp]) -> row softmax -> O = P V written to out[N*L, ldo] at column h*d.
 // [ref: ldm/modules/attention.py:204-220]
 void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads, int d, __half* out, long long ldo,
-               float scale, int q_off, int k_off, int v_off) {
-  if (c.attn_flash && attention_flash(c, qkv, ldq, N, L, heads, d, out, ldo, scale, q_off, k_off, v_off)) return;
+               float scale, int q_off, int k_off, int v_off, int hs) {
+  if (hs <= 0) hs = d;
+  if (c.attn_flash && attention_flash(c, qkv, ldq, N, L, heads, d, out, ldo, scale, q_off, k_off, v_off, hs)) return;
   const size_t mk = c.mark();
   const int Z = N * heads;
   const int Lp = round_up(L, 8);
@@ -433,7 +434,7 @@ void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads
     fill_epi(g, e, S, Lp);
     g.zdiv = 1, g.zs_outer = (long long)L * Lp, g.zs_inner = 0;
     const uint64_t dq[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)L, (uint64_t)N};
-    const uint64_t sq[3] = {(uint64_t)d * 2, (uint64_t)ldq * 2, (uint64_t)L * ldq * 2};
+    const uint64_t sq[3] = {(uint64_t)hs * 2, (uint64_t)ldq * 2, (uint64_t)L * ldq * 2};
     const uint32_t bq[4] = {64, 1, 128, 1};
     const uint32_t bk[4] = {64, 1, (uint32_t)g.BN, 1};
     CUtensorMap tmA = make_tmap(c, qkv + q_off, 4, dq, sq, bq);
@@ -445,7 +446,7 @@ void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads
   LAUNCH_CHECK(c);
   {
     dim3 grid((unsigned)((Lp + 31) / 32), (unsigned)((d + 31) / 32), (unsigned)Z), block(32, 8);
-    transpose_v_kernel<<<grid, block, 0, c.stream>>>(qkv + v_off, Vt, N, L, heads, d, ldq, Lp);
+    transpose_v_kernel<<<grid, block, 0, c.stream>>>(qkv + v_off, Vt, N, L, heads, d, ldq, Lp, hs);
     LAUNCH_CHECK(c);
   }
   {
@@ -477,24 +478,27 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
   Tens y = c.new_tens(x.n, x.h, x.w, x.c);
   const size_t mk = c.mark();
   const int HW = x.h * x.w, C = x.c, cv = C / 8;
-  RFB_CHECK(cv <= 1024, "GroupNorm: too many channels");
-  const int R = std::max(1, 512 / cv);
+  RFB_CHECK(cv <= 512, "GroupNorm: too many channels");
+  int R = std::max(1, 512 / cv);
   if (c.gn_fused) {
+    R = std::max(1, std::min(c.gn_threads, 512) / cv);
+    const int GC = c.gn_cluster;
     // one launch: a cluster of GN_CLUSTER CTAs per sample (statistics exchanged through DSMEM), see elem.cuh
     static bool attr = false;
     if (!attr) {
       CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       attr = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)GN_CLUSTER, (unsigned)x.n);
+    cfg.gridDim = dim3((unsigned)GC, (unsigned)x.n);
     cfg.blockDim = dim3((unsigned)(cv * R));
-    cfg.dynamicSmemBytes = ((size_t)(R + 1) * 2 * C + 4 * 32) * sizeof(float);
+    cfg.dynamicSmemBytes = ((size_t)std::max(R * 2 * C, 64 * GC) + 2 * C + 4 * 32) * sizeof(float);
     cfg.stream = c.stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = GN_CLUSTER, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = GC, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
     cfg.attrs = at, cfg.numAttrs = 1;
     RFB_CHECK(cfg.dynamicSmemBytes <= 96 * 1024, "GroupNorm: smem over budget");
     CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const __half*)x.p, gamma, beta, y.p, HW, C, 32, eps,

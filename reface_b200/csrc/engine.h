@@ -73,12 +73,16 @@ struct Ctx {
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
   long long launches = 0;     // kernels launched by this library (reported by bench)
   int gemm_smem_budget = 110 * 1024;  // per-CTA smem target (2 CTAs/SM)
-  int force_bn = 0, force_stages = 0, attn_flash = 2, gemm_persistent = 1, gemm_kmerge = 1;
+  int force_bn = 0, force_stages = 0, attn_flash = 4, gemm_persistent = 1, gemm_kmerge = 1;
   // 2-CTA (cta_group::2) kernel: correct and faster on isolated long-K GEMMs (1180 vs 1114 TFLOP/s) but measured
   // ~4 % slower over the whole UNet step than 1-CTA tiles (profiles/r01_gemm_sweep_v2.txt) -> opt-in
   int gemm_pair = 0;
+  int attn_stagger = 0;  // attention v4: cycles by which the second query tile's softmax starts late
+  int attn_pad = 0;      // test hook: rfb_op_attention repacks q/k/v with 64-element head slices
+  int attn_poly = 0;     // attention v3: exponentials per 8 evaluated on the FMA pipe (0..3)
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)
   int gn_fused = 1;  // single-launch cluster GroupNorm (0: stats / finalize / apply kernels)
+  int gn_cluster = 16, gn_threads = 512;  // fused GroupNorm: CTAs per sample (cluster size), threads per CTA
   int ln_vec = 1;    // 16-byte-vectorised LayerNorm (0: one warp per row, 4-byte loads)
   int gemm_epi3_max_nk = 10;  // K <= 640: 3 epilogue warps per TMEM lane quadrant
   int gemm_pair_min_nk = 12;  // CTA pairs only for K >= 768: short-K GEMMs are epilogue-bound and measured faster on 1-CTA tiles
@@ -136,8 +140,9 @@ int pick_bn(Ctx& c, long long M, int N, bool geglu, int K = 0, bool allow16 = fa
 CUtensorMap make_tmap(Ctx& c, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
                       const uint32_t* box);
 // fused flash-style attention (tcgen05, S and O tiles in TMEM); returns false when the shape is not covered
+// hs = distance in elements between consecutive heads inside a q / k / v section (0: packed, hs = d)
 bool attention_flash(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads, int d, __half* out,
-                     long long ldo, float scale, int q_off, int k_off, int v_off);
+                     long long ldo, float scale, int q_off, int k_off, int v_off, int hs = 0);
 
 // ---- op launchers (all asynchronous on c.stream)
 void gemm(Ctx& c, const __half* A, long long lda, long long M, int K, const __half* W, int kp, int N, __half* out,
@@ -148,7 +153,7 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride = 1, int
                int pad_b = 1, int pad_r = 1);
 Tens linear_t(Ctx& c, const Tens& x, const LinW& w, Epi e);
 void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads, int d, __half* out, long long ldo,
-               float scale, int q_off, int k_off, int v_off);
+               float scale, int q_off, int k_off, int v_off, int hs = 0);
 Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps, bool silu);
 Tens layernorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps);
 Tens upsample2x(Ctx& c, const Tens& x);

@@ -19,14 +19,16 @@ HBM = float(peaks.get("hbm_gbs", 6549.1))
 eng = Engine(0, arena_bytes=16 << 30)
 out = {"attention": [], "groupnorm": [], "layernorm": []}
 
-for (N, L, heads, d) in [(16, 4096, 8, 40), (16, 1024, 8, 80), (4, 16384, 8, 40)]:
+for (N, L, heads, d) in ([] if os.environ.get("ONLY") == "gn" else [(16, 4096, 8, 40), (16, 1024, 8, 80), (4, 16384, 8, 40)]):
     C = heads * d
     qkv = torch.randn(N, L, 3 * C, device="cuda").half().float()
     q, k, v = qkv.chunk(3, dim=-1)
     sp = lambda t: t.reshape(N, L, heads, d).transpose(1, 2)
     ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(N, L, C)
-    for mode in (1, 2):
+    for mode, poly, pad in ((2, 0, 0), (4, 0, 0), (4, 0, 600), (4, 0, 1000), (4, 0, 1400), (4, 0, 1800), (4, 1, 1000), (4, 1, 1400)):
         eng.set_option("attn_flash", mode)
+        eng.set_option("attn_poly", poly)
+        eng.set_option("attn_stagger", pad)
         y = eng.op_attention(qkv, heads)
         err = float((y - ref).abs().max())
         best = 1e9
@@ -38,24 +40,31 @@ for (N, L, heads, d) in [(16, 4096, 8, 40), (16, 1024, 8, 80), (4, 16384, 8, 40)
             best = min(best, ms)
         tf = 4.0 * L * L * d * N * heads / best / 1e9
         exps = N * heads * L * L / (best * 1e-3) / 1e12
-        print(f"attention v{mode} N={N} L={L} d={d}: {best*1e3:8.1f} us  {tf:7.1f} TFLOP/s  {exps:5.2f} Texp/s  "
+        print(f"attention v{mode} poly={poly} stagger={pad} N={N} L={L} d={d}: {best*1e3:8.1f} us  {tf:7.1f} TFLOP/s  {exps:5.2f} Texp/s  "
               f"max_err={err:.2e}", flush=True)
-        out["attention"].append({"mode": mode, "N": N, "L": L, "d": d, "us": best * 1e3, "tflops": tf, "err": err})
+        out["attention"].append({"mode": mode, "poly": poly, "N": N, "L": L, "d": d, "us": best * 1e3, "tflops": tf, "err": err})
     del qkv, ref, y
-eng.set_option("attn_flash", 2)
+eng.set_option("attn_flash", 4)
+eng.set_option("attn_poly", 0)
+eng.set_option("attn_stagger", 0)
+if os.environ.get("ONLY") == "attn":
+    sys.exit(0)
+if os.environ.get("ONLY") == "gn":
+    pass
 
 for (N, Cc, H) in [(16, 320, 64), (16, 640, 64), (16, 960, 64), (16, 640, 32), (16, 1280, 32), (16, 1920, 32),
                    (16, 1280, 16), (16, 2560, 16), (16, 1280, 8), (16, 2560, 8), (8, 128, 512), (8, 256, 256), (2, 320, 64)]:
     row = {"N": N, "C": Cc, "H": H}
-    for mode in (0, 1):
-        eng.set_option("gn_fused", mode)
+    gb = 2.0 * N * Cc * H * H * 2 / 1e9
+    txt = []
+    for name, fused, cl, th in (("split", 0, 8, 512), ("c8t512", 1, 8, 512), ("c16t512", 1, 16, 512), ("c16t256", 1, 16, 256)):
+        eng.set_option("gn_fused", fused); eng.set_option("gn_cluster", cl); eng.set_option("gn_threads", th)
         ms = eng.bench_norm(0, N, Cc, H, H)
-        gb = 2.0 * N * Cc * H * H * 2 / 1e9
-        row["fused" if mode else "split"] = ms * 1e3
-        row["frac_fused" if mode else "frac_split"] = gb / (ms * 1e-3) / HBM
-    print(f"groupnorm N={N} C={Cc} H={H}: split {row['split']:7.1f} us ({row['frac_split']:.2f} of HBM)   "
-          f"fused {row['fused']:7.1f} us ({row['frac_fused']:.2f} of HBM)", flush=True)
+        row[name] = ms * 1e3
+        txt.append(f"{name} {ms*1e3:6.1f} us ({gb / (ms * 1e-3) / HBM:.2f})")
+    print(f"groupnorm N={N} C={Cc} H={H}: " + "  ".join(txt), flush=True)
     out["groupnorm"].append(row)
+eng.set_option("gn_cluster", 16); eng.set_option("gn_threads", 512)
 eng.set_option("gn_fused", 1)
 
 for (N, Cc, H) in [(16, 320, 64), (16, 640, 32), (16, 1280, 16), (16, 1280, 8), (8, 1024, 16)]:

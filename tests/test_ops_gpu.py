@@ -114,8 +114,9 @@ def test_layernorm(engine, rows, C, vec):
 
 
 @pytest.mark.parametrize("N,L,heads,d", [(2, 256, 8, 40), (1, 1024, 8, 80), (2, 64, 8, 160), (1, 257, 16, 64),
-                                         (1, 256, 1, 512), (2, 16, 8, 40), (1, 4096, 8, 40)])
-@pytest.mark.parametrize("flash", [0, 1, 2])
+                                         (1, 256, 1, 512), (2, 16, 8, 40), (1, 4096, 8, 40), (3, 384, 8, 40),
+                                         (2, 1024, 8, 40)])
+@pytest.mark.parametrize("flash", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("gain", [1.0, 3.0])
 def test_attention(engine, N, L, heads, d, flash, gain):
     """flash=2 (default): fused tcgen05 kernel, O accumulated in TMEM with lazy rescaling, where the shape allows
@@ -131,7 +132,7 @@ def test_attention(engine, N, L, heads, d, flash, gain):
     try:
         y = engine.op_attention(qkv, heads)
     finally:
-        engine.set_option("attn_flash", 2)
+        engine.set_option("attn_flash", 4)
     q, k, v = qkv.chunk(3, dim=-1)
     sp = lambda t: t.reshape(N, L, heads, d).transpose(1, 2)
     ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(N, L, C)
