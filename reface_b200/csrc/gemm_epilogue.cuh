@@ -22,6 +22,23 @@ static constexpr int EPI_WARP_BYTES = 4096 + 512;          // staging tile + bia
 enum EpiMode { EPI_FAST = 0, EPI_GEGLU = 1, EPI_GENERIC = 2 };
 
 // exact-erf GELU with a cheap erf (Abramowitz-Stegun 7.1.26, |err| < 1.5e-7: far below the fp16 output ulp)
+// exact-erf GELU in 8 instructions and one MUFU: with u = |x| and E(u) = 1 - Phi(u) = 0.5 * erfc(u / sqrt 2),
+//   gelu(x) = x * Phi(x) = max(x, 0) - u * E(u)          (both signs)
+// and E(u) = 2^-q(u) with q a degree-5 polynomial fitted to -log2(0.5 erfc(u / sqrt 2)) so that the ABSOLUTE error of
+// u * E(u) is minimal: |gelu error| < 5.1e-7 for every fp32 input (q is increasing for all u >= 0, so E -> 0 for large
+// |x| and nothing overflows).  The GEGLU FF GEMMs at 64^2 (K = 320) are bound by the epilogue's instruction issue: the
+// previous Abramowitz-Stegun erf needed ~17 instructions and two MUFUs per element.
+__device__ __forceinline__ float gelu_exp2poly(float x) {
+  const float u = fabsf(x);
+  float q = fmaf(0.0004687140753958374f, u, -0.007054118439555168f);
+  q = fmaf(q, u, 0.05175532400608063f);
+  q = fmaf(q, u, 0.46006664633750916f);
+  q = fmaf(q, u, 1.1507560014724731f);
+  q = fmaf(q, u, 1.0000418424606323f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q));
+  return fmaf(-u, e, fmaxf(x, 0.f));
+}
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
   const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
@@ -186,10 +203,10 @@ __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile&
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          v[4 * j + 0] = (__uint_as_float(acc[4 * j + 0]) + b1[j].x) * gelu_erf_fast(__uint_as_float(gat[4 * j + 0]) + b2[j].x);
-          v[4 * j + 1] = (__uint_as_float(acc[4 * j + 1]) + b1[j].y) * gelu_erf_fast(__uint_as_float(gat[4 * j + 1]) + b2[j].y);
-          v[4 * j + 2] = (__uint_as_float(acc[4 * j + 2]) + b1[j].z) * gelu_erf_fast(__uint_as_float(gat[4 * j + 2]) + b2[j].z);
-          v[4 * j + 3] = (__uint_as_float(acc[4 * j + 3]) + b1[j].w) * gelu_erf_fast(__uint_as_float(gat[4 * j + 3]) + b2[j].w);
+          v[4 * j + 0] = (__uint_as_float(acc[4 * j + 0]) + b1[j].x) * gelu_exp2poly(__uint_as_float(gat[4 * j + 0]) + b2[j].x);
+          v[4 * j + 1] = (__uint_as_float(acc[4 * j + 1]) + b1[j].y) * gelu_exp2poly(__uint_as_float(gat[4 * j + 1]) + b2[j].y);
+          v[4 * j + 2] = (__uint_as_float(acc[4 * j + 2]) + b1[j].z) * gelu_exp2poly(__uint_as_float(gat[4 * j + 2]) + b2[j].z);
+          v[4 * j + 3] = (__uint_as_float(acc[4 * j + 3]) + b1[j].w) * gelu_exp2poly(__uint_as_float(gat[4 * j + 3]) + b2[j].w);
         }
       } else {
         tmem_ld_wait();

@@ -101,8 +101,10 @@ def test_ddim_update_with_noise_bit_exact(engine, oracle):
         # (2) within 1 ulp of the torch-CPU oracle: this torch build's vectorised CPU sqrt is 1 ulp off the correctly
         #     rounded value for some schedule entries (e.g. sqrt(a_prev[7])), the CUDA kernel and numpy are not
         rxp, rp0, _ = oracle.cfg_ddim_update(x, eps2[:2], eps2[2:], 3.5, *a, noise=nz)
-        assert float(((xp.cpu() - rxp).abs() / rxp.abs().clamp_min(1e-3)).max()) < 2.5e-7
-        assert float(((p0.cpu() - rp0).abs() / rp0.abs().clamp_min(1e-3)).max()) < 2.5e-7
+        #     (absolute bound: one ulp of the largest term, |x| < 4 -> 2.4e-7; a relative bound would blow up on the
+        #     elements where the terms cancel)
+        assert float((xp.cpu() - rxp).abs().max()) < 5e-7
+        assert float((p0.cpu() - rp0).abs().max()) < 5e-7 * float(rp0.abs().max().clamp_min(1.0))
     from reface_b200.runtime import ddim_schedule
     s2 = ddim_schedule(50, 0.7)
     assert np.array_equal(s2["sigma"], sch["sigma"])
