@@ -76,6 +76,18 @@ int rfb_ddim_sample(rfb_ctx* ctx, const float* x_T, const float* z_inpaint, cons
                     const float* a_prev, const float* sigma, const float* sqrt_one_minus_a, int n_steps, float cfg_scale,
                     const float* noise, int log_every_t, float* x0_out, float* inter_x, float* inter_pred_x0,
                     void* stream);
+/* PLMSSampler.plms_sampling with test_model_kwargs (ldm/models/diffusion/plms.py:116-242): pseudo improved Euler on
+ * the first step (two UNet evaluations), then Adams-Bashforth of order 2-4 over the last three eps.  Same argument
+ * meaning as rfb_ddim_sample; every sigma must be 0 (plms.py:25-26 raises for eta != 0). */
+int rfb_plms_sample(rfb_ctx* ctx, const float* x_T, const float* z_inpaint, const float* mask, const float* cond,
+                    const float* uncond, int B, int L, int T, const int64_t* timesteps, const float* a_t,
+                    const float* a_prev, const float* sigma, const float* sqrt_one_minus_a, int n_steps, float cfg_scale,
+                    int log_every_t, float* x0_out, float* inter_x, float* inter_pred_x0, void* stream);
+/* DDPM.q_sample (ldm/models/diffusion/ddpm.py:412-415), the --Start_from_target initialisation of
+ * scripts/inference_test_bench.py:414-435: out[b] = coef[2b] * x_start[b] + coef[2b+1] * noise[b] with
+ * coef = (sqrt_alphas_cumprod[t_b], sqrt_one_minus_alphas_cumprod[t_b]) ([host], 2*B floats). */
+int rfb_q_sample(rfb_ctx* ctx, const float* x_start, const float* noise, const float* coef, int B, long long per_sample,
+                 float* out, void* stream);
 /* get_first_stage_encoding(encode_first_stage(x)) (ddpm.py:1402-1439, 850-857; autoencoder.py:324-328;
  * distributions.py:24-37): img [B,3,H,W] -> z = 0.18215*(mean + std*noise) [B,4,H/8,W/8].
  * noise NULL => mode() (z = scaled mean).  mean/logvar outputs optional (NULL). */

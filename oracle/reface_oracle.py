@@ -591,6 +591,72 @@ def ddim_sample(P_unet, x_T, z_inpaint, mask, c, uc, S, scale, eta=0.0, log_ever
     return img, inter
 
 
+def plms_eps_prime(e_t, old_eps, e_t_next=None):
+    """p_sample_plms, plms.py:225-240: pseudo improved Euler on the first step, then Adams-Bashforth of order 2-4."""
+    if len(old_eps) == 0:
+        return (e_t + e_t_next) / 2
+    if len(old_eps) == 1:
+        return (3 * e_t - old_eps[-1]) / 2
+    if len(old_eps) == 2:
+        return (23 * e_t - 16 * old_eps[-1] + 5 * old_eps[-2]) / 12
+    return (55 * e_t - 59 * old_eps[-1] + 37 * old_eps[-2] - 9 * old_eps[-3]) / 24
+
+
+def plms_sample(P_unet, x_T, z_inpaint, mask, c, uc, S, scale, log_every_t=100, cfg=UNET_CFG, n_steps_limit=None):
+    """PLMSSampler.sample with test_model_kwargs (plms.py:58-172 driving p_sample_plms :174-242; eta must be 0, :25-26).
+    Returns (x0, inter)."""
+    sch = ddim_schedule(S, 0.0)
+    ts = sch["timesteps"]
+    total = len(ts)
+    time_range = np.flip(ts)
+    img = x_T
+    inter = {"x_inter": [img], "pred_x0": [img]}
+    b = x_T.shape[0]
+    old_eps = []
+
+    def model_output(x, step):                                   # get_model_output, plms.py:178-192
+        t = torch.full((b,), int(step), dtype=torch.long)
+        x9 = concat9(x, z_inpaint, mask)
+        if uc is None or scale == 1.0:
+            return unet_forward(P_unet, x9, t, c, cfg)
+        e_u, e_c = unet_forward(P_unet, torch.cat([x9] * 2), torch.cat([t] * 2), torch.cat([uc, c]), cfg).chunk(2)
+        return e_u + scale * (e_c - e_u)
+
+    def x_prev_and_pred_x0(x, e, index):                         # get_x_prev_and_pred_x0, plms.py:199-217 (sigma = 0)
+        xp, p0, _ = cfg_ddim_update(x, e, e, 1.0, sch["a_t"][index], sch["a_prev"][index], sch["sigma"][index],
+                                    sch["sqrt_one_minus_a"][index])
+        return xp, p0
+
+    for i, step in enumerate(time_range):
+        if n_steps_limit is not None and i >= n_steps_limit:
+            break
+        index = total - i - 1
+        step_next = time_range[min(i + 1, len(time_range) - 1)]
+        e_t = model_output(img, step)
+        e_next = None
+        if len(old_eps) == 0:
+            x_prev, _ = x_prev_and_pred_x0(img, e_t, index)
+            e_next = model_output(x_prev, step_next)
+        e_prime = plms_eps_prime(e_t, old_eps, e_next)
+        img, pred_x0 = x_prev_and_pred_x0(img, e_prime, index)
+        old_eps.append(e_t)
+        if len(old_eps) >= 4:
+            old_eps.pop(0)
+        if index % log_every_t == 0 or index == total - 1:
+            inter["x_inter"].append(img)
+            inter["pred_x0"].append(pred_x0)
+    return img, inter
+
+
+def q_sample(x_start, t, noise):
+    """DDPM.q_sample (ddpm.py:412-415) with the fp32 buffers of register_schedule (ddpm.py:283-285): the
+    --Start_from_target initialisation of scripts/inference_test_bench.py:414-435."""
+    ac = np.cumprod(1.0 - make_beta_schedule(), axis=0)          # fp64, as in register_schedule
+    sa = torch.tensor(np.sqrt(ac), dtype=torch.float32)[t].reshape(-1, 1, 1, 1)
+    s1 = torch.tensor(np.sqrt(1.0 - ac), dtype=torch.float32)[t].reshape(-1, 1, 1, 1)
+    return sa * x_start + s1 * noise
+
+
 # --------------------------------------------------------------------------------------------
 # specs + whole pipeline (scripts/inference_test_bench.py:438-495)
 # --------------------------------------------------------------------------------------------

@@ -231,6 +231,37 @@ int rfb_ddim_sample(rfb_ctx* h, const float* x_T, const float* z_inpaint, const 
               inter_pred_x0, log_every_t);
   API_END
 }
+int rfb_plms_sample(rfb_ctx* h, const float* x_T, const float* z_inpaint, const float* mask, const float* cond,
+                    const float* uncond, int B, int L, int T, const int64_t* timesteps, const float* a_t,
+                    const float* a_prev, const float* sigma, const float* sqrt_one_minus_a, int n_steps, float cfg_scale,
+                    int log_every_t, float* x0_out, float* inter_x, float* inter_pred_x0, void* stream) {
+  API_BEGIN(h)
+  RFB_CHECK(c.unet, "rfb_build_unet has not been called");
+  c.stream = (cudaStream_t)stream;
+  DdimSchedule s;
+  s.n = n_steps;
+  s.timesteps.assign(timesteps, timesteps + n_steps);
+  s.a_t.assign(a_t, a_t + n_steps);
+  s.a_prev.assign(a_prev, a_prev + n_steps);
+  s.sigma.assign(sigma, sigma + n_steps);
+  s.sqrt_one_minus_a.assign(sqrt_one_minus_a, sqrt_one_minus_a + n_steps);
+  for (int i = 0; i < n_steps; ++i) RFB_CHECK(sigma[i] == 0.0f, "ddim_eta must be 0 for PLMS");  // plms.py:25-26
+  plms_sample(c, *c.unet, x_T, z_inpaint, mask, cond, uncond, B, L, T, s, cfg_scale, x0_out, inter_x, inter_pred_x0,
+              log_every_t);
+  API_END
+}
+int rfb_q_sample(rfb_ctx* h, const float* x_start, const float* noise, const float* coef, int B, long long per_sample,
+                 float* out, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  const size_t mk = c.mark();
+  float* cd = c.alloc_t<float>((size_t)2 * B);
+  CUDA_OK(cudaMemcpyAsync(cd, coef, (size_t)2 * B * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+  q_sample(c, x_start, noise, cd, out, per_sample, B);
+  CUDA_OK(cudaStreamSynchronize(c.stream));  // `coef` is a host array owned by the caller
+  c.release(mk);
+  API_END
+}
 int rfb_vae_encode(rfb_ctx* h, const float* img, const float* noise, int B, int H, int W, float* z, float* mean,
                    float* logvar, void* stream) {
   API_BEGIN(h)

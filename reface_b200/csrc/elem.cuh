@@ -541,6 +541,74 @@ __global__ void transpose_v_kernel(const __half* __restrict__ v, __half* __restr
   }
 }
 
+// ------------------------------------------------------------------ cross-attention with a short context (T <= 16)
+// attention.py:204-221 for context length T > 1 (`stack_feat`-style conditioning): one thread per (token, head).
+// q: [N*L, C] fp16 (to_q of LN2(x)); kc, vc: [N*T, C] fp32 (to_k / to_v of the context, staged in smem per sample);
+// out: [N*L, C] fp16 = softmax_T(scale * q k^T) v.  The score row has only T entries: no tensor cores needed.
+template <int TMAX>
+__global__ void cross_attn_small_kernel(const __half* __restrict__ q, const float* __restrict__ kc,
+                                        const float* __restrict__ vc, __half* __restrict__ out, int L, int T, int C,
+                                        int heads, float scale) {
+  extern __shared__ float kv[];  // [2][T][C]
+  const int n = blockIdx.y;
+  const int d = C / heads;
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+    kv[i] = kc[(long long)n * T * C + i];
+    kv[T * C + i] = vc[(long long)n * T * C + i];
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // token * heads + head
+  if (idx >= L * heads) return;
+  const int tok = idx / heads, h = idx - tok * heads;
+  const __half* qp = q + ((long long)n * L + tok) * C + h * d;
+  float s[TMAX];
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t) s[t] = 0.f;
+  for (int j = 0; j < d; j += 8) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(qp + j));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float qv[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_h2(w[e]);
+      qv[2 * e] = f.x, qv[2 * e + 1] = f.y;
+    }
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t)
+      if (t < T) {
+        const float* kp = kv + t * C + h * d + j;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[t] = fmaf(qv[e], kp[e], s[t]);
+      }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t)
+    if (t < T) s[t] *= scale, mx = fmaxf(mx, s[t]);
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t)
+    if (t < T) s[t] = __expf(s[t] - mx), sum += s[t];
+  const float inv = 1.0f / sum;
+  __half* op = out + ((long long)n * L + tok) * C + h * d;
+  for (int j = 0; j < d; j += 8) {
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t)
+      if (t < T) {
+        const float* vp = kv + (T + t) * C + h * d + j;
+        const float pt = s[t] * inv;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(pt, vp[e], o[e]);
+      }
+    uint4 r;
+    r.x = pack_h2(o[0], o[1]), r.y = pack_h2(o[2], o[3]), r.z = pack_h2(o[4], o[5]), r.w = pack_h2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(op + j) = r;
+  }
+}
+
 // ------------------------------------------------------------------ small-M linear (fp32 in, fp32 weights)
 // out[r, o] = act_out(bias[o] + sum_k act_in(x[r, k]) * W[o, k]) (+ res[r, o]) for r < R <= RMAX.
 // One warp per output column; x is staged (activated once) through shared memory in 512-wide K chunks,
@@ -649,6 +717,45 @@ __global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float*
     const float nz = noise ? __fmul_rn(sigma, noise[i]) : 0.0f;
     x_prev[i] = __fadd_rn(__fadd_rn(__fmul_rn(sqrt_aprev, p0), dir), nz);
     if (pred_x0) pred_x0[i] = p0;
+  }
+}
+
+// classifier-free guidance combine alone (get_model_output, plms.py:184-188): e = e_u + scale * (e_c - e_u)
+__global__ void cfg_combine_kernel(const float* __restrict__ eps2, float* __restrict__ out, long long count, float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const float eu = eps2[i], ec = eps2[count + i];
+    out[i] = __fadd_rn(eu, __fmul_rn(scale, __fsub_rn(ec, eu)));
+  }
+}
+// e_t' of p_sample_plms (plms.py:225-240), same fp32 op order, no FMA contraction.  order = len(old_eps) clipped to 3;
+// o1/o2/o3 = old_eps[-1], [-2], [-3]; e_next only for order 0 (pseudo improved Euler).
+__global__ void plms_combine_kernel(const float* __restrict__ e_t, const float* __restrict__ o1,
+                                    const float* __restrict__ o2, const float* __restrict__ o3,
+                                    const float* __restrict__ e_next, float* __restrict__ out, long long count, int order) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const float e = e_t[i];
+    float r;
+    if (order == 0) {
+      r = __fdiv_rn(__fadd_rn(e, e_next[i]), 2.0f);
+    } else if (order == 1) {
+      r = __fdiv_rn(__fsub_rn(__fmul_rn(3.0f, e), o1[i]), 2.0f);
+    } else if (order == 2) {
+      r = __fdiv_rn(__fadd_rn(__fsub_rn(__fmul_rn(23.0f, e), __fmul_rn(16.0f, o1[i])), __fmul_rn(5.0f, o2[i])), 12.0f);
+    } else {
+      r = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(__fmul_rn(55.0f, e), __fmul_rn(59.0f, o1[i])), __fmul_rn(37.0f, o2[i])),
+                              __fmul_rn(9.0f, o3[i])),
+                    24.0f);
+    }
+    out[i] = r;
+  }
+}
+// DDPM.q_sample (ddpm.py:412-415): out = sqrt_ac[t[b]] * x0 + sqrt_1m_ac[t[b]] * noise, per sample b
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                const float* __restrict__ coef, float* __restrict__ out, long long per_sample, int B) {
+  const long long total = per_sample * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_sample);
+    out[i] = __fadd_rn(__fmul_rn(coef[2 * b], x0[i]), __fmul_rn(coef[2 * b + 1], noise[i]));
   }
 }
 

@@ -561,6 +561,23 @@ Tens layernorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
   return y;
 }
 
+void cross_attn_small(Ctx& c, const __half* q, const float* kc, const float* vc, __half* out, int N, int L, int T, int C,
+                      int heads) {
+  RFB_CHECK(T >= 1 && T <= 16, "cross-attention: context length must be in [1, 16]");
+  RFB_CHECK(C % heads == 0 && (C / heads) % 8 == 0, "cross-attention: head dim must be a multiple of 8");
+  const size_t smem = (size_t)2 * T * C * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    CUDA_OK(cudaFuncSetAttribute(cross_attn_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  RFB_CHECK(smem <= 200 * 1024, "cross-attention: context does not fit shared memory");
+  dim3 grid((unsigned)((L * heads + 255) / 256), (unsigned)N);
+  cross_attn_small_kernel<16><<<grid, 256, smem, c.stream>>>(q, kc, vc, out, L, T, C, heads,
+                                                             1.0f / sqrtf((float)(C / heads)));
+  LAUNCH_CHECK(c);
+}
+
 Tens upsample2x(Ctx& c, const Tens& x) {
   Tens y = c.new_tens(x.n, x.h * 2, x.w * 2, x.c);
   upsample2x_kernel<<<grid_for(y.rows() * (x.c / 8)), 256, 0, c.stream>>>(x.p, y.p, x.n, x.h, x.w, x.c);
@@ -614,6 +631,20 @@ void cfg_ddim_update(Ctx& c, const float* x, const float* eps2, const float* noi
                      int has_uncond) {
   cfg_ddim_update_kernel<<<grid_for(count), 256, 0, c.stream>>>(x, eps2, noise, x_prev, pred_x0, count, scale, a_t,
                                                                 a_prev, sigma, sqrt_one_minus_at, has_uncond);
+  LAUNCH_CHECK(c);
+}
+
+void cfg_combine(Ctx& c, const float* eps2, float* out, long long count, float scale) {
+  cfg_combine_kernel<<<grid_for(count), 256, 0, c.stream>>>(eps2, out, count, scale);
+  LAUNCH_CHECK(c);
+}
+void plms_combine(Ctx& c, const float* e_t, const float* o1, const float* o2, const float* o3, const float* e_next,
+                  float* out, long long count, int order) {
+  plms_combine_kernel<<<grid_for(count), 256, 0, c.stream>>>(e_t, o1, o2, o3, e_next, out, count, order);
+  LAUNCH_CHECK(c);
+}
+void q_sample(Ctx& c, const float* x0, const float* noise, const float* coef_dev, float* out, long long per_sample, int B) {
+  q_sample_kernel<<<grid_for(per_sample * B), 256, 0, c.stream>>>(x0, noise, coef_dev, out, per_sample, B);
   LAUNCH_CHECK(c);
 }
 

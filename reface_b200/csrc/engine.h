@@ -154,6 +154,9 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride = 1, int
 Tens linear_t(Ctx& c, const Tens& x, const LinW& w, Epi e);
 void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads, int d, __half* out, long long ldo,
                float scale, int q_off, int k_off, int v_off, int hs = 0);
+// softmax_T(q k^T / sqrt(d)) v for a short context (T <= 16 tokens per sample); kc / vc fp32 [N*T, C]
+void cross_attn_small(Ctx& c, const __half* q, const float* kc, const float* vc, __half* out, int N, int L, int T, int C,
+                      int heads);
 Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps, bool silu);
 Tens layernorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps);
 Tens upsample2x(Ctx& c, const Tens& x);
@@ -168,6 +171,11 @@ void concat9(Ctx& c, const float* x, const float* z, const float* mask, float* o
 void cfg_ddim_update(Ctx& c, const float* x, const float* eps2, const float* noise, float* x_prev, float* pred_x0,
                      long long count, float scale, float a_t, float a_prev, float sigma, float sqrt_one_minus_at,
                      int has_uncond);
+
+void cfg_combine(Ctx& c, const float* eps2, float* out, long long count, float scale);
+void plms_combine(Ctx& c, const float* e_t, const float* o1, const float* o2, const float* o3, const float* e_next,
+                  float* out, long long count, int order);
+void q_sample(Ctx& c, const float* x0, const float* noise, const float* coef_dev, float* out, long long per_sample, int B);
 
 inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
   long long g = (total + block - 1) / block;

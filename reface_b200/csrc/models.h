@@ -24,7 +24,7 @@ struct STW {
               *ln3g = nullptr, *ln3b = nullptr;
   ConvW proj_in, proj_out;
   LinW qkv, o1, ff1, ff2, q2, kv2, o2h;
-  Lin32 v2, o2;
+  Lin32 v2, o2, k2;
   int c = 0, heads = 0, d = 0, ctx_dim = 0, ff_bn = 256;
 };
 enum UOpKind { OP_CONV_IN, OP_RES, OP_ATTN, OP_DOWN, OP_UP };
@@ -62,6 +62,9 @@ Tens cross_attention_general(Ctx& c, const STW& s, const Tens& x, const float* c
 void ddim_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, const float* mask, const float* cond,
                  const float* uncond, int B, int L, int T, const DdimSchedule& s, float scale, const float* noise,
                  float* x0_out, float* inter_x, float* inter_p0, int log_every_t);
+void plms_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, const float* mask, const float* cond,
+                 const float* uncond, int B, int L, int T, const DdimSchedule& s, float scale, float* x0_out,
+                 float* inter_x, float* inter_p0, int log_every_t);
 
 // ---- AutoencoderKL
 struct VResW {

@@ -37,6 +37,7 @@ static STW build_st(Ctx& c, const std::string& p, int ch, int heads, int ctx_dim
   s.qkv = pack_linear_rows(c, {b + "attn1.to_q.weight", b + "attn1.to_k.weight", b + "attn1.to_v.weight"});
   s.o1 = pack_linear(c, b + "attn1.to_out.0.weight", b + "attn1.to_out.0.bias");
   s.v2 = lin32(c, b + "attn2.to_v.weight", "");
+  s.k2 = lin32(c, b + "attn2.to_k.weight", "");
   s.o2 = lin32(c, b + "attn2.to_out.0.weight", b + "attn2.to_out.0.bias");
   // general (context length > 1) cross-attention operands
   s.q2 = pack_linear(c, b + "attn2.to_q.weight", "");
@@ -235,12 +236,22 @@ static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T,
   return conv3x3_t(c, h2, s.proj_out, e3, 1, 0, 0, 0, 0);
 }
 
-// General cross-attention for context length T > 1 (stack_feat configs, ddpm.py:1027-1030): the context
-// projections are tiny (T rows), so K/V are computed per sample and attention runs through the same
-// batched GEMM path with L_kv = T.
+// General cross-attention for context length T > 1 (stack_feat configs, ddpm.py:1027-1030; attention.py:179-221):
+//   x + to_out(softmax(to_q(LN2 x) to_k(ctx)^T / sqrt d) to_v(ctx)).  The context projections are tiny (T rows per
+// sample, fp32 GEMV path); the T-wide softmax runs on CUDA cores; q and the out-projection use the tensor-core GEMM.
 Tens cross_attention_general(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T, int N) {
-  (void)s, (void)x, (void)ctx, (void)T, (void)N;
-  throw std::runtime_error("cross-attention with context length > 1 is not implemented yet (shipped config uses T=1)");
+  const int C = s.c, L = x.h * x.w;
+  Tens n2 = layernorm(c, x, s.ln2g, s.ln2b, 1e-5f);
+  Tens q = linear_t(c, n2, s.q2, Epi());
+  float* kc = c.alloc_t<float>((size_t)N * T * C);
+  float* vc = c.alloc_t<float>((size_t)N * T * C);
+  linear_small(c, ctx, s.ctx_dim, N * T, s.k2, kc, C, 0, 0);
+  linear_small(c, ctx, s.ctx_dim, N * T, s.v2, vc, C, 0, 0);
+  Tens a = c.new_tens(x.n, x.h, x.w, C);
+  cross_attn_small(c, q.p, kc, vc, a.p, N, L, T, C, s.heads);
+  Epi e;
+  e.res = x.p, e.ldr = C;
+  return linear_t(c, a, s.o2h, e);
 }
 
 struct RunState {
@@ -362,6 +373,83 @@ void ddim_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, cons
                     s.a_prev[index], s.sigma[index], s.sqrt_one_minus_a[index], cfg ? 1 : 0);
     std::swap(xa, xb);
     if (log_every_t > 0 && (index % log_every_t == 0 || index == s.n - 1)) {  // ddim.py:247-249
+      if (inter_x)
+        CUDA_OK(cudaMemcpyAsync(inter_x + (size_t)n_inter * cnt, xa, cnt * sizeof(float), cudaMemcpyDeviceToDevice,
+                                c.stream));
+      if (inter_p0)
+        CUDA_OK(cudaMemcpyAsync(inter_p0 + (size_t)n_inter * cnt, p0, cnt * sizeof(float), cudaMemcpyDeviceToDevice,
+                                c.stream));
+      ++n_inter;
+    }
+  }
+  CUDA_OK(cudaMemcpyAsync(x0_out, xa, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  c.release(mk);
+}
+
+// ---------------------------------------------------------------------------------------------- PLMS loop
+// PLMSSampler.plms_sampling / p_sample_plms with test_model_kwargs (ldm/models/diffusion/plms.py:116-242), eta = 0.
+void plms_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, const float* mask, const float* cond,
+                 const float* uncond, int B, int L, int T, const DdimSchedule& s, float scale, float* x0_out,
+                 float* inter_x, float* inter_p0, int log_every_t) {
+  const size_t mk = c.mark();
+  const long long HW = (long long)L * L, cnt = (long long)B * 4 * HW;
+  const bool cfg = uncond != nullptr && scale != 1.0f;  // plms.py:179
+  const int dup = cfg ? 2 : 1, N = dup * B;
+  float* xa = c.alloc_t<float>(cnt);
+  float* xb = c.alloc_t<float>(cnt);
+  float* p0 = c.alloc_t<float>(cnt);
+  float* e_next = c.alloc_t<float>(cnt);
+  float* e_prime = c.alloc_t<float>(cnt);
+  float* ring[4];
+  for (int i = 0; i < 4; ++i) ring[i] = c.alloc_t<float>(cnt);
+  float* x9 = c.alloc_t<float>((size_t)N * 9 * HW);
+  float* eps2 = c.alloc_t<float>((size_t)N * 4 * HW);
+  float* ctx = c.alloc_t<float>((size_t)N * T * 768);
+  long long* ts = c.alloc_t<long long>((size_t)s.n * N);
+  {
+    std::vector<long long> h((size_t)s.n * N);
+    for (int i = 0; i < s.n; ++i)
+      for (int j = 0; j < N; ++j) h[(size_t)i * N + j] = s.timesteps[i];
+    CUDA_OK(cudaMemcpyAsync(ts, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+    CUDA_OK(cudaStreamSynchronize(c.stream));
+  }
+  const size_t cb = (size_t)B * T * 768 * sizeof(float);
+  if (cfg) {
+    CUDA_OK(cudaMemcpyAsync(ctx, uncond, cb, cudaMemcpyDeviceToDevice, c.stream));
+    CUDA_OK(cudaMemcpyAsync(ctx + (size_t)B * T * 768, cond, cb, cudaMemcpyDeviceToDevice, c.stream));
+  } else {
+    CUDA_OK(cudaMemcpyAsync(ctx, cond, cb, cudaMemcpyDeviceToDevice, c.stream));
+  }
+  CUDA_OK(cudaMemcpyAsync(xa, x_T, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  UNetAux aux;
+  aux.uniform_t = 1;
+  aux.crossvec = unet_cross_vectors(c, u, ctx, N, T);
+  // get_model_output (plms.py:178-192): e = eps(x, t) with classifier-free guidance
+  auto model_output = [&](const float* x, int index, float* e) {
+    concat9(c, x, z_inpaint, mask, x9, B, (int)HW, dup);
+    unet_forward(c, u, x9, ts + (size_t)index * N, ctx, N, L, T, cfg ? eps2 : e, &aux);
+    if (cfg) cfg_combine(c, eps2, e, cnt, scale);
+  };
+  // get_x_prev_and_pred_x0 (plms.py:199-217) with sigma = 0
+  auto step_from = [&](const float* x, const float* e, int index, float* x_prev, float* pred) {
+    cfg_ddim_update(c, x, e, nullptr, x_prev, pred, cnt, 1.0f, s.a_t[index], s.a_prev[index], s.sigma[index],
+                    s.sqrt_one_minus_a[index], 0);
+  };
+  int n_inter = 0;
+  for (int i = 0; i < s.n; ++i) {
+    const int index = s.n - 1 - i;
+    const int index_next = s.n - 1 - std::min(i + 1, s.n - 1);  // time_range[min(i + 1, len - 1)], plms.py:146
+    float* e_t = ring[i & 3];
+    model_output(xa, index, e_t);
+    const int order = std::min(i, 3);
+    if (order == 0) {  // pseudo improved Euler: second model evaluation at the predicted x_prev
+      step_from(xa, e_t, index, xb, nullptr);
+      model_output(xb, index_next, e_next);
+    }
+    plms_combine(c, e_t, ring[(i + 3) & 3], ring[(i + 2) & 3], ring[(i + 1) & 3], e_next, e_prime, cnt, order);
+    step_from(xa, e_prime, index, xb, p0);
+    std::swap(xa, xb);
+    if (log_every_t > 0 && (index % log_every_t == 0 || index == s.n - 1)) {  // plms.py:168-170
       if (inter_x)
         CUDA_OK(cudaMemcpyAsync(inter_x + (size_t)n_inter * cnt, xa, cnt * sizeof(float), cudaMemcpyDeviceToDevice,
                                 c.stream));

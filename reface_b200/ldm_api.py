@@ -215,6 +215,11 @@ class LatentDiffusion:
             return self.scale_factor * posterior.sample(noise)
         return self.scale_factor * posterior
 
+    def q_sample(self, x_start, t, noise=None):                            # ddpm.py:412-415
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        return self.engine.q_sample(x_start, t, noise, self.linear_start, self.linear_end, self.num_timesteps)
+
     def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):   # ddpm.py:1277-1337
         return self.engine.vae_decode(z)
 
@@ -298,6 +303,39 @@ class DDIMSampler:
                                       schedule=self._sch)
         inter = {"x_inter": [x_T] + list(ix), "pred_x0": [x_T] + list(ip)}                             # ddim.py:221,247-249
         return x0_, inter
+
+
+class PLMSSampler(DDIMSampler):
+    """ldm/models/diffusion/plms.py:11-242: same constructor and `sample` signature as the reference's PLMSSampler;
+    the loop (pseudo improved Euler + Adams-Bashforth over the last three eps) runs inside one C-ABI call
+    (rfb_plms_sample)."""
+
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0.0, verbose=True):
+        if ddim_eta != 0:
+            raise ValueError("ddim_eta must be 0 for PLMS")                                            # plms.py:25-26
+        super().make_schedule(ddim_num_steps, ddim_discretize, ddim_eta, verbose)
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None, img_callback=None,
+               quantize_x0=False, eta=0.0, mask=None, x0=None, temperature=1.0, noise_dropout=0.0, score_corrector=None,
+               corrector_kwargs=None, verbose=True, x_T=None, log_every_t=100, unconditional_guidance_scale=1.0,
+               unconditional_conditioning=None, **kwargs):
+        if conditioning is not None and not isinstance(conditioning, dict) and conditioning.shape[0] != batch_size:
+            print(f"Warning: Got {conditioning.shape[0]} conditionings but batch-size is {batch_size}")   # plms.py:89-90
+        tk = kwargs["test_model_kwargs"]                                                               # plms.py:218 (KeyError as there)
+        for name, v in dict(mask=mask, score_corrector=score_corrector, callback=callback, img_callback=img_callback).items():
+            if v is not None:
+                raise NotImplementedError(f"{name} is not supported by the fused PLMS loop")
+        if quantize_x0 or noise_dropout > 0.0:
+            raise NotImplementedError("quantize_x0 / noise_dropout are not supported")
+        self.make_schedule(S, ddim_eta=eta, verbose=verbose)
+        C, H, W = shape
+        if x_T is None:
+            x_T = torch.randn(batch_size, C, H, W, device=self.model.device)                           # plms.py:125-126
+        x0_, ix, ip = self.model.engine.plms_sample(x_T, tk["inpaint_image"], tk["inpaint_mask"], conditioning,
+                                                    unconditional_conditioning, S, unconditional_guidance_scale,
+                                                    log_every_t=log_every_t, schedule=self._sch)
+        return x0_, {"x_inter": [x_T] + list(ix), "pred_x0": [x_T] + list(ip)}                          # plms.py:136,168-170
 
 
 def swap_faces(model: LatentDiffusion, ref_img, tar_img, inpaint_img, mask_lat, landmarks136, x_T, enc_noise, S=50,

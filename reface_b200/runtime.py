@@ -39,6 +39,9 @@ SIGNATURES = {
     "rfb_cfg_ddim_update": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp]),
     "rfb_ddim_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _vp, _i, _vp,
                              _vp, _vp, _vp]),
+    "rfb_plms_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp, _vp,
+                             _vp]),
+    "rfb_q_sample": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp]),
     "rfb_vae_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "rfb_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "rfb_clip_encode": (_i, [_vp, _vp, _i, _vp, _vp]),
@@ -233,6 +236,42 @@ class Engine:
                                           _ptr(noise), int(log_every_t), _ptr(x0), _ptr(inter_x), _ptr(inter_p),
                                           self._stream()))
         return x0, inter_x[:K], inter_p[:K]
+
+    def plms_sample(self, x_T, z_inpaint, mask, cond, uncond, S, scale, log_every_t=100, schedule=None, n_steps_limit=None):
+        """Runs the whole PLMS loop (plms.py:116-242, eta = 0) on the device; same returns as ddim_sample."""
+        sch = schedule or ddim_schedule(S, 0.0)
+        x_T, z_inpaint, mask, cond, uncond = (self._in(v) for v in (x_T, z_inpaint, mask, cond, uncond))
+        B, _, L, _ = x_T.shape
+        T = cond.shape[1]
+        ts = np.ascontiguousarray(sch["timesteps"], dtype=np.int64)
+        tabs = [np.ascontiguousarray(sch[k], dtype=np.float32) for k in ("a_t", "a_prev", "sigma", "sqrt_one_minus_a")]
+        n = len(ts)
+        if n_steps_limit is not None:
+            k = int(n_steps_limit)
+            ts, tabs = ts[n - k:], [t[n - k:] for t in tabs]
+            n = k
+        K = len([i for i in range(n) if log_every_t > 0 and (i % log_every_t == 0 or i == n - 1)])
+        x0 = torch.empty_like(x_T)
+        inter_x, inter_p = self._new(max(K, 1), *x_T.shape), self._new(max(K, 1), *x_T.shape)
+        hp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._ck(self.lib.rfb_plms_sample(self.h, _ptr(x_T), _ptr(z_inpaint), _ptr(mask), _ptr(cond), _ptr(uncond), B, L, T,
+                                          hp(ts), hp(tabs[0]), hp(tabs[1]), hp(tabs[2]), hp(tabs[3]), n, float(scale),
+                                          int(log_every_t), _ptr(x0), _ptr(inter_x), _ptr(inter_p), self._stream()))
+        return x0, inter_x[:K], inter_p[:K]
+
+    def q_sample(self, x_start, t, noise, linear_start=0.00085, linear_end=0.012, T=1000):
+        """DDPM.q_sample (ddpm.py:412-415) with the buffers of register_schedule (fp64 sqrt, cast to fp32)."""
+        x_start, noise = self._in(x_start), self._in(noise)
+        betas = np.linspace(linear_start ** 0.5, linear_end ** 0.5, T, dtype=np.float64) ** 2
+        ac = np.cumprod(1.0 - betas, axis=0)
+        tt = np.asarray(t.cpu() if torch.is_tensor(t) else t, dtype=np.int64).reshape(-1)
+        coef = np.ascontiguousarray(np.stack([np.sqrt(ac)[tt], np.sqrt(1.0 - ac)[tt]], 1), dtype=np.float32)
+        B = x_start.shape[0]
+        assert len(tt) == B
+        out = torch.empty_like(x_start)
+        self._ck(self.lib.rfb_q_sample(self.h, _ptr(x_start), _ptr(noise), coef.ctypes.data_as(C.c_void_p), B,
+                                       x_start[0].numel(), _ptr(out), self._stream()))
+        return out
 
     def vae_encode(self, img, noise=None, return_moments=False):
         img, noise = self._in(img), self._in(noise)

@@ -132,6 +132,54 @@ def golden_ddim(unet, sd):
     assert torch.equal(O.concat9(x_T, z, mask), torch.cat([x_T, z, mask], 1))
 
 
+def golden_plms(unet, sd):
+    print("plms (reference PLMSSampler driving the reference UNet) + q_sample")
+    from ldm.models.diffusion.plms import PLMSSampler
+    PLMSSampler.register_buffer = lambda self, n, a: setattr(self, n, a)   # plms.py:18-22 hard-codes cuda
+    ac = O.alphas_cumprod_f32()
+
+    class FakeLD:   # the attributes PLMSSampler touches (plms.py:15,27-35,123,183-187)
+        num_timesteps = 1000
+        betas = torch.tensor(O.make_beta_schedule(), dtype=torch.float32)
+        alphas_cumprod = ac
+        alphas_cumprod_prev = torch.tensor(np.append(1.0, ac.double().numpy()[:-1]), dtype=torch.float32)
+        device = torch.device("cpu")
+
+        def apply_model(self, x, t, c):
+            return unet(x, t, context=torch.cat([c], 1))
+
+    g = torch.Generator().manual_seed(3)
+    B, L, S, scale = 1, 16, 6, 3.5
+    x_T = torch.randn(B, 4, L, L, generator=g)
+    z = torch.randn(B, 4, L, L, generator=g)
+    mask = (torch.rand(B, 1, L, L, generator=g) > 0.5).float()
+    c = torch.randn(B, 1, 768, generator=g)
+    uc = torch.randn(B, 1, 768, generator=g)
+    smp = PLMSSampler(FakeLD())
+    ref, inter = smp.sample(S=S, conditioning=c, batch_size=B, shape=[4, L, L], verbose=False,
+                            unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0, x_T=x_T,
+                            log_every_t=2, test_model_kwargs={"inpaint_image": z, "inpaint_mask": mask})
+    ora, ointer = O.plms_sample(O.Params(sd, O.PFX_UNET), x_T, z, mask, c, uc, S, scale, log_every_t=2)
+    check("plms x0", ref, ora, 5e-5)
+    assert len(inter["x_inter"]) == len(ointer["x_inter"])
+    # q_sample (ddpm.py:412-415) through the reference's own buffers (register_schedule, ddpm.py:255-285)
+    import ldm.models.diffusion.ddpm as ddpm
+
+    class Sched(ddpm.DDPM):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+            self.v_posterior, self.parameterization = 0.0, "eps"
+            self.register_schedule(beta_schedule="linear", timesteps=1000, linear_start=0.00085, linear_end=0.012)
+
+    sch = Sched()
+    t = torch.tensor([999])
+    nz = torch.randn(B, 4, L, L, generator=g)
+    qs = sch.q_sample(x_start=z, t=t, noise=nz)
+    assert torch.equal(qs, O.q_sample(z, t, nz)), "q_sample must be bit exact (two fp32 multiplies and one add)"
+    save("plms_S6_L16", x_T=x_T, z=z, mask=mask, c=c, uc=uc, x0=ref, n_inter=len(inter["x_inter"]),
+         pred_x0_last=inter["pred_x0"][-1], q_t=t, q_noise=nz, q_out=qs)
+
+
 def golden_vae():
     print("vae")
     from ldm.models.autoencoder import AutoencoderKL
@@ -248,6 +296,11 @@ if __name__ == "__main__":
     if "unet" in which:
         m, sd = golden_unet()
         golden_ddim(m, sd)
+        golden_plms(m, sd)
+        del m, sd
+    if "plms" in which and "unet" not in which:      # regenerate only the PLMS / q_sample fixture
+        m, sd = golden_unet()
+        golden_plms(m, sd)
         del m, sd
     if "vae" in which:
         golden_vae()

@@ -44,6 +44,17 @@ def test_ddim_matches_reference_sampler(oracle, unet_sd):
     assert (inter["pred_x0"][-1] - g["pred_x0_last"]).abs().max() < 1e-3 * float(g["x0"].abs().max())
 
 
+def test_plms_and_q_sample_match_reference_golden(oracle, unet_sd):
+    """PLMSSampler (plms.py) and DDPM.q_sample (ddpm.py:412-415): fixtures written by tests/golden/make_golden.py from the
+    reference's own classes."""
+    g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "plms_S6_L16.npz")).items()}
+    assert torch.equal(oracle.q_sample(g["z"], g["q_t"], g["q_noise"]), g["q_out"])
+    x0, inter = oracle.plms_sample(oracle.Params(unet_sd, oracle.PFX_UNET), g["x_T"], g["z"], g["mask"], g["c"], g["uc"], 6,
+                                   3.5, log_every_t=2)
+    assert len(inter["x_inter"]) == int(g["n_inter"])
+    assert float((x0 - g["x0"]).abs().max()) <= 5e-5 * float(g["x0"].abs().max())
+
+
 def test_vae_matches_reference_golden(oracle, vae_sd):
     g = _g("vae_64")
     P = oracle.Params(vae_sd, oracle.PFX_VAE)
