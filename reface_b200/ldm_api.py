@@ -246,6 +246,24 @@ class LatentDiffusion:
                 raise NotImplementedError("pass raw landmarks via landmarks136=...")
         return e.condition_fuse(c_src, c_tgt, idf, landmarks136, self.clip_weight, self.ID_weight, self.Landmarks_weight)
 
+    def source_features(self, x):
+        """CLIP embedding and ArcFace identity of the source face(s): the part of conditioning_with_feat that depends
+        on the source only.  Video mode computes it once and reuses it for every frame (the reference recomputes it
+        for every batch from the repeated source image, scripts/inference_swap_video.py:627-632; same values)."""
+        return self.engine.clip_encode(x), self.engine.arcface_embed(x)
+
+    def conditioning_from_source_features(self, src_feats, tar, landmarks136=None):
+        """conditioning_with_feat (ddpm.py:872-1045) with the source terms taken from source_features()."""
+        e = self.engine
+        b = tar.shape[0]
+        c_src, idf = src_feats
+        if c_src.shape[0] == 1 and b > 1:
+            c_src, idf = c_src.repeat(b, 1, 1), idf.repeat(b, 1)
+        c_tgt = e.clip_encode(e.target_clip_input(tar))
+        if landmarks136 is None:
+            landmarks136 = torch.zeros(b, 136, device=self.device)
+        return e.condition_fuse(c_src, c_tgt, idf, landmarks136, self.clip_weight, self.ID_weight, self.Landmarks_weight)
+
 
 class DDIMSampler:
     """ldm/models/diffusion/ddim.py:96-251: same constructor and `sample` signature; the 50-step loop runs inside
@@ -352,3 +370,31 @@ def swap_faces(model: LatentDiffusion, ref_img, tar_img, inpaint_img, mask_lat, 
                                 test_model_kwargs={"inpaint_image": z_inpaint, "inpaint_mask": mask_lat})   # :469-479
     x = model.decode_first_stage(samples)                                                              # :493
     return dict(c=c, z_inpaint=z_inpaint, samples=samples, image=torch.clamp((x + 1.0) / 2.0, 0.0, 1.0))
+
+
+def swap_video(model: LatentDiffusion, ref_img, tar_img, inpaint_img, mask_lat, x_T, enc_noise, landmarks136=None, S=30,
+               scale=3.0, chunk=30, rank=0, world=1):
+    """Video mode (BASELINE configs[4]; scripts/inference_swap_video.py:560-724 with inference_video_swap.sh:28-29:
+    30 DDIM steps -> 31 timesteps, scale 3): ONE source face [1,3,224,224], F target frames [F,...].  The frames are
+    streamed in contiguous chunks (reface_b200.shard.video_segments: chunk k -> rank k % world), the source CLIP /
+    ArcFace features are computed once, the target CLIP embedding per frame.  Returns {frame_index: image[3,H,W]} for
+    the frames of this rank; every frame's result is bitwise the one swap_faces gives for it (no cross-sample
+    arithmetic anywhere in the path)."""
+    from .shard import video_segments
+    F_ = tar_img.shape[0]
+    feats = model.source_features(ref_img[:1])
+    sampler = DDIMSampler(model)
+    out = {}
+    for lo, hi in video_segments(F_, chunk, rank, world):
+        b = hi - lo
+        uc = model.learnable_vector.repeat(b, 1, 1)
+        lm = None if landmarks136 is None else landmarks136[lo:hi]
+        c = model.conditioning_from_source_features(feats, tar_img[lo:hi], lm)
+        z = model.get_first_stage_encoding(model.encode_first_stage(inpaint_img[lo:hi]), noise=enc_noise[lo:hi])
+        smp, _ = sampler.sample(S=S, conditioning=c, batch_size=b, shape=[4, x_T.shape[2], x_T.shape[3]], verbose=False,
+                                unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0, x_T=x_T[lo:hi],
+                                test_model_kwargs={"inpaint_image": z, "inpaint_mask": mask_lat[lo:hi]})
+        img = torch.clamp((model.decode_first_stage(smp) + 1.0) / 2.0, 0.0, 1.0)
+        for i in range(b):
+            out[lo + i] = img[i]
+    return out

@@ -20,6 +20,15 @@ def shard_batch(batch: dict, rank: int, world: int):
     return {k: v[lo:hi] for k, v in batch.items()}
 
 
+def video_segments(n_frames: int, chunk: int, rank: int, world: int):
+    """Video mode (BASELINE configs[4]; scripts/inference_swap_video.py:560-724): frames are streamed in contiguous
+    chunks of `chunk` frames, chunk k goes to rank k % world; every frame keeps its index (the reference's
+    `segment_id`) so that results can be put back in order (inference_swap_video.py:710-713).
+    Returns this rank's list of (first_frame, last_frame_exclusive)."""
+    chunks = [(lo, min(n_frames, lo + chunk)) for lo in range(0, n_frames, chunk)]
+    return [c for k, c in enumerate(chunks) if k % world == rank]
+
+
 def broadcast_checkpoint(flat: torch.Tensor, src: int = 0):
     """One collective for the whole (flat fp32) checkpoint; NCCL over NVLink on GPUs, gloo in the CPU tests."""
     if dist.is_initialized() and dist.get_world_size() > 1:

@@ -108,3 +108,24 @@ def test_full_swap_path_vs_oracle(engine, oracle, unet_sd, vae_sd, clip_sd, arc_
     print("image max", float(d.max()), "mean", float(d.mean()))
     assert rel(out["c"], ref["c"]) < 3e-2 and rel(out["z_inpaint"], ref["z_inpaint"]) < 2e-2
     assert float(d.max()) < 0.08 and float(d.mean()) < 0.01
+
+
+def test_video_mode_equals_per_frame_swaps(engine, unet_sd, vae_sd, clip_sd, arc_sd, fusion_sd):
+    """BASELINE configs[4] at test size (5 frames of 128x128, S=6 -> 7 steps, chunks of 2 over 2 simulated ranks): the
+    streamed video path (source features computed once) gives, frame for frame, exactly the bits of swap_faces."""
+    from reface_b200 import synth
+    from reface_b200.ldm_api import LatentDiffusion, swap_faces, swap_video
+    sd = {**unet_sd, **vae_sd, **clip_sd, **arc_sd, **fusion_sd}
+    model = LatentDiffusion(sd, engine=engine)
+    F_, H = 5, 128
+    inp = synth.synthetic_inputs(F_, H, engine.device, seed=5)
+    inp["ref_img"] = inp["ref_img"][:1].repeat(F_, 1, 1, 1)          # one source face for every frame
+    vid = {}
+    for rank in range(2):
+        vid.update(swap_video(model, inp["ref_img"], inp["tar_img"], inp["inpaint_img"], inp["mask_lat"], inp["x_T"],
+                              inp["enc_noise"], inp["landmarks136"], S=6, scale=3.0, chunk=2, rank=rank, world=2))
+    assert sorted(vid) == list(range(F_))
+    ref = swap_faces(model, S=6, scale=3.0, **inp)["image"]
+    assert torch.isfinite(ref).all()
+    for i in range(F_):
+        assert torch.equal(vid[i], ref[i]), i

@@ -51,3 +51,17 @@ def test_shard_range_partitions():
             rs = [shard_range(total, r, world) for r in range(world)]
             assert rs[0][0] == 0 and rs[-1][1] == total and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
             assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1
+
+
+def test_video_segments_cover_every_frame_once():
+    """Video mode: contiguous chunks round-robined over the ranks; together the ranks cover every frame exactly once
+    and the frame index (the reference's segment_id) restores the order."""
+    from reface_b200.shard import video_segments
+    for n, chunk, world in ((240, 30, 8), (240, 30, 1), (7, 3, 2), (31, 30, 4), (5, 30, 8)):
+        seen = []
+        for r in range(world):
+            for lo, hi in video_segments(n, chunk, r, world):
+                assert 0 < hi - lo <= chunk
+                seen += list(range(lo, hi))
+        assert sorted(seen) == list(range(n))
+    assert video_segments(240, 30, 1, 8) == [(30, 60)]
