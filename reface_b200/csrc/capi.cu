@@ -141,6 +141,7 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "attn_flash") c.attn_flash = (int)value;
   else if (k == "profile") c.profile = (int)value;
   else if (k == "gn_fused") c.gn_fused = (int)value;
+  else if (k == "cfg_share") c.cfg_share = (int)value;
   else if (k == "gn_cluster") c.gn_cluster = (int)value;
   else if (k == "gn_threads") c.gn_threads = (int)value;
   else if (k == "attn_poly") c.attn_poly = (int)value;

@@ -53,6 +53,10 @@ struct DdimSchedule {
 UNet* build_unet(Ctx& c, const std::string& pfx, const UNetCfg& cfg);
 struct UNetAux {                        // optional step-invariant inputs of a forward pass
   int uniform_t = 0;                    // all N samples share t[0] (DDIM loop)
+  // classifier-free guidance batch: x9[n] == x9[n + N/2] and t[n] == t[n + N/2] (ddim.py:338-344), only the context
+  // differs.  Everything before the first context-dependent operation (conv_in, the first ResBlock, attn1 of the first
+  // SpatialTransformer) is then computed once for both halves.
+  int cfg_dup = 0;
   std::vector<const float*> crossvec;   // per SpatialTransformer (execution order): to_out(to_v(ctx)) [N, C]
 };
 std::vector<const float*> unet_cross_vectors(Ctx& c, UNet& u, const float* ctx, int N, int T);

@@ -200,7 +200,20 @@ static float* cross_vec(Ctx& c, const STW& s, const float* ctx, int N) {
   return vec;
 }
 
-static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T, int N, const float* vec_pre) {
+// [n, h, w, c] -> [2n, h, w, c]: both CFG halves of a tensor that was computed once
+static Tens dup2(Ctx& c, const Tens& x) {
+  Tens y = c.new_tens(2 * x.n, x.h, x.w, x.c);
+  const size_t bytes = (size_t)x.rows() * x.c * sizeof(__half);
+  CUDA_OK(cudaMemcpyAsync(y.p, x.p, bytes, cudaMemcpyDeviceToDevice, c.stream));
+  CUDA_OK(cudaMemcpyAsync(y.p + (size_t)x.rows() * x.c, x.p, bytes, cudaMemcpyDeviceToDevice, c.stream));
+  return y;
+}
+
+// share_halves: x holds ONE copy of the N/2 distinct samples of a CFG batch (UNetAux::cfg_dup); GroupNorm, proj_in,
+// LN1, the QKV projection and the self-attention do not see the context and run once, attn1's out-projection is issued
+// per half with that half's cross-attention vectors, and the block continues with all N samples.
+static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T, int N, const float* vec_pre,
+                   bool share_halves = false) {
   const int C = s.c;
   Tens xn = groupnorm(c, x, s.gn_g, s.gn_b, 1e-6f, false);
   Tens h = conv3x3_t(c, xn, s.proj_in, Epi(), 1, 0, 0, 0, 0);
@@ -209,9 +222,21 @@ static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T,
   Tens n1 = layernorm(c, h, s.ln1g, s.ln1b, 1e-5f);
   Tens qkv = linear_t(c, n1, s.qkv, Epi());
   Tens a = c.new_tens(x.n, x.h, x.w, C);
-  attention(c, qkv.p, 3 * C, N, L, s.heads, s.d, a.p, C, 1.0f / sqrtf((float)s.d), 0, C, 2 * C);
+  attention(c, qkv.p, 3 * C, x.n, L, s.heads, s.d, a.p, C, 1.0f / sqrtf((float)s.d), 0, C, 2 * C);
   Tens h1;
-  if (T == 1) {
+  Tens xres = x;  // residual of proj_out
+  if (share_halves) {
+    RFB_CHECK(T == 1 && N == 2 * x.n, "shared CFG halves need the single-token context path");
+    const float* vec = vec_pre ? vec_pre : cross_vec(c, s, ctx, N);
+    h1 = c.new_tens(N, x.h, x.w, C);
+    const long long Mh = x.rows();
+    for (int half = 0; half < 2; ++half) {
+      Epi e;
+      e.bias = s.o1.b, e.res = h.p, e.ldr = C, e.rowvec = vec + (size_t)half * x.n * C, e.ldv = C, e.rows_per_vec = L;
+      gemm(c, a.p, C, Mh, C, s.o1.w, s.o1.kp, s.o1.out, h1.p + (size_t)half * Mh * C, C, e);
+    }
+    xres = dup2(c, x);
+  } else if (T == 1) {
     // --- attn2 (degenerate, see cross_vec) folded into attn1's out-projection epilogue
     const float* vec = vec_pre ? vec_pre : cross_vec(c, s, ctx, N);
     Epi e;
@@ -232,7 +257,7 @@ static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T,
   e2.res = h1.p, e2.ldr = C;
   Tens h2 = linear_t(c, ff, s.ff2, e2);
   Epi e3;
-  e3.res = x.p, e3.ldr = C;
+  e3.res = xres.p, e3.ldr = C;
   return conv3x3_t(c, h2, s.proj_out, e3, 1, 0, 0, 0, 0);
 }
 
@@ -309,10 +334,28 @@ void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const fl
   float* emb_all = c.alloc_t<float>((size_t)er * u.emb_cat.out);
   linear_small(c, emb, 4 * mc, er, u.emb_cat, emb_all, u.emb_cat.out, /*act_in=silu*/ 1, 0);
   RunState rs{emb_all, er, u.emb_cat.out, ctx, T, N, aux, 0};
-  Tens h = from_nchw_f32(c, x9, N, u.cfg.in_channels, L, L, u.cfg.in_channels);
   std::vector<Tens> hs;
-  for (auto& ops : u.inp) {
-    h = run_ops(c, ops, h, rs);
+  Tens h;
+  size_t first = 0;
+  const bool share = aux && aux->cfg_dup && c.cfg_share && T == 1 && N % 2 == 0 && u.inp.size() >= 2 &&
+                     u.inp[0].size() == 1 && u.inp[0][0].kind == OP_CONV_IN && u.inp[1].size() == 2 &&
+                     u.inp[1][0].kind == OP_RES && u.inp[1][1].kind == OP_ATTN;
+  if (share) {
+    // CFG batch: the two halves only differ in the context, which first enters in attn2 of input_blocks.1
+    Tens x8 = from_nchw_f32(c, x9, N / 2, u.cfg.in_channels, L, L, u.cfg.in_channels);
+    Tens h0 = conv3x3_t(c, x8, u.inp[0][0].conv, Epi());
+    hs.push_back(dup2(c, h0));
+    Tens r = run_res(c, u.inp[1][0].res, h0, rs.emb, rs.emb_rows, rs.emb_ld);
+    const float* pre = !aux->crossvec.empty() ? aux->crossvec[0] : nullptr;
+    h = run_st(c, u.inp[1][1].st, r, ctx, T, N, pre, true);
+    rs.st_idx = 1;
+    hs.push_back(h);
+    first = 2;
+  } else {
+    h = from_nchw_f32(c, x9, N, u.cfg.in_channels, L, L, u.cfg.in_channels);
+  }
+  for (size_t bi = first; bi < u.inp.size(); ++bi) {
+    h = run_ops(c, u.inp[bi], h, rs);
     hs.push_back(h);
   }
   h = run_ops(c, u.mid, h, rs);
@@ -363,6 +406,7 @@ void ddim_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, cons
   // the context only; every sample shares the step's timestep, so one time-embedding row serves the batch.
   UNetAux aux;
   aux.uniform_t = 1;
+  aux.cfg_dup = cfg ? 1 : 0;
   aux.crossvec = unet_cross_vectors(c, u, ctx, N, T);
   int n_inter = 0;
   for (int i = 0; i < s.n; ++i) {
@@ -423,6 +467,7 @@ void plms_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, cons
   CUDA_OK(cudaMemcpyAsync(xa, x_T, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
   UNetAux aux;
   aux.uniform_t = 1;
+  aux.cfg_dup = cfg ? 1 : 0;
   aux.crossvec = unet_cross_vectors(c, u, ctx, N, T);
   // get_model_output (plms.py:178-192): e = eps(x, t) with classifier-free guidance
   auto model_output = [&](const float* x, int index, float* e) {

@@ -94,6 +94,21 @@ def test_ddim_loop_vs_reference_golden(unet_engine):
     assert perr < 5e-2, perr
 
 
+def test_cfg_head_sharing_is_bit_exact(unet_engine):
+    """Inside the samplers the two CFG halves share their input and timestep (ddim.py:338-344): conv_in, the first
+    ResBlock and attn1 of the first SpatialTransformer are computed once per pair (option cfg_share).  The results
+    must be the bits of the unshared evaluation."""
+    g = _g("ddim_S5_L16")
+    outs = []
+    for share in (1, 0):
+        unet_engine.set_option("cfg_share", share)
+        try:
+            outs.append(unet_engine.ddim_sample(g["x_T"], g["z"], g["mask"], g["c"], g["uc"], S=5, scale=3.5)[0].cpu())
+        finally:
+            unet_engine.set_option("cfg_share", 1)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_plms_loop_vs_reference_golden(unet_engine):
     """rfb_plms_sample against the reference PLMSSampler's output (tests/golden/plms_S6_L16.npz; 7 steps, 8 UNet calls)."""
     g = _g("plms_S6_L16")
