@@ -1076,15 +1076,35 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const bool any = __any_sync(0xffffffffu, need);
       float rs0 = 0.f, rs1 = 0.f;
       uint32_t pk[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      // POLY of every 8 exponentials (whole fp16 pairs) go to the FMA pipe.  A warp issues in order, so a warp that is
+      // blocked on a full MUFU queue cannot reach polynomial work further down its stream: the two column halves of a
+      // quadrant (which share an SM sub-partition) therefore run the two kinds in OPPOSITE order.
+      auto exp_pair = [&](int i, bool poly) {
         const float x0 = fmaf(__uint_as_float(sv[2 * i]), scale_log2e, -m);
         const float x1 = fmaf(__uint_as_float(sv[2 * i + 1]), scale_log2e, -m);
-        const float p0 = (((2 * i) & 7) < POLY) ? poly_exp2(x0) : fast_exp2(x0);
-        const float p1 = (((2 * i + 1) & 7) < POLY) ? poly_exp2(x1) : fast_exp2(x1);
+        const float p0 = poly ? poly_exp2(x0) : fast_exp2(x0);
+        const float p1 = poly ? poly_exp2(x1) : fast_exp2(x1);
         rs0 += p0;
         rs1 += p1;
         pk[i] = pack_h2(p0, p1);
+      };
+      if (POLY == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) exp_pair(i, false);
+      } else if (hh == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (((2 * i) & 7) < POLY) exp_pair(i, true);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (((2 * i) & 7) >= POLY) exp_pair(i, false);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (((2 * i) & 7) >= POLY) exp_pair(i, false);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (((2 * i) & 7) < POLY) exp_pair(i, true);
       }
       l = fmaf(l, alpha, rs0 + rs1);
       if (tw) RFB_STAMP(j, 7);
@@ -1150,9 +1170,8 @@ static void launch_flash4(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, 
   static bool attr = false;
   if (!attr) {
     CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 0, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 1, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 2, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 3, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 4, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
   dim3 grid((unsigned)(L / 256), (unsigned)(N * heads));
@@ -1175,9 +1194,7 @@ static void launch_flash4(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, 
   switch (c.attn_poly) {
     case 0: attn_flash4_kernel<DP, 0, NS><<<grid, 576, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg,
                                                                                        c.attn_stagger); break;
-    case 1: attn_flash4_kernel<DP, 1, NS><<<grid, 576, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg,
-                                                                                       c.attn_stagger); break;
-    case 3: attn_flash4_kernel<DP, 3, NS><<<grid, 576, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg,
+    case 4: attn_flash4_kernel<DP, 4, NS><<<grid, 576, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg,
                                                                                        c.attn_stagger); break;
     default: attn_flash4_kernel<DP, 2, NS><<<grid, 576, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg,
                                                                                        c.attn_stagger); break;

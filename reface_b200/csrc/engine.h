@@ -79,7 +79,7 @@ struct Ctx {
   int gemm_pair = 0;
   int attn_stagger = 0;  // attention v4: cycles by which the second query tile's softmax starts late
   int attn_pad = 0;      // test hook: rfb_op_attention repacks q/k/v with 64-element head slices
-  int attn_poly = 0;     // attention v3: exponentials per 8 evaluated on the FMA pipe (0..3)
+  int attn_poly = 0;     // attention v3/v4: exponentials per 8 evaluated on the FMA pipe (measured slower: off)
   int cfg_share = 1;     // samplers: compute the context-independent head of the UNet once per CFG pair
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)
   int gn_fused = 1;  // single-launch cluster GroupNorm (0: stats / finalize / apply kernels)

@@ -17,5 +17,13 @@ if "gn" in what:
     eng.bench_norm(0, 8, 128, 512, 512, iters=1)
 if "ln" in what:
     eng.bench_norm(1, 16, 320, 64, 64, iters=1)
+if "lin" in what:   # the HBM-bound K=320 projection of the 64x64 level with bias + residual (attn1.to_out / proj_out)
+    M, K, N = 65536, 320, 320
+    x = torch.randn(M, K, device="cuda").half().float(); w = torch.randn(N, K, device="cuda").half().float() / 18
+    b = torch.randn(N, device="cuda"); r = torch.randn(M, N, device="cuda").half().float()
+    eng.op_linear(x, w, b, residual=r)
+if "conv" in what:  # the dominant long-K implicit-GEMM conv (ResBlock 3x3, 640 ch at 32x32, N=16)
+    x = torch.randn(16, 640, 32, 32, device="cuda").half().float(); w = torch.randn(640, 640, 3, 3, device="cuda").half().float() / 76
+    eng.op_conv2d(x, w, torch.randn(640, device="cuda"))
 torch.cuda.synchronize()
 print("done")
