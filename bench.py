@@ -37,10 +37,12 @@ def peaks():
 
 def traffic_from_profiles():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, averaged over the launches of
-    the committed `ncu --set full` capture (profiles/r01_traffic.json, written by scripts/ncu_summary.py)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get("dram_bytes_per_launch")
+    the committed `ncu --set full` capture (profiles/r01s2_traffic.json, written by scripts/ncu_summary.py --traffic:
+    the long-K implicit-GEMM conv 640->640 at 32x32, N=16, of scripts/ncu_ops.py)."""
+    for name in ("r01s2_traffic.json", "r01_traffic.json"):       # newest capture first
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p)).get("dram_bytes_per_launch")
     return None
 
 
@@ -232,7 +234,7 @@ def main():
                 gpu_launches=int(launches),
                 roofline=dict(bound="tensor", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s",
                               frac=achieved / pk["tflops"], traffic=traffic_from_profiles(),
-                              kernel="gemm_persist_kernel (tcgen05 GEMM / implicit-GEMM conv) + attn_flash_kernel",
+                              kernel="gemm_persist_kernel (tcgen05 GEMM / implicit-GEMM conv) + attn_flash4/3_kernel (fused attention)",
                               launches_per_step=int(g_n), kernel_ms_per_step=g_ms, alg_tflop_per_step=g_flops / 1e12,
                               share_of_step=g_ms / (ms / args.steps), peak_source=pk["source"] + ", sustained bf16",
                               whole_path_frac=(value / world) * fpf / (pk["tflops"] * 1e12) if fpf else None),
