@@ -82,7 +82,8 @@ __device__ __forceinline__ EpiTile epi_tile_info(const GemmArgs& g, int q, int m
   t.NO = (MODE == EPI_GEGLU) ? (g.N >> 1) : g.N;
   t.ocol_tile = (MODE == EPI_GEGLU) ? n_tile * t.halfN : n_tile * g.BN;
   t.m_base = (long long)m_tile * GEMM_BM + q * 32;
-  t.zoff = (long long)(z / g.zdiv) * g.zs_outer + (long long)(z % g.zdiv) * g.zs_inner;
+  t.zoff = (g.zdiv == 1) ? (long long)z * g.zs_outer  // plain / conv / per-sample batches: no division per tile
+                         : (long long)(z / g.zdiv) * g.zs_outer + (long long)(z % g.zdiv) * g.zs_inner;
   t.vec_ok = g.out != nullptr && (t.NO & 7) == 0 && (g.ldo & 7) == 0 && (t.zoff & 7) == 0 &&
              (!g.res || (g.ldr & 7) == 0);
   return t;

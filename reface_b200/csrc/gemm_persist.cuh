@@ -25,6 +25,27 @@ __host__ __device__ inline size_t gemmp_smem_bytes(int stages, int BN, int np = 
          (size_t)(4 * np) * EPI_WARP_BYTES;
 }
 
+// (z, m_tile, n_tile) of the tiles a CTA visits (tile = blockIdx.x + i * gridDim.x), advanced with adds and compares:
+// decomposing the linear tile index with runtime integer divisions cost ~280 instructions per epilogue warp and
+// tile (28 % of everything the K=320 GEMMs executed, profiles/r01s2_gemm_k320_ncu_full.txt).
+struct TileIter {
+  int z, m_tile, n_tile, step_z, step_m, step_n;
+  __device__ __forceinline__ void init(int tile, int stride, int m_tiles, int n_tiles) {
+    const int per_z = m_tiles * n_tiles;
+    z = tile / per_z;
+    int rem = tile - z * per_z;
+    m_tile = rem / n_tiles, n_tile = rem - m_tile * n_tiles;
+    step_z = stride / per_z;
+    rem = stride - step_z * per_z;
+    step_m = rem / n_tiles, step_n = rem - step_m * n_tiles;
+  }
+  __device__ __forceinline__ void next(int m_tiles, int n_tiles) {
+    n_tile += step_n, m_tile += step_m, z += step_z;
+    if (n_tile >= n_tiles) n_tile -= n_tiles, ++m_tile;
+    if (m_tile >= m_tiles) m_tile -= m_tiles, ++z;
+  }
+};
+
 template <int MODE, int NP>
 __global__ void __launch_bounds__(64 + NP * 128, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g,
@@ -65,16 +86,15 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
-  const int per_z = m_tiles * n_tiles;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (converged warp, elected issue)
     const uint32_t tx = GEMM_A_STAGE_BYTES + b_stage_bytes;
     uint32_t st = 0, sp = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int z = tile / per_z;
-      const int rem = tile - z * per_z;
-      const int m_tile = rem / n_tiles, n_tile = rem - m_tile * n_tiles;
+    TileIter it;
+    it.init(blockIdx.x, gridDim.x, m_tiles, n_tiles);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it.next(m_tiles, n_tiles)) {
+      const int z = it.z, m_tile = it.m_tile, n_tile = it.n_tile;
       int cw = 0, ch = 0, cn = 0;
       if (g.a_mode == A_CONV3) {
         if (g.bimg > 1) {
@@ -151,25 +171,20 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t stage = epi_stage + (uint32_t)e * EPI_WARP_BYTES;  // this warp's staging tile + bias strip
     uint32_t ti = 0;
     float nb[4] = {0.f, 0.f, 0.f, 0.f};
-    auto tile_info = [&](int tile, int& m_tile, int& n_tile, int& z) {
-      z = tile / per_z;
-      const int rem = tile - z * per_z;
-      m_tile = rem / n_tiles, n_tile = rem - m_tile * n_tiles;
-      return epi_tile_info<MODE>(g, q, m_tile, n_tile, z);
-    };
+    TileIter it;
+    it.init(blockIdx.x, gridDim.x, m_tiles, n_tiles);
     if ((int)blockIdx.x < total_tiles) {
-      int a, b, c2;
-      const EpiTile e0 = tile_info(blockIdx.x, a, b, c2);
+      const EpiTile e0 = epi_tile_info<MODE>(g, q, it.m_tile, it.n_tile, it.z);
       epilogue_lookahead<MODE, NP>(g, e0, lane, half, nb);
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
-      int m_tile, n_tile, z;
-      const EpiTile et = tile_info(tile, m_tile, n_tile, z);
+      const int n_tile = it.n_tile;
+      const EpiTile et = epi_tile_info<MODE>(g, q, it.m_tile, it.n_tile, it.z);
       epilogue_prefetch<MODE, NP>(g, et, stage, lane, half, n_tile, nb);  // bias / residual while the MMAs still run
+      it.next(m_tiles, n_tiles);
       if (tile + (int)gridDim.x < total_tiles) {  // next tile's bias -> registers, residual lines -> L2
-        int a, b, c2;
-        const EpiTile en = tile_info(tile + gridDim.x, a, b, c2);
+        const EpiTile en = epi_tile_info<MODE>(g, q, it.m_tile, it.n_tile, it.z);
         epilogue_lookahead<MODE, NP>(g, en, lane, half, nb);
       }
       mbar_wait(bar_accf + 8u * as, aph);
