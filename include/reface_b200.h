@@ -41,6 +41,8 @@ int rfb_build_unet(rfb_ctx* ctx, const char* prefix);
 int rfb_build_vae(rfb_ctx* ctx, const char* prefix);
 int rfb_build_clip(rfb_ctx* ctx, const char* prefix);
 int rfb_build_arcface(rfb_ctx* ctx, const char* prefix);
+/* BiSeNet(n_classes=19) of pretrained/face_parsing/model.py:214-239 (keys below `prefix`, e.g. "face_parser.seg."). */
+int rfb_build_face_parser(rfb_ctx* ctx, const char* prefix);
 /* Tunables ("gemm_bn", "gemm_stages", "gemm_smem_budget", "attn_flash", "profile"); returns 0 if known. */
 int rfb_set_option(rfb_ctx* ctx, const char* key, long long value);
 long long rfb_launch_count(rfb_ctx* ctx); /* kernels launched by this library so far */
@@ -88,6 +90,17 @@ int rfb_plms_sample(rfb_ctx* ctx, const float* x_T, const float* z_inpaint, cons
  * coef = (sqrt_alphas_cumprod[t_b], sqrt_one_minus_alphas_cumprod[t_b]) ([host], 2*B floats). */
 int rfb_q_sample(rfb_ctx* ctx, const float* x_start, const float* noise, const float* coef, int B, long long per_sample,
                  float* out, void* stream);
+/* Face parsing, the step before the swap path.  FaceParser.forward for an already 512-sized input
+ * (pretrained/face_parsing/face_parsing_demo.py:266-281: clamp, ImageNet normalisation, BiSeNet, argmax) and
+ * __ffhq_masks_to_faceParser_mask_detailed (:74-122).  img01 [B,3,H,W] fp32 in [0,1], H and W multiples of 32.
+ * Outputs (each may be NULL): logits8 fp32 [B,19,H/8,W/8] (before the bilinear align_corners upsampling),
+ * seg19 / seg12 uint8 [B,H,W]. */
+int rfb_face_parse(rfb_ctx* ctx, const float* img01, int B, int H, int W, float* logits8, uint8_t* seg19, uint8_t* seg12,
+                   void* stream);
+/* mask = 1 - isin(seg12, remove), inpaint = img * mask (ldm/data/video_swap_dataset.py:150-222).  img [B,3,H,W] fp32,
+ * remove: [host] label list (project_ffhq.yaml remove_mask_tar_FFHQ), mask [B,1,H,W], inpaint [B,3,H,W] (may be NULL). */
+int rfb_inpaint_from_parsing(rfb_ctx* ctx, const float* img, const uint8_t* seg12, const int* remove, int n_remove, int B,
+                             int H, int W, float* mask, float* inpaint, void* stream);
 /* get_first_stage_encoding(encode_first_stage(x)) (ddpm.py:1402-1439, 850-857; autoencoder.py:324-328;
  * distributions.py:24-37): img [B,3,H,W] -> z = 0.18215*(mean + std*noise) [B,4,H/8,W/8].
  * noise NULL => mode() (z = scaled mean).  mean/logvar outputs optional (NULL). */

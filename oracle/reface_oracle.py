@@ -658,6 +658,101 @@ def q_sample(x_start, t, noise):
 
 
 # --------------------------------------------------------------------------------------------
+# face parsing: BiSeNet on a ResNet-18 context path + label / mask preparation
+#   pretrained/face_parsing/model.py:19-262, resnet.py:19-85, face_parsing_demo.py:74-122,236-281,
+#   ldm/data/video_swap_dataset.py:135-240 (mask from the label map, inpaint image)
+# --------------------------------------------------------------------------------------------
+PFX_PARSE = "face_parser.seg."
+SEG_MEAN = (0.485, 0.456, 0.406)     # model.py:15
+SEG_STD = (0.229, 0.224, 0.225)      # model.py:16
+# __ffhq_masks_to_faceParser_mask_detailed (face_parsing_demo.py:74-122): 19 face-parsing.PyTorch classes -> 12
+FFHQ19_TO_12 = (0, 6, 2, 2, 3, 3, 10, 7, 7, 11, 5, 9, 1, 1, 8, 0, 0, 4, 0)
+REMOVE_MASK_TAR_FFHQ = (1, 2, 3, 5, 6, 7, 9)   # project_ffhq.yaml:209-216
+
+
+def _cbr(P, name, x, cin, cout, ks=3, stride=1, padding=1):
+    # ConvBNReLU, model.py:19-35
+    x = _conv(P, name + ".conv", x, cin, cout, ks, stride, padding, bias=False)
+    return F.relu(_bn(P, name + ".bn", x, cout))
+
+
+def _basic_block(P, name, x, cin, cout, stride):
+    # BasicBlock, resnet.py:19-48
+    r = _conv(P, name + ".conv1", x, cin, cout, 3, stride, 1, bias=False)
+    r = F.relu(_bn(P, name + ".bn1", r, cout))
+    r = _conv(P, name + ".conv2", r, cout, cout, 3, 1, 1, bias=False)
+    r = _bn(P, name + ".bn2", r, cout)
+    sc = x
+    if cin != cout or stride != 1:
+        sc = _bn(P, name + ".downsample.1", _conv(P, name + ".downsample.0", x, cin, cout, 1, stride, 0, bias=False), cout)
+    return F.relu(sc + r)
+
+
+def resnet18_features(P, x):
+    # Resnet18.forward, resnet.py:71-81
+    x = F.relu(_bn(P, "bn1", _conv(P, "conv1", x, 3, 64, 7, 2, 3, bias=False), 64))
+    x = F.max_pool2d(x, 3, 2, 1)
+    feats = []
+    cin = 64
+    for li, (cout, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2)), 1):
+        x = _basic_block(P, f"layer{li}.0", x, cin, cout, stride)
+        x = _basic_block(P, f"layer{li}.1", x, cout, cout, 1)
+        cin = cout
+        feats.append(x)
+    return feats[1], feats[2], feats[3]      # 1/8, 1/16, 1/32
+
+
+def _arm(P, name, x, cin, cout):
+    # AttentionRefinementModule, model.py:71-88
+    feat = _cbr(P, name + ".conv", x, cin, cout)
+    att = F.avg_pool2d(feat, feat.shape[2:])
+    att = _bn(P, name + ".bn_atten", _conv(P, name + ".conv_atten", att, cout, cout, 1, bias=False), cout)
+    return feat * torch.sigmoid(att)
+
+
+def bisenet_logits(P, x, n_classes=19, upsample=True):
+    """BiSeNet.forward (model.py:241-256), first output only (the one inference uses, face_parsing_demo.py:277):
+    [B,3,H,W] normalised image -> [B,n_classes,H,W] logits."""
+    H, W = x.shape[2:]
+    cp = P.sub("cp.")
+    f8, f16, f32 = resnet18_features(cp.sub("resnet."), x)
+    avg = _cbr(cp, "conv_avg", F.avg_pool2d(f32, f32.shape[2:]), 512, 128, 1, 1, 0)
+    f32s = _arm(cp, "arm32", f32, 512, 128) + avg                       # avg_up: nearest from 1x1 = broadcast
+    f32u = _cbr(cp, "conv_head32", F.interpolate(f32s, f16.shape[2:], mode="nearest"), 128, 128)
+    f16s = _arm(cp, "arm16", f16, 256, 128) + f32u
+    f16u = _cbr(cp, "conv_head16", F.interpolate(f16s, f8.shape[2:], mode="nearest"), 128, 128)
+    # FeatureFusionModule, model.py:175-212 (feat_sp = res3b1 feature f8, model.py:245-246)
+    fm = P.sub("ffm.")
+    feat = _cbr(fm, "convblk", torch.cat([f8, f16u], 1), 256, 256, 1, 1, 0)
+    att = F.avg_pool2d(feat, feat.shape[2:])
+    att = torch.sigmoid(_conv(fm, "conv2", F.relu(_conv(fm, "conv1", att, 256, 64, 1, bias=False)), 64, 256, 1, bias=False))
+    fuse = feat * att + feat
+    # BiSeNetOutput, model.py:43-52
+    o = P.sub("conv_out.")
+    out = _conv(o, "conv_out", _cbr(o, "conv", fuse, 256, 256), 256, n_classes, 1, bias=False)
+    if not upsample:
+        return out                                                      # [B, n_classes, H/8, W/8]
+    return F.interpolate(out, (H, W), mode="bilinear", align_corners=True)
+
+
+def face_parse(P, img01):
+    """FaceParser.forward for a 512x512 input (face_parsing_demo.py:260-281) + the 19 -> 12 class conversion (:74-122):
+    img01 [B,3,512,512] in [0,1] -> (seg19 [B,H,W] int64, seg12 [B,H,W] int64)."""
+    mean = torch.tensor(SEG_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(SEG_STD).view(1, 3, 1, 1)
+    im = (img01.clamp(0, 1) - mean) / std
+    seg19 = torch.argmax(bisenet_logits(P, im), dim=1)
+    return seg19, torch.tensor(FFHQ19_TO_12)[seg19]
+
+
+def inpaint_from_parsing(img_m11, seg12, remove=REMOVE_MASK_TAR_FFHQ):
+    """ldm/data/video_swap_dataset.py:150-222: mask = 1 - isin(label, remove_tar); inpaint = image * mask.
+    img_m11 [B,3,H,W] in [-1,1], seg12 [B,H,W] -> (mask [B,1,H,W] in {0,1}, inpaint [B,3,H,W])."""
+    m = 1.0 - torch.isin(seg12, torch.tensor(remove)).float().unsqueeze(1)
+    return m, img_m11 * m
+
+
+# --------------------------------------------------------------------------------------------
 # specs + whole pipeline (scripts/inference_test_bench.py:438-495)
 # --------------------------------------------------------------------------------------------
 def _meta(*shape, dtype=torch.float32):
@@ -687,6 +782,12 @@ def arcface_spec(prefix=PFX_ARC):
     P = Params(None, prefix)
     with torch.no_grad():
         arcface_backbone(P, _meta(1, 3, 112, 112))
+    return P.spec
+
+
+def parse_spec(prefix=PFX_PARSE):
+    P = Params(None, prefix)
+    bisenet_logits(P, _meta(1, 3, 64, 64))
     return P.spec
 
 

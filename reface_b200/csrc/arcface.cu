@@ -103,11 +103,18 @@ __global__ void arcface_preproc_kernel(const float* __restrict__ img, __half* __
   }
 }
 
-static void bn_affine(Ctx& c, const std::string& p, int C, float** s, float** t) {
+void bn_affine(Ctx& c, const std::string& p, int C, float** s, float** t) {
   *s = (float*)c.dmalloc(C * sizeof(float));
   *t = (float*)c.dmalloc(C * sizeof(float));
   bn_affine_kernel<<<(C + 127) / 128, 128, 0, c.stream>>>(c.pf(p + ".weight"), c.pf(p + ".bias"), c.pf(p + ".running_mean"),
                                                          c.pf(p + ".running_var"), *s, *t, C, 1e-5f);
+  CUDA_OK(cudaGetLastError());
+  c.launches++;
+}
+
+void channel_mean(Ctx& c, const Tens& x, float* out) {
+  dim3 g((unsigned)((x.c + 127) / 128), (unsigned)x.n);
+  channel_mean_kernel<<<g, 128, 0, c.stream>>>(x.p, out, x.h * x.w, x.c);
   CUDA_OK(cudaGetLastError());
   c.launches++;
 }

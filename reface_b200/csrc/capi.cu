@@ -77,6 +77,7 @@ void rfb_destroy(rfb_ctx* h) {
   delete c.vae;
   delete c.clip;
   delete c.arc;
+  delete c.parser;
   delete h;
 }
 
@@ -128,6 +129,14 @@ int rfb_build_arcface(rfb_ctx* h, const char* prefix) {
   delete c.arc;
   c.arc = nullptr;
   c.arc = build_arcface(c, prefix);
+  API_END
+}
+
+int rfb_build_face_parser(rfb_ctx* h, const char* prefix) {
+  API_BEGIN(h)
+  delete c.parser;
+  c.parser = nullptr;
+  c.parser = build_face_parser(c, prefix);
   API_END
 }
 
@@ -261,6 +270,26 @@ int rfb_q_sample(rfb_ctx* h, const float* x_start, const float* noise, const flo
   q_sample(c, x_start, noise, cd, out, per_sample, B);
   CUDA_OK(cudaStreamSynchronize(c.stream));  // `coef` is a host array owned by the caller
   c.release(mk);
+  API_END
+}
+int rfb_face_parse(rfb_ctx* h, const float* img01, int B, int H, int W, float* logits8, uint8_t* seg19, uint8_t* seg12,
+                   void* stream) {
+  API_BEGIN(h)
+  RFB_CHECK(c.parser, "rfb_build_face_parser has not been called");
+  c.stream = (cudaStream_t)stream;
+  face_parse(c, *c.parser, img01, B, H, W, logits8, seg19, seg12);
+  API_END
+}
+int rfb_inpaint_from_parsing(rfb_ctx* h, const float* img, const uint8_t* seg12, const int* remove, int n_remove, int B,
+                             int H, int W, float* mask, float* inpaint, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  unsigned bits = 0;
+  for (int i = 0; i < n_remove; ++i) {
+    RFB_CHECK(remove[i] >= 0 && remove[i] < 32, "label out of range");
+    bits |= 1u << remove[i];
+  }
+  inpaint_from_parsing(c, img, seg12, bits, B, H, W, mask, inpaint);
   API_END
 }
 int rfb_vae_encode(rfb_ctx* h, const float* img, const float* noise, int B, int H, int W, float* z, float* mean,

@@ -261,7 +261,7 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     cfg.attrs = at, cfg.numAttrs = 1;
     if (g.geglu)
       CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI_GEGLU>, tmA, tmB2, g, m_pairs, n_tiles, total_pairs));
-    else if (g.act == 0 && g.out32 == nullptr && g.alpha == 1.0f)
+    else if (g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f)
       CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI_FAST>, tmA, tmB2, g, m_pairs, n_tiles, total_pairs));
     else
       CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI_GENERIC>, tmA, tmB2, g, m_pairs, n_tiles, total_pairs));
@@ -278,7 +278,7 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
       attr2 = true;
     }
     // short-K GEMMs are epilogue-bound: 3 epilogue warps per lane quadrant (448 threads) instead of 2
-    const int np = (g.nk <= c.gemm_epi3_max_nk && g.BN > 64 && g.act == 0 && g.out32 == nullptr && g.alpha == 1.0f) ? 3 : 2;
+    const int np = (g.nk <= c.gemm_epi3_max_nk && g.BN > 64 && g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f) ? 3 : 2;
     const int budget = (227 - 3) * 1024 - 4 * np * EPI_WARP_BYTES;
     int ps = c.force_stages ? c.force_stages : std::max(2, std::min(8, budget / stage_bytes));
     g.stages = ps;
@@ -291,13 +291,14 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     if (g.geglu) {
       if (np == 3) gemm_persist_kernel<EPI_GEGLU, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
       else gemm_persist_kernel<EPI_GEGLU, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
-    } else if (g.act == 0 && g.out32 == nullptr && g.alpha == 1.0f) {
+    } else if (g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f) {
       if (np == 3) gemm_persist_kernel<EPI_FAST, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
       else gemm_persist_kernel<EPI_FAST, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
     } else {
       gemm_persist_kernel<EPI_GENERIC, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
     }
   } else {
+    RFB_CHECK(!g.relu_after_res, "relu_after_res needs the persistent kernel");
     gemm_tc_kernel<<<grid, GEMM_THREADS, smem, c.stream>>>(tmA, tmB, g);
   }
   LAUNCH_CHECK(c);
@@ -310,6 +311,7 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
 static void fill_epi(GemmArgs& g, const Epi& e, __half* out, long long ldo) {
   g.alpha = e.alpha, g.bias = e.bias, g.rowvec = e.rowvec, g.rows_per_vec = e.rows_per_vec, g.ldv = e.ldv;
   g.act_param = e.act_param, g.act = e.act, g.geglu = e.geglu, g.res = e.res, g.ldr = e.ldr;
+  g.relu_after_res = e.relu_after_res;
   g.out = out, g.ldo = ldo, g.out32 = e.out32, g.o32_sn = e.o32_sn, g.o32_sp = e.o32_sp, g.o32_sc = e.o32_sc;
   g.o32_rpn = e.o32_rpn;
 }

@@ -47,6 +47,7 @@ struct Epi {
   int act = 0;
   const float* act_param = nullptr;
   int geglu = 0;
+  int relu_after_res = 0;  // ReLU after the residual add (needs the generic epilogue)
   const __half* res = nullptr;
   long long ldr = 0;
   float alpha = 1.0f;
@@ -60,6 +61,7 @@ struct UNet;
 struct VAE;
 struct ClipVision;
 struct ArcFace;
+struct FaceParser;
 
 struct Ctx {
   int device = 0;
@@ -97,6 +99,7 @@ struct Ctx {
   VAE* vae = nullptr;
   ClipVision* clip = nullptr;
   ArcFace* arc = nullptr;
+  FaceParser* parser = nullptr;
 
   void* alloc(size_t bytes);  // arena bump allocation (256 B aligned)
   size_t mark() const { return arena_off; }

@@ -261,6 +261,10 @@ __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile&
               v[u4 * 8 + 2 * e + 1] += f.y;
             }
           }
+          if (MODE == EPI_GENERIC && g.relu_after_res) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[u4 * 8 + e] = fmaxf(v[u4 * 8 + e], 0.f);
+          }
           uint4 o;
           o.x = pack_h2(v[u4 * 8 + 0], v[u4 * 8 + 1]);
           o.y = pack_h2(v[u4 * 8 + 2], v[u4 * 8 + 3]);
@@ -274,6 +278,10 @@ __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile&
           const __half* rp = g.res + t.zoff + m * g.ldr + oc;
           for (int j = 0; j < 32; ++j)
             if (oc + j < t.NO) v[j] += __half2float(rp[j]);
+        }
+        if (MODE == EPI_GENERIC && g.relu_after_res) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (g.out) {
           __half* op = g.out + t.zoff + m * g.ldo + oc;

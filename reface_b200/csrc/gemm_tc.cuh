@@ -30,6 +30,7 @@ struct GemmArgs {
   int rows_per_vec, ldv;
   const float* act_param;  // PReLU slopes [N]
   int act, geglu;
+  int relu_after_res;  // ReLU applied AFTER the residual add (ResNet BasicBlock: relu(shortcut + bn(conv)))
   const __half* res;  // residual [M, ldr] added after activation
   long long ldr;
   __half* out;  // fp16 [M, ldo]

@@ -149,6 +149,33 @@ struct ArcFace {
   float* fc_w = nullptr; float* fc_b = nullptr;
 };
 ArcFace* build_arcface(Ctx& c, const std::string& pfx);
+// eval-mode BatchNorm `p` as a per-channel affine: s = gamma / sqrt(var + eps), t = beta - mean * s (device arrays)
+void bn_affine(Ctx& c, const std::string& p, int C, float** s, float** t);
+void channel_mean(Ctx& c, const Tens& x, float* out);  // mean over H*W per (n, c): fp32 [N, C]
+
+// ---- face parsing (BiSeNet, pretrained/face_parsing/model.py)
+struct ParseCBR {  // bias-free conv with the following BatchNorm folded in (+ ReLU in the epilogue)
+  ConvW w;
+  float* bias = nullptr;
+};
+struct ParseBlock {  // resnet.py BasicBlock
+  ParseCBR c1, c2, ds;
+  bool down = false;
+  int stride = 1;
+};
+struct FaceParser {
+  std::string pfx;
+  ParseCBR stem, arm32, arm16, head32, head16, ffm_blk, out_cbr;
+  std::vector<ParseBlock> blocks;
+  Lin32 conv_avg, arm32_att, arm16_att, ffm1, ffm2;  // 1x1 convs on per-sample channel vectors (fp32 GEMV path)
+  ConvW out_conv;
+  int n_classes = 19;
+};
+FaceParser* build_face_parser(Ctx& c, const std::string& pfx);
+void face_parse(Ctx& c, FaceParser& m, const float* img01, int B, int H, int W, float* logits8, uint8_t* seg19,
+                uint8_t* seg12);
+void inpaint_from_parsing(Ctx& c, const float* img, const uint8_t* seg12, unsigned remove_bits, int B, int H, int W,
+                          float* mask, float* inpaint);
 void arcface_embed(Ctx& c, ArcFace& m, const float* img224, int B, float* out512);
 
 }  // namespace rfb

@@ -29,6 +29,7 @@ SIGNATURES = {
     "rfb_build_vae": (_i, [_vp, C.c_char_p]),
     "rfb_build_clip": (_i, [_vp, C.c_char_p]),
     "rfb_build_arcface": (_i, [_vp, C.c_char_p]),
+    "rfb_build_face_parser": (_i, [_vp, C.c_char_p]),
     "rfb_set_option": (_i, [_vp, C.c_char_p, _ll]),
     "rfb_launch_count": (_ll, [_vp]),
     "rfb_arena_peak": (_sz, [_vp]),
@@ -42,6 +43,8 @@ SIGNATURES = {
     "rfb_plms_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp, _vp,
                              _vp]),
     "rfb_q_sample": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp]),
+    "rfb_face_parse": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "rfb_inpaint_from_parsing": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rfb_vae_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "rfb_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "rfb_clip_encode": (_i, [_vp, _vp, _i, _vp, _vp]),
@@ -272,6 +275,30 @@ class Engine:
         self._ck(self.lib.rfb_q_sample(self.h, _ptr(x_start), _ptr(noise), coef.ctypes.data_as(C.c_void_p), B,
                                        x_start[0].numel(), _ptr(out), self._stream()))
         return out
+
+    def build_face_parser(self, prefix="face_parser.seg."):
+        self._ck(self.lib.rfb_build_face_parser(self.h, prefix.encode()))
+
+    def face_parse(self, img01, return_logits=False):
+        """BiSeNet face parsing: img01 [B,3,H,W] in [0,1] -> (seg19, seg12) uint8 [B,H,W] (+ logits [B,19,H/8,W/8])."""
+        img01 = self._in(img01)
+        B, _, H, W = img01.shape
+        seg19 = torch.empty(B, H, W, dtype=torch.uint8, device=self.device)
+        seg12 = torch.empty(B, H, W, dtype=torch.uint8, device=self.device)
+        lg = self._new(B, 19, H // 8, W // 8) if return_logits else None
+        self._ck(self.lib.rfb_face_parse(self.h, _ptr(img01), B, H, W, _ptr(lg), _ptr(seg19), _ptr(seg12), self._stream()))
+        return (seg19, seg12, lg) if return_logits else (seg19, seg12)
+
+    def inpaint_from_parsing(self, img, seg12, remove=(1, 2, 3, 5, 6, 7, 9)):
+        """mask = 1 - isin(seg12, remove); inpaint = img * mask (video_swap_dataset.py:150-222)."""
+        img = self._in(img)
+        seg12 = seg12.to(self.device, torch.uint8).contiguous()
+        B, _, H, W = img.shape
+        mask, inp = self._new(B, 1, H, W), torch.empty_like(img)
+        rem = (C.c_int * len(remove))(*[int(r) for r in remove])
+        self._ck(self.lib.rfb_inpaint_from_parsing(self.h, _ptr(img), _ptr(seg12), rem, len(remove), B, H, W, _ptr(mask),
+                                                   _ptr(inp), self._stream()))
+        return mask, inp
 
     def vae_encode(self, img, noise=None, return_moments=False):
         img, noise = self._in(img), self._in(noise)

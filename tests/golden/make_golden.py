@@ -289,8 +289,51 @@ def _mk_linear(sd, name, i, o):
     return l
 
 
+def golden_parse():
+    print("face parsing (reference BiSeNet + 19->12 label conversion + mask preparation)")
+    _cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self       # model.py:15-16 move two constants to cuda at import time
+    import torch.utils.model_zoo as mz
+    mz.load_url = lambda *a, **k: {}                     # resnet.py:83 downloads ImageNet weights in __init__
+    try:
+        import pretrained.face_parsing.face_parsing_demo as fpd
+        from pretrained.face_parsing.model import BiSeNet
+    finally:
+        torch.Tensor.cuda = _cuda
+    net = BiSeNet(n_classes=19).eval()
+    sd, sub = sub_sd(O.parse_spec(), O.PFX_PARSE)
+    missing, unexpected = net.load_state_dict(sub, strict=False)
+    assert not unexpected, unexpected
+    for k in missing:   # the auxiliary training heads and BN step counters are the only keys the oracle does not hold
+        assert k.startswith(("conv_out16.", "conv_out32.")) or k.endswith("num_batches_tracked"), k
+    g = torch.Generator().manual_seed(6)
+    H = 256
+    img01 = torch.rand(1, 3, H, H, generator=g)
+    mean = torch.tensor(O.SEG_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(O.SEG_STD).view(1, 3, 1, 1)
+    im = (img01.clamp(0, 1) - mean) / std                # FaceParser.preprocess_img, face_parsing_demo.py:266-268
+    ref_logits = net(im)[0]
+    ora_logits = O.bisenet_logits(O.Params(sd, O.PFX_PARSE), im)
+    check("bisenet logits", ref_logits, ora_logits, 2e-5)
+    seg19 = torch.argmax(ref_logits, dim=1)
+    o19, o12 = O.face_parse(O.Params(sd, O.PFX_PARSE), img01)
+    assert torch.equal(o19, seg19)
+    conv = getattr(fpd, "__ffhq_masks_to_faceParser_mask_detailed")
+    seg12 = torch.from_numpy(conv(seg19[0].numpy().astype(np.uint8)).astype(np.int64))[None]
+    assert torch.equal(o12, seg12)
+    # mask / inpaint image exactly as ldm/data/video_swap_dataset.py:150-222 builds them (numpy isin + 1 - mask)
+    img_m11 = img01 * 2 - 1
+    keep = np.isin(seg12[0].numpy(), list(O.REMOVE_MASK_TAR_FFHQ))
+    mask_ref = torch.from_numpy(1.0 - keep.astype(np.float32))[None, None]
+    m, inp = O.inpaint_from_parsing(img_m11, seg12)
+    assert torch.equal(m, mask_ref) and torch.equal(inp, img_m11 * mask_ref)
+    top2 = ref_logits.topk(2, dim=1).values
+    save("parse_256", img_seed=6, seg19=seg19.to(torch.uint8), seg12=seg12.to(torch.uint8),
+         logits_sub=ref_logits[:, :, ::16, ::16], margin=(top2[:, 0] - top2[:, 1]).to(torch.float16))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "unet", "vae", "clip"]
+    which = sys.argv[1:] or ["schedule", "unet", "vae", "clip", "parse"]
     if "schedule" in which:
         golden_schedule()
     if "unet" in which:
@@ -307,4 +350,6 @@ if __name__ == "__main__":
     if "clip" in which:
         cm, csd = golden_clip()
         golden_arcface_and_fusion(cm, csd)
+    if "parse" in which:
+        golden_parse()
     print("OK")

@@ -55,6 +55,21 @@ def test_plms_and_q_sample_match_reference_golden(oracle, unet_sd):
     assert float((x0 - g["x0"]).abs().max()) <= 5e-5 * float(g["x0"].abs().max())
 
 
+def test_face_parser_matches_reference_golden(oracle):
+    """BiSeNet + label conversion (pretrained/face_parsing): fixture written from the reference's own modules."""
+    g = _g("parse_256")
+    sd = oracle.init_state_dict(oracle.parse_spec(), 0)
+    img01 = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(int(g["img_seed"])))
+    seg19, seg12 = oracle.face_parse(oracle.Params(sd, oracle.PFX_PARSE), img01)
+    assert torch.equal(seg19.to(torch.uint8), g["seg19"]) and torch.equal(seg12.to(torch.uint8), g["seg12"])
+    mean = torch.tensor(oracle.SEG_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(oracle.SEG_STD).view(1, 3, 1, 1)
+    lg = oracle.bisenet_logits(oracle.Params(sd, oracle.PFX_PARSE), (img01 - mean) / std)
+    assert float((lg[:, :, ::16, ::16] - g["logits_sub"]).abs().max()) < 1e-4
+    m, inp = oracle.inpaint_from_parsing(img01 * 2 - 1, seg12)
+    assert set(m.unique().tolist()) <= {0.0, 1.0} and torch.equal(inp, (img01 * 2 - 1) * m)
+
+
 def test_vae_matches_reference_golden(oracle, vae_sd):
     g = _g("vae_64")
     P = oracle.Params(vae_sd, oracle.PFX_VAE)
