@@ -101,6 +101,13 @@ int rfb_face_parse(rfb_ctx* ctx, const float* img01, int B, int H, int W, float*
  * remove: [host] label list (project_ffhq.yaml remove_mask_tar_FFHQ), mask [B,1,H,W], inpaint [B,3,H,W] (may be NULL). */
 int rfb_inpaint_from_parsing(rfb_ctx* ctx, const float* img, const uint8_t* seg12, const int* remove, int n_remove, int B,
                              int H, int W, float* mask, float* inpaint, void* stream);
+/* Paste-back of scripts/inference_swap_video.py:702-721 without the PIL round trip, bit exact with Pillow:
+ * uint8 conversion of the decoded face x01 [B,3,h,w] (fp32 in [0,1], device), Image.resize((up, up), BILINEAR) (up = 0: no
+ * resize), Image.transform(frame size, PERSPECTIVE, coeffs, BILINEAR) and alpha_composite over orig [B,H,W,3] (uint8,
+ * device).  coeffs: [host] [B,8] doubles, the inverse perspective coefficients the reference stores per frame
+ * (inference_swap_video.py:495-499,713).  out [B,H,W,3] uint8 (device). */
+int rfb_paste_back(rfb_ctx* ctx, const float* x01, const uint8_t* orig, const double* coeffs, int B, int h, int w, int up,
+                   int H, int W, uint8_t* out, void* stream);
 /* get_first_stage_encoding(encode_first_stage(x)) (ddpm.py:1402-1439, 850-857; autoencoder.py:324-328;
  * distributions.py:24-37): img [B,3,H,W] -> z = 0.18215*(mean + std*noise) [B,4,H/8,W/8].
  * noise NULL => mode() (z = scaled mean).  mean/logvar outputs optional (NULL). */

@@ -753,6 +753,106 @@ def inpaint_from_parsing(img_m11, seg12, remove=REMOVE_MASK_TAR_FFHQ):
 
 
 # --------------------------------------------------------------------------------------------
+# paste-back: scripts/inference_swap_video.py:702-724 -- the decoded 512x512 face is converted to uint8,
+# resized to 1024x1024 with PIL BILINEAR, warped back into the frame with PIL's PERSPECTIVE transform (BILINEAR filter)
+# and alpha-composited.  The arithmetic lives in a third-party dependency that is not under /root/reference:
+# Pillow (requirements.txt:25 pins 9.0.1, environment.yml:175 pins 9.5.0).  Below is a restatement of its published
+# algorithm (src/libImaging/Resample.c: precompute_coeffs / normalize_coeffs_8bpc / ImagingResampleHorizontal_8bpc /
+# Vertical_8bpc; Geometry.c: perspective_transform, bilinear_filter32RGB, ImagingGenericTransform; AlphaComposite.c),
+# pinned bit-for-bit against the Pillow installed in the build container (12.2.0) by tests/golden/make_golden.py.
+# --------------------------------------------------------------------------------------------
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def pil_bilinear_coeffs(insize, outsize):
+    """precompute_coeffs (triangle filter, support 1) + normalize_coeffs_8bpc: (bounds [out,2], kk [out,ksize]) int64."""
+    scale = insize / outsize
+    fs = max(scale, 1.0)
+    support = 1.0 * fs
+    ksize = int(np.ceil(support)) * 2 + 1
+    bounds = np.zeros((outsize, 2), np.int64)
+    kk = np.zeros((outsize, ksize), np.int64)
+    ss = 1.0 / fs
+    for xx in range(outsize):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), insize) - xmin
+        w = np.zeros(ksize)
+        for x in range(xmax):
+            a = abs((x + xmin - center + 0.5) * ss)
+            w[x] = 1.0 - a if a < 1.0 else 0.0
+        ww = w[:xmax].sum()
+        if ww != 0.0:
+            w[:xmax] /= ww
+        for x in range(ksize):
+            kk[xx, x] = int(-0.5 + w[x] * (1 << PIL_PRECISION_BITS)) if w[x] < 0 else int(0.5 + w[x] * (1 << PIL_PRECISION_BITS))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def pil_resize_bilinear_u8(img, out_h, out_w):
+    """Image.resize((out_w, out_h), Image.BILINEAR) for a uint8 [H,W,C] image: horizontal then vertical pass, fixed
+    point with PRECISION_BITS = 22, uint8 intermediate (inference_swap_video.py:706)."""
+    H, W, C = img.shape
+    P = PIL_PRECISION_BITS
+    bx, kx = pil_bilinear_coeffs(W, out_w)
+    tmp = np.zeros((H, out_w, C), np.uint8)
+    src = img.astype(np.int64)
+    for xx in range(out_w):
+        xmin, n = bx[xx]
+        acc = np.full((H, C), 1 << (P - 1), np.int64)
+        for x in range(n):
+            acc += src[:, xmin + x, :] * kx[xx, x]
+        tmp[:, xx, :] = np.clip(acc >> P, 0, 255)
+    by, ky = pil_bilinear_coeffs(H, out_h)
+    out = np.zeros((out_h, out_w, C), np.uint8)
+    src = tmp.astype(np.int64)
+    for yy in range(out_h):
+        ymin, n = by[yy]
+        acc = np.full((out_w, C), 1 << (P - 1), np.int64)
+        for y in range(n):
+            acc += src[ymin + y] * ky[yy, y]
+        out[yy] = np.clip(acc >> P, 0, 255)
+    return out
+
+
+def pil_perspective_paste(swapped, orig, coeffs):
+    """swapped(RGBA, alpha 255).transform(orig.size, PERSPECTIVE, coeffs, BILINEAR) alpha-composited over orig
+    (inference_swap_video.py:715-721).  Inside the warped quad alpha is exactly 255, outside exactly 0, so the composite
+    is a select.  swapped [h,w,3] uint8, orig [H,W,3] uint8, coeffs: 8 floats -> (pasted [H,W,3] uint8, inside [H,W])."""
+    h, w, _ = swapped.shape
+    H, W, _ = orig.shape
+    a = [float(v) for v in coeffs]
+    ys, xs = np.mgrid[0:H, 0:W]
+    xin, yin = xs + 0.5, ys + 0.5
+    den = a[6] * xin + a[7] * yin + 1
+    sx = (a[0] * xin + a[1] * yin + a[2]) / den
+    sy = (a[3] * xin + a[4] * yin + a[5]) / den
+    inside = ~((sx < 0.0) | (sx >= w) | (sy < 0.0) | (sy >= h))
+    sx, sy = sx - 0.5, sy - 0.5
+    fl = lambda v: np.where(v < 0.0, np.floor(v), np.trunc(v)).astype(np.int64)
+    x, y = fl(sx), fl(sy)
+    dx, dy = sx - x, sy - y
+    x0, x1 = np.clip(x, 0, w - 1), np.clip(x + 1, 0, w - 1)
+    y0, y1 = np.clip(y, 0, h - 1), np.clip(y + 1, 0, h - 1)
+    s = swapped.astype(np.float64)
+    v1 = s[y0, x0] + (s[y0, x1] - s[y0, x0]) * dx[..., None]
+    v2 = s[y1, x0] + (s[y1, x1] - s[y1, x0]) * dx[..., None]
+    v2 = np.where(((y + 1 >= 0) & (y + 1 < h))[..., None], v2, v1)
+    proj = (v1 + (v2 - v1) * dy[..., None]).astype(np.uint8)          # (UINT8) v: truncation
+    return np.where(inside[..., None], proj, orig), inside
+
+
+def paste_back(x_sample01, orig_u8, coeffs, up=1024):
+    """inference_swap_video.py:702-721 for one frame: x_sample01 [3,h,w] fp32 in [0,1] (clamped decoder output),
+    orig_u8 [H,W,3], inverse perspective coefficients -> pasted frame [H,W,3] uint8."""
+    x = 255.0 * np.transpose(np.asarray(x_sample01, dtype=np.float32), (1, 2, 0))      # :702, float32 arithmetic
+    img = x.astype(np.uint8)                                                         # :706, truncation
+    big = pil_resize_bilinear_u8(img, up, up)
+    return pil_perspective_paste(big, np.asarray(orig_u8), coeffs)[0]
+
+
+# --------------------------------------------------------------------------------------------
 # specs + whole pipeline (scripts/inference_test_bench.py:438-495)
 # --------------------------------------------------------------------------------------------
 def _meta(*shape, dtype=torch.float32):

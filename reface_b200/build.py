@@ -16,7 +16,7 @@ OBJ = os.path.join(HERE, "_build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
-SOURCES = ["engine.cu", "unet.cu", "vae.cu", "clip.cu", "arcface.cu", "parse.cu", "attn_flash.cu", "capi.cu"]
+SOURCES = ["engine.cu", "unet.cu", "vae.cu", "clip.cu", "arcface.cu", "parse.cu", "paste.cu", "attn_flash.cu", "capi.cu"]
 
 
 def _newest(paths):

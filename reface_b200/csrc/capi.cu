@@ -292,6 +292,13 @@ int rfb_inpaint_from_parsing(rfb_ctx* h, const float* img, const uint8_t* seg12,
   inpaint_from_parsing(c, img, seg12, bits, B, H, W, mask, inpaint);
   API_END
 }
+int rfb_paste_back(rfb_ctx* h, const float* x01, const uint8_t* orig, const double* coeffs, int B, int hh, int ww, int up,
+                   int H, int W, uint8_t* out, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  paste_back(c, x01, orig, coeffs, B, hh, ww, up, H, W, out);
+  API_END
+}
 int rfb_vae_encode(rfb_ctx* h, const float* img, const float* noise, int B, int H, int W, float* z, float* mean,
                    float* logvar, void* stream) {
   API_BEGIN(h)

@@ -174,6 +174,9 @@ struct FaceParser {
 FaceParser* build_face_parser(Ctx& c, const std::string& pfx);
 void face_parse(Ctx& c, FaceParser& m, const float* img01, int B, int H, int W, float* logits8, uint8_t* seg19,
                 uint8_t* seg12);
+// paste-back (scripts/inference_swap_video.py:702-721), Pillow-exact: see paste.cu
+void paste_back(Ctx& c, const float* x01, const uint8_t* orig, const double* coeffs, int B, int h, int w, int up, int H, int W,
+                uint8_t* out);
 void inpaint_from_parsing(Ctx& c, const float* img, const uint8_t* seg12, unsigned remove_bits, int B, int H, int W,
                           float* mask, float* inpaint);
 void arcface_embed(Ctx& c, ArcFace& m, const float* img224, int B, float* out512);

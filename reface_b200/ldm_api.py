@@ -398,3 +398,10 @@ def swap_video(model: LatentDiffusion, ref_img, tar_img, inpaint_img, mask_lat, 
         for i in range(b):
             out[lo + i] = img[i]
     return out
+
+
+def paste_back(model: LatentDiffusion, images, orig_frames_u8, inv_coeffs, up=1024):
+    """scripts/inference_swap_video.py:702-721 for a batch of frames, on the device and bit exact with Pillow:
+    images [B,3,h,w] in [0,1] (swap_faces / swap_video outputs), orig_frames_u8 [B,H,W,3] uint8, inv_coeffs [B,8] (the
+    per-frame inverse perspective coefficients of crop_and_align_face, :71-103,713) -> pasted frames [B,H,W,3] uint8."""
+    return model.engine.paste_back(images, orig_frames_u8, inv_coeffs, up=up)

@@ -45,6 +45,7 @@ SIGNATURES = {
     "rfb_q_sample": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp]),
     "rfb_face_parse": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "rfb_inpaint_from_parsing": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "rfb_paste_back": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "rfb_vae_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "rfb_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "rfb_clip_encode": (_i, [_vp, _vp, _i, _vp, _vp]),
@@ -299,6 +300,19 @@ class Engine:
         self._ck(self.lib.rfb_inpaint_from_parsing(self.h, _ptr(img), _ptr(seg12), rem, len(remove), B, H, W, _ptr(mask),
                                                    _ptr(inp), self._stream()))
         return mask, inp
+
+    def paste_back(self, x01, orig_u8, coeffs, up=1024):
+        """inference_swap_video.py:702-721 on the device, bit exact with Pillow: x01 [B,3,h,w] in [0,1], orig_u8 [B,H,W,3]
+        uint8, coeffs [B,8] inverse perspective coefficients -> pasted frames [B,H,W,3] uint8."""
+        x01 = self._in(x01)
+        orig_u8 = orig_u8.to(self.device, torch.uint8).contiguous()
+        B, _, h, w = x01.shape
+        _, H, W, _ = orig_u8.shape
+        co = np.ascontiguousarray(np.asarray(coeffs, dtype=np.float64).reshape(B, 8))
+        out = torch.empty_like(orig_u8)
+        self._ck(self.lib.rfb_paste_back(self.h, _ptr(x01), _ptr(orig_u8), co.ctypes.data_as(C.c_void_p), B, h, w, int(up),
+                                         H, W, _ptr(out), self._stream()))
+        return out
 
     def vae_encode(self, img, noise=None, return_moments=False):
         img, noise = self._in(img), self._in(noise)

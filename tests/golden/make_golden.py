@@ -332,8 +332,39 @@ def golden_parse():
          logits_sub=ref_logits[:, :, ::16, ::16], margin=(top2[:, 0] - top2[:, 1]).to(torch.float16))
 
 
+def golden_paste():
+    print("paste-back (Pillow itself: resize BILINEAR, PERSPECTIVE transform, alpha composite)")
+    import PIL
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    # the restatement of Pillow's resampling / transform is bit exact at several shapes ...
+    for (h, w, oh, ow) in ((37, 53, 74, 106), (64, 64, 128, 128), (50, 50, 75, 120), (96, 96, 48, 60)):
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(a).resize((ow, oh), Image.BILINEAR))
+        assert np.array_equal(ref, O.pil_resize_bilinear_u8(a, oh, ow)), (h, w, oh, ow)
+    # ... and so is the whole per-frame paste-back of scripts/inference_swap_video.py:702-721
+    g = torch.Generator().manual_seed(12)
+    x01 = torch.rand(3, 64, 64, generator=g).clamp(0, 1)
+    orig = rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)
+    coeffs = np.array([0.93, 0.07, -14.0, -0.05, 1.04, -9.0, 3e-5, -2e-5])
+    up = 128
+    x_sample = 255. * np.transpose(x01.numpy(), (1, 2, 0))
+    img = Image.fromarray(x_sample.astype(np.uint8)).resize((up, up), Image.BILINEAR)
+    swapped_and_pasted = img.convert('RGBA')
+    pasted_image = Image.fromarray(orig).convert('RGBA')
+    swapped_and_pasted.putalpha(255)
+    projected = swapped_and_pasted.transform((orig.shape[1], orig.shape[0]), Image.PERSPECTIVE, coeffs, Image.BILINEAR)
+    pasted_image.alpha_composite(projected)
+    ref = np.asarray(pasted_image)[..., :3]
+    assert set(np.unique(np.asarray(projected)[..., 3])) <= {0, 255}
+    mine = O.paste_back(x01.numpy(), orig, coeffs, up=up)
+    assert np.array_equal(ref, mine)
+    print(f"  paste-back bit exact vs Pillow {PIL.__version__}; inside fraction {(np.asarray(projected)[..., 3] == 255).mean():.3f}")
+    save("paste_64", x01=x01, orig=orig, coeffs=coeffs, up=up, pasted=ref, pillow=np.array(PIL.__version__))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "unet", "vae", "clip", "parse"]
+    which = sys.argv[1:] or ["schedule", "unet", "vae", "clip", "parse", "paste"]
     if "schedule" in which:
         golden_schedule()
     if "unet" in which:
@@ -352,4 +383,6 @@ if __name__ == "__main__":
         golden_arcface_and_fusion(cm, csd)
     if "parse" in which:
         golden_parse()
+    if "paste" in which:
+        golden_paste()
     print("OK")

@@ -154,3 +154,23 @@ def test_concat9_bit_exact_and_ddim_update(engine, oracle):
         xp, p0 = engine.cfg_ddim_update(x, eps2, 3.5, *a)
         rxp, rp0, _ = oracle.cfg_ddim_update(x, eps2[:B], eps2[B:], 3.5, *a)
         assert torch.equal(xp.cpu(), rxp) and torch.equal(p0.cpu(), rp0)   # same fp32 op order: bit exact
+
+
+def test_paste_back_bit_exact(engine, oracle):
+    """rfb_paste_back vs the Pillow-written fixture (bit exact) and vs the oracle at the real sizes
+    (512 -> 1024 resize, 720p frame, two frames with different coefficients)."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "paste_64.npz"))
+    out = engine.paste_back(torch.from_numpy(g["x01"])[None], torch.from_numpy(g["orig"])[None], g["coeffs"][None],
+                            up=int(g["up"]))
+    assert np.array_equal(out[0].cpu().numpy(), g["pasted"])
+    gen = torch.Generator().manual_seed(21)
+    x01 = torch.rand(2, 3, 512, 512, generator=gen)
+    orig = torch.randint(0, 256, (2, 720, 1280, 3), generator=gen, dtype=torch.uint8)
+    co = np.array([[1.45, 0.05, -310.0, -0.04, 1.5, -95.0, 2e-5, -1e-5], [1.2, -0.1, -150.0, 0.08, 1.25, -60.0, -3e-5, 4e-5]])
+    out = engine.paste_back(x01, orig, co, up=1024).cpu().numpy()
+    for i in range(2):
+        ref = oracle.paste_back(x01[i].numpy(), orig[i].numpy(), co[i], up=1024)
+        assert np.array_equal(out[i], ref), i

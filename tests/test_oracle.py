@@ -70,6 +70,15 @@ def test_face_parser_matches_reference_golden(oracle):
     assert set(m.unique().tolist()) <= {0.0, 1.0} and torch.equal(inp, (img01 * 2 - 1) * m)
 
 
+def test_paste_back_matches_pillow_golden(oracle):
+    """Paste-back (inference_swap_video.py:702-721): the restatement of Pillow's resize / PERSPECTIVE transform / alpha
+    composite reproduces the fixture written by Pillow itself bit for bit."""
+    g = np.load(os.path.join(GOLDEN, "paste_64.npz"))
+    out = oracle.paste_back(g["x01"], g["orig"], g["coeffs"], up=int(g["up"]))
+    assert np.array_equal(out, g["pasted"])
+    assert 0.2 < float((out != g["orig"]).any(-1).mean()) < 1.0       # part of the frame is replaced, part shows through
+
+
 def test_vae_matches_reference_golden(oracle, vae_sd):
     g = _g("vae_64")
     P = oracle.Params(vae_sd, oracle.PFX_VAE)
