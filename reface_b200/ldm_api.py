@@ -236,8 +236,10 @@ class LatentDiffusion:
         `landmarks136` (raw 68x2 dlib points) may be given instead of the projected `landmarks`."""
         e = self.engine
         b = x.shape[0]
-        c_src = e.clip_encode(x)
-        c_tgt = e.clip_encode(e.target_clip_input(tar))
+        # one CLIP pass over [source ; resized target] (the reference encodes them separately, ddpm.py:884,913: same
+        # values, every sample is independent)
+        c_both = e.clip_encode(torch.cat([x, e.target_clip_input(tar)], 0))
+        c_src, c_tgt = c_both[:b], c_both[b:]
         idf = e.arcface_embed(x)
         if landmarks136 is None:
             landmarks136 = torch.zeros(b, 136, device=self.device)
