@@ -759,6 +759,40 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __res
   }
 }
 
+// split-K reduction: out[m, n] = fp16(sum_z part[z][m][n] (fixed order) + bias[n] + rowvec[(m / rpv) * ldv + n] + res[m, n])
+// -- the epilogue terms of the GEMM in the same order as the fused epilogue (bias, row vector, residual).  N % 4 == 0.
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int ks, long long M, int N,
+                                     const float* __restrict__ bias, const float* __restrict__ rowvec, int rpv, int ldv,
+                                     const __half* __restrict__ res, long long ldr, __half* __restrict__ out, long long ldo) {
+  const int nv = N >> 2;
+  const long long total = M * nv;
+  const long long zs = M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % nv);
+    const long long m = i / nv;
+    const float* p = part + m * N + c4 * 4;
+    float4 a = *reinterpret_cast<const float4*>(p);
+    for (int z = 1; z < ks; ++z) {
+      const float4 b = *reinterpret_cast<const float4*>(p + z * zs);
+      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    }
+    const int n = c4 * 4;
+    if (bias) a.x += bias[n], a.y += bias[n + 1], a.z += bias[n + 2], a.w += bias[n + 3];
+    if (rowvec) {
+      const float* rv = rowvec + (m / rpv) * ldv + n;
+      a.x += rv[0], a.y += rv[1], a.z += rv[2], a.w += rv[3];
+    }
+    if (res) {
+      const uint2 u = *reinterpret_cast<const uint2*>(res + m * ldr + n);
+      const float2 f0 = unpack_h2(u.x), f1 = unpack_h2(u.y);
+      a.x += f0.x, a.y += f0.y, a.z += f1.x, a.w += f1.y;
+    }
+    uint2 o;
+    o.x = pack_h2(a.x, a.y), o.y = pack_h2(a.z, a.w);
+    *reinterpret_cast<uint2*>(out + m * ldo + n) = o;
+  }
+}
+
 // fp32 -> fp16 copy with optional row padding: dst[r, 0..Kp) = src[r, 0..K) (zeros beyond K)
 __global__ void pack_rows_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long rows, int K,
                                      int Kp) {

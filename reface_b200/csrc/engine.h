@@ -83,6 +83,7 @@ struct Ctx {
   int attn_pad = 0;      // test hook: rfb_op_attention repacks q/k/v with 64-element head slices
   int attn_poly = 0;     // attention v3/v4: exponentials per 8 evaluated on the FMA pipe (measured slower: off)
   int cfg_share = 1;     // samplers: compute the context-independent head of the UNet once per CFG pair
+  int gemm_splitk = 0;   // split-K for long-K GEMMs with few output tiles (not bitwise batch-independent: opt-in)
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)
   int gn_fused = 1;  // single-launch cluster GroupNorm (0: stats / finalize / apply kernels)
   int gn_cluster = 16, gn_threads = 512;  // fused GroupNorm: CTAs per sample (cluster size), threads per CTA

@@ -69,7 +69,7 @@ __device__ __forceinline__ void sts32f(uint32_t a, float v) {
 }
 
 struct EpiTile {  // warp-uniform description of one output tile for one epilogue warp
-  int ncols, NO, ocol_tile, halfN;
+  int ncols, NO, ocol_tile, halfN, z;
   long long m_base, zoff;
   bool vec_ok;
 };
@@ -82,6 +82,7 @@ __device__ __forceinline__ EpiTile epi_tile_info(const GemmArgs& g, int q, int m
   t.NO = (MODE == EPI_GEGLU) ? (g.N >> 1) : g.N;
   t.ocol_tile = (MODE == EPI_GEGLU) ? n_tile * t.halfN : n_tile * g.BN;
   t.m_base = (long long)m_tile * GEMM_BM + q * 32;
+  t.z = z;
   t.zoff = (g.zdiv == 1) ? (long long)z * g.zs_outer  // plain / conv / per-sample batches: no division per tile
                          : (long long)(z / g.zdiv) * g.zs_outer + (long long)(z % g.zdiv) * g.zs_inner;
   t.vec_ok = g.out != nullptr && (t.NO & 7) == 0 && (g.ldo & 7) == 0 && (t.zoff & 7) == 0 &&
@@ -245,6 +246,26 @@ __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile&
             v[j] = apply_act(v[j], g.act, (g.act == ACT_PRELU && col < g.N) ? __ldg(g.act_param + col) : 0.f);
           }
         }
+      }
+      if (MODE == EPI_GENERIC && g.ksplit) {
+        // split-K: the raw fp32 accumulators of this K slice -> out32[z][M][N], through the (otherwise idle) staging
+        // tile so that the stores are coalesced: a row of 32 floats is exactly one 128-byte staging row
+#pragma unroll
+        for (int u4 = 0; u4 < 8; ++u4)
+          sts128(my_row + (uint32_t)((u4 ^ sw) << 4),
+                 make_uint4(__float_as_uint(v[4 * u4]), __float_as_uint(v[4 * u4 + 1]), __float_as_uint(v[4 * u4 + 2]),
+                            __float_as_uint(v[4 * u4 + 3])));
+        __syncwarp();
+        float* part = g.out32 + (long long)t.z * g.M * g.N;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + (lane >> 3), unit = lane & 7;
+          const long long gm = t.m_base + row;
+          const uint4 val = lds128(stage + (uint32_t)row * 128u + (uint32_t)((unit ^ (row & 7)) << 4));
+          if (gm < g.M && oc + unit * 4 < g.N) *reinterpret_cast<uint4*>(part + gm * g.N + oc + unit * 4) = val;
+        }
+        __syncwarp();
+        continue;
       }
       if (t.vec_ok) {
         // own row: add the staged residual, then overwrite the same 16-byte units with the fp16 result

@@ -117,11 +117,12 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_expect_tx(full, tx);
           const uint32_t dA = sA + s * GEMM_A_STAGE_BYTES;
           const uint32_t dB = sB + s * b_stage_bytes;
+          const int kg = g.ksplit ? z * g.nk + kb : kb;  // split-K: this unit's slice of the K range
           switch (g.a_mode) {
-            case A_PLAIN: tma_load_2d(dA, &tmA, full, kb * GEMM_BK, m0); break;
+            case A_PLAIN: tma_load_2d(dA, &tmA, full, kg * GEMM_BK, m0); break;
             case A_CONV3: {
-              const int tap = kb / g.cblocks;
-              const int cb = kb - tap * g.cblocks;
+              const int tap = kg / g.cblocks;
+              const int cb = kg - tap * g.cblocks;
               const int dy = tap / 3 - 1, dx = tap % 3 - 1;
               tma_load_4d(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn);
             } break;
@@ -129,7 +130,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             default: tma_load_4d(dA, &tmA, full, kb * GEMM_BK, z % g.heads, m0, z / g.heads); break;
           }
           switch (g.b_mode) {
-            case B_PLAIN: tma_load_2d(dB, &tmB, full, kb * GEMM_BK, n0); break;
+            case B_PLAIN: tma_load_2d(dB, &tmB, full, kg * GEMM_BK, n0); break;
             case B_BATCH3: tma_load_3d(dB, &tmB, full, kb * GEMM_BK, n0, z); break;
             default: tma_load_4d(dB, &tmB, full, kb * GEMM_BK, z % g.heads, n0, z / g.heads); break;
           }

@@ -38,6 +38,8 @@ struct GemmArgs {
   float* out32;  // optional fp32 strided output: (m / o32_rpn) * o32_sn + (m % o32_rpn) * o32_sp + col * o32_sc
   long long o32_sn, o32_sp, o32_sc;
   int o32_rpn;
+  // split-K: blockIdx.z = K slice; k-block index = z * nk + kb; raw fp32 partial tiles go to out32[z][M][N]
+  int ksplit;
   // batch (blockIdx.z) offsets in elements for out/res: (z / zdiv) * zs_outer + (z % zdiv) * zs_inner
   long long zs_outer, zs_inner;
   int zdiv;

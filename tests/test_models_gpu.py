@@ -165,3 +165,18 @@ def test_face_parser_vs_reference_golden(engine, oracle):
     img2 = torch.cat([img01, torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(7))])
     s2, _ = engine.face_parse(img2)
     assert torch.equal(s2[0], seg19[0])
+
+
+def test_full_path_at_1024(engine, unet_sd, vae_sd, clip_sd, arc_sd, fusion_sd):
+    """BASELINE configs[3] shape (1024x1024 image, latent 128x128: 16384-token attention in the UNet and in the VAE
+    mid block) through the whole path with 2 DDIM steps: finite output in [0,1]; the same call repeated gives the
+    same bits (no atomics / races anywhere in the path)."""
+    from reface_b200 import synth
+    from reface_b200.ldm_api import LatentDiffusion, swap_faces
+    model = LatentDiffusion({**unet_sd, **vae_sd, **clip_sd, **arc_sd, **fusion_sd}, engine=engine)
+    inp = synth.synthetic_inputs(1, 1024, engine.device, seed=3)
+    a = swap_faces(model, S=2, scale=3.5, **inp)["image"]
+    b = swap_faces(model, S=2, scale=3.5, **inp)["image"]
+    assert a.shape == (1, 3, 1024, 1024) and bool(torch.isfinite(a).all())
+    assert float(a.min()) >= 0.0 and float(a.max()) <= 1.0 and float(a.std()) > 1e-3
+    assert torch.equal(a, b)
