@@ -132,9 +132,11 @@ Lin32 lin32(Ctx& c, const std::string& wname, const std::string& bname) {
 
 // ------------------------------------------------------------------------------------------ TMA descriptors
 CUtensorMap make_tmap(Ctx& c, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                             const uint32_t* box) {
+                             const uint32_t* box, const uint32_t* elem_strides) {
   CUtensorMap m;
   uint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides)
+    for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   RFB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
   for (int i = 0; i + 1 < rank; ++i) RFB_CHECK(strides_b[i] % 16 == 0, "TMA strides must be multiples of 16 bytes");
   auto fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(c.encode_fn);
@@ -218,6 +220,8 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     rec.mode = g.a_mode * 100 + (g.geglu ? 10 : 0) + (g.res ? 1 : 0) + (g.rowvec ? 2 : 0) + (g.out32 ? 4 : 0);
     CUDA_OK(cudaEventRecord(rec.a, c.stream));
   }
+  RFB_CHECK(g.a_mode != A_CONV3 || g.cstride == 1 || (c.gemm_persistent && !c.gemm_pair),
+            "strided implicit-GEMM convolutions need the persistent 1-CTA kernel");
   const bool pair_ok = c.gemm_pair && c.gemm_persistent && Bplain != nullptr && grid.z == 1 && grid.x >= 2 &&
                        (g.a_mode == A_PLAIN || g.a_mode == A_CONV3) && g.b_mode == B_PLAIN && g.nk >= c.gemm_pair_min_nk &&
                        (long long)grid.x * grid.y >= c.num_sms / 2;
@@ -393,10 +397,19 @@ Tens linear_t(Ctx& c, const Tens& x, const LinW& w, Epi e) {
   return y;
 }
 
-static bool conv_tma_ok(const Tens& x, const ConvW& w, int stride, int pt, int pl, int pb, int pr) {
-  if (w.ksz != 3 || stride != 1 || pt != 1 || pl != 1 || pb != 1 || pr != 1) return false;
-  if (w.cin % 64 != 0) return false;
-  const int W = x.w, H = x.h;
+// Implicit GEMM straight from the NHWC activation: stride 1 with padding 1, or (option conv_tma_stride2) stride 2 with
+// any top/left padding in {0, 1} -- the A tile of tap (ky, kx) is then a 4-D TMA box with element strides {1,2,2,1}
+// starting at (2*ox0 + kx - pad_l, 2*oy0 + ky - pad_t); out-of-range pixels are zero-filled by TMA on every side.
+static bool conv_tma_ok(Ctx& c, const Tens& x, const ConvW& w, int stride, int pt, int pl, int pb, int pr, int Ho, int Wo) {
+  if (w.ksz != 3 || w.cin % 64 != 0) return false;
+  if (stride == 1) {
+    if (pt != 1 || pl != 1 || pb != 1 || pr != 1) return false;
+  } else if (stride == 2) {
+    if (!c.conv_tma_stride2 || pt < 0 || pt > 1 || pl < 0 || pl > 1) return false;
+  } else {
+    return false;
+  }
+  const int W = Wo, H = Ho;  // tiles are cut from the OUTPUT map
   if (W >= 128) return W % 128 == 0;
   if (128 % W != 0) return false;
   const int rows = 128 / W;  // image rows per tile
@@ -419,7 +432,7 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
     gemm(c, x.p, x.c, M, x.c, w.w, w.kp, w.cout, y.p, y.c, e);
     return y;
   }
-  if (conv_tma_ok(x, w, stride, pad_t, pad_l, pad_b, pad_r)) {
+  if (conv_tma_ok(c, x, w, stride, pad_t, pad_l, pad_b, pad_r, Ho, Wo)) {
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.M = (int)M, g.N = w.cout, g.cblocks = w.cin / 64, g.nk = 9 * g.cblocks;
@@ -438,18 +451,21 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
                   : pick_bn(c, M, w.cout, false, 9 * w.cin,
                             e.out32 == nullptr && (w.cout & 7) == 0 && (!e.res || (e.ldr & 7) == 0));
     g.a_mode = A_CONV3, g.b_mode = B_PLAIN;
-    g.bw = std::min(x.w, 128);
-    g.bh = std::min(x.h, 128 / g.bw);
+    g.bw = std::min(Wo, 128);
+    g.bh = std::min(Ho, 128 / g.bw);
     g.bimg = 128 / (g.bw * g.bh);
-    g.tiles_w = x.w / g.bw, g.tiles_h = x.h / g.bh;
+    g.tiles_w = Wo / g.bw, g.tiles_h = Ho / g.bh;
+    g.cstride = stride, g.cpad_l = pad_l, g.cpad_t = pad_t;
     fill_epi(g, e, ks > 1 ? nullptr : y.p, y.c);
     const uint64_t da[4] = {(uint64_t)x.c, (uint64_t)x.w, (uint64_t)x.h, (uint64_t)x.n};
     const uint64_t sa[3] = {(uint64_t)x.c * 2, (uint64_t)x.w * x.c * 2, (uint64_t)x.h * x.w * x.c * 2};
-    const uint32_t ba[4] = {64, (uint32_t)g.bw, (uint32_t)g.bh, (uint32_t)g.bimg};
+    // with element strides the box spans stride * (elements loaded) positions of the traversed dimension
+    const uint32_t ba[4] = {64, (uint32_t)(g.bw * stride), (uint32_t)(g.bh * stride), (uint32_t)g.bimg};
+    const uint32_t ea[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     const uint64_t db[2] = {(uint64_t)w.kp, (uint64_t)round_up(w.cout, 32)};
     const uint64_t sb[1] = {(uint64_t)w.kp * 2};
     const uint32_t bb[2] = {64, (uint32_t)g.BN};
-    CUtensorMap tmA = make_tmap(c, x.p, 4, da, sa, ba);
+    CUtensorMap tmA = make_tmap(c, x.p, 4, da, sa, ba, stride > 1 ? ea : nullptr);
     CUtensorMap tmB = make_tmap(c, w.w, 2, db, sb, bb);
     dim3 grid((unsigned)((M + 127) / 128), (unsigned)((w.cout + g.BN - 1) / g.BN), (unsigned)ks);
     launch_gemm(c, tmA, tmB, g, grid, 9.0 * w.cin / ks, w.w, w.kp, round_up(w.cout, 32));
@@ -546,14 +562,29 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
   int R = std::max(1, 512 / cv);
   if (c.gn_fused) {
     R = std::max(1, std::min(c.gn_threads, 512) / cv);
-    const int GC = c.gn_cluster;
-    // one launch: a cluster of GN_CLUSTER CTAs per sample (statistics exchanged through DSMEM), see elem.cuh
+    // one launch: a cluster of 16 (or 8) CTAs per sample (statistics exchanged through DSMEM), see elem.cuh
     static bool attr = false;
+    static int max_cluster = 16;
     if (!attr) {
       CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      // 16-CTA clusters are a non-portable size: fall back to the portable 8 where the device (e.g. a partitioned
+      // GPU) cannot co-schedule them.  The choice is fixed per process, so results stay reproducible.
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(16, 1), q.blockDim = dim3(512), q.dynamicSmemBytes = 48 * 1024;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 16, qa[0].val.clusterDim.y = 1, qa[0].val.clusterDim.z = 1;
+      q.attrs = qa, q.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, gn_fused_kernel, &q) != cudaSuccess || nclusters < 1) {
+        cudaGetLastError();
+        max_cluster = 8;
+      }
       attr = true;
     }
+    const int GC = std::min(c.gn_cluster, max_cluster);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)GC, (unsigned)x.n);

@@ -83,6 +83,7 @@ struct Ctx {
   int attn_pad = 0;      // test hook: rfb_op_attention repacks q/k/v with 64-element head slices
   int attn_poly = 0;     // attention v3/v4: exponentials per 8 evaluated on the FMA pipe (measured slower: off)
   int cfg_share = 1;     // samplers: compute the context-independent head of the UNet once per CFG pair
+  int conv_tma_stride2 = 1;  // stride-2 3x3 convs as implicit GEMM through strided TMA boxes (0: explicit im2col)
   int gemm_splitk = 0;   // split-K for long-K GEMMs with few output tiles (not bitwise batch-independent: opt-in)
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)
   int gn_fused = 1;  // single-launch cluster GroupNorm (0: stats / finalize / apply kernels)
@@ -143,7 +144,7 @@ int pick_bn(Ctx& c, long long M, int N, bool geglu, int K = 0, bool allow16 = fa
 
 // TMA descriptor (fp16, 128-byte swizzle, zero fill out of bounds); dims/box innermost first, strides in bytes
 CUtensorMap make_tmap(Ctx& c, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                      const uint32_t* box);
+                      const uint32_t* box, const uint32_t* elem_strides = nullptr);
 // fused flash-style attention (tcgen05, S and O tiles in TMEM); returns false when the shape is not covered
 // hs = distance in elements between consecutive heads inside a q / k / v section (0: packed, hs = d)
 bool attention_flash(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads, int d, __half* out,

@@ -123,8 +123,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             case A_CONV3: {
               const int tap = kg / g.cblocks;
               const int cb = kg - tap * g.cblocks;
-              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-              tma_load_4d(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn);
+              const int dy = tap / 3 - g.cpad_t, dx = tap % 3 - g.cpad_l;
+              tma_load_4d(dA, &tmA, full, cb * GEMM_BK, cw * g.cstride + dx, ch * g.cstride + dy, cn);
             } break;
             case A_BATCH3: tma_load_3d(dA, &tmA, full, kb * GEMM_BK, m0, z); break;
             default: tma_load_4d(dA, &tmA, full, kb * GEMM_BK, z % g.heads, m0, z / g.heads); break;

@@ -22,6 +22,7 @@ struct GemmArgs {
   int a_mode, b_mode;
   // A_CONV3 geometry: tile = bimg images x bh rows x bw cols (=128 output pixels), K = taps x cblocks x 64
   int cblocks, bw, bh, bimg, tiles_w, tiles_h;
+  int cstride, cpad_l, cpad_t;  // conv stride (1 or 2) and left / top padding: input coordinate = stride * out + tap - pad
   int heads;  // *_HEADS4: z = n*heads + head
   // epilogue
   float alpha;

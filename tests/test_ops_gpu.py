@@ -70,10 +70,18 @@ def test_conv3x3_implicit_gemm_tma(engine, N, C, H, O):
                                              (1, 128, 32, 128, 3, 2, (0, 0, 1, 1)), (2, 3, 28, 64, 3, 1, (1, 1, 1, 1)),
                                              (2, 64, 14, 128, 1, 2, (0, 0, 0, 0)), (1, 3, 56, 128, 14, 14, (0, 0, 0, 0)),
                                              (2, 64, 28, 64, 3, 1, (1, 1, 1, 1)), (2, 4, 8, 512, 3, 1, (1, 1, 1, 1)),
-                                             (2, 960, 8, 320, 1, 1, (0, 0, 0, 0))])
-def test_conv_generic_im2col(engine, N, C, H, O, k, s, pad):
+                                             (2, 960, 8, 320, 1, 1, (0, 0, 0, 0)), (2, 320, 64, 320, 3, 2, (1, 1, 1, 1)),
+                                             (1, 128, 256, 128, 3, 2, (0, 0, 1, 1)), (4, 640, 32, 640, 3, 2, (1, 1, 1, 1))])
+@pytest.mark.parametrize("tma_s2", [0, 1])
+def test_conv_generic_im2col(engine, N, C, H, O, k, s, pad, tma_s2):
+    """tma_s2=1: stride-2 3x3 convolutions with Cin % 64 == 0 run as implicit GEMM through strided TMA boxes
+    (option conv_tma_stride2) instead of an explicit im2col; every other case takes the im2col path either way."""
     x, w, b = h(rn(N, C, H, H, seed=1)), h(rn(O, C, k, k, seed=2) / math.sqrt(k * k * C)), rn(O, seed=3)
-    y = engine.op_conv2d(x, w, b, stride=s, pad=pad)
+    engine.set_option("conv_tma_stride2", tma_s2)
+    try:
+        y = engine.op_conv2d(x, w, b, stride=s, pad=pad)
+    finally:
+        engine.set_option("conv_tma_stride2", 1)
     pt, pl, pb, pr = pad
     ref = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, b, stride=s)
     assert y.shape == ref.shape
