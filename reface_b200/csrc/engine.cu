@@ -560,7 +560,10 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
   const int HW = x.h * x.w, C = x.c, cv = C / 8;
   RFB_CHECK(cv <= 512, "GroupNorm: too many channels");
   int R = std::max(1, 512 / cv);
-  if (c.gn_fused) {
+  // One cluster launch for the UNet's maps; the three-kernel path (whole-grid statistics, finalize, whole-grid apply) for
+  // maps of >= gn_fused_max_elems elements per sample (the VAE's 256^2 / 512^2 levels), where 16 CTAs per sample are too
+  // few to stream from HBM (profiles/r01s2_micro_bench.txt).  The choice depends on the per-sample shape only.
+  if (c.gn_fused && (long long)HW * C < c.gn_fused_max_elems) {
     R = std::max(1, std::min(c.gn_threads, 512) / cv);
     // one launch: a cluster of 16 (or 8) CTAs per sample (statistics exchanged through DSMEM), see elem.cuh
     static bool attr = false;

@@ -98,10 +98,12 @@ def test_groupnorm(engine, N, C, H, eps, silu, fused):
     x = h(rn(N, C, H, H, seed=1) * 2 + 0.5)
     gam, bet = 1 + 0.1 * rn(C, seed=2), 0.1 * rn(C, seed=3)
     engine.set_option("gn_fused", fused)
+    engine.set_option("gn_fused_max_elems", 1 << 40)      # exercise the cluster kernel at every test shape
     try:
         y = engine.op_groupnorm(x, gam, bet, eps, silu)
     finally:
         engine.set_option("gn_fused", 1)
+        engine.set_option("gn_fused_max_elems", 4 << 20)
     ref = F.group_norm(x, 32, gam, bet, eps)
     ref = F.silu(ref) if silu else ref
     assert float((y - ref).abs().max()) < 6e-3
