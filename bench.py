@@ -129,8 +129,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
-    # stdout carries exactly ONE JSON line: NCCL's version banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    # version banner there on the first collective), so fd 1 is pointed at stderr for the whole run and the JSON line is
+    # written to the saved original descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -149,7 +158,7 @@ def main():
                     warmup=args.warmup, ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32", data="synthetic", config=config, impl="reference", cpu_baseline=cb,
                     e2e=dict(value=cb["value"], unit="faces/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch.distributed as dist
@@ -247,7 +256,7 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(args, 1, 1)[0]
             except Exception as e:  # the GPU number stands on its own
                 line["cpu_baseline"] = dict(error=repr(e))
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
