@@ -152,6 +152,7 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "gn_fused") c.gn_fused = (int)value;
   else if (k == "cfg_share") c.cfg_share = (int)value;
   else if (k == "gn_cluster") c.gn_cluster = (int)value;
+  else if (k == "gn_split2") c.gn_split2 = (int)value;
   else if (k == "gn_fused_max_elems") c.gn_fused_max_elems = value;
   else if (k == "gn_threads") c.gn_threads = (int)value;
   else if (k == "attn_poly") c.attn_poly = (int)value;

@@ -263,6 +263,138 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __res
   }
 }
 
+// Two-launch GroupNorm (whole-grid): gn_stats2 = gn_stats with 8 batched 16-byte loads in flight per thread and
+// bank-conflict-free partial sums; gn_apply2 = gn_apply with the finalize step (fixed-order fold of the per-slab partials,
+// same arithmetic as gn_finalize_kernel) done by every CTA for its own sample instead of a separate launch.
+__global__ void __launch_bounds__(512)
+gn_stats2_kernel(const __half* __restrict__ x, float* __restrict__ stats, int HW, int C, int slab, int G) {
+  extern __shared__ float sh[];  // [R][16][cv] + [2*C]
+  const int cv = C >> 3;
+  const int R = blockDim.x / cv;
+  const int cq = threadIdx.x % cv, pr = threadIdx.x / cv;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * slab;
+  const int p1 = min(HW, p0 + slab);
+  const __half* xn = x + (long long)n * HW * C + cq * 8;
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  for (int pb = p0 + pr; pb < p1; pb += 8 * R) {
+    uint4 u[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int p = pb + k * R;
+      u[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * C));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack_h2(w[t]);
+        s[2 * t] += f.x;
+        ss[2 * t] = fmaf(f.x, f.x, ss[2 * t]);
+        s[2 * t + 1] += f.y;
+        ss[2 * t + 1] = fmaf(f.y, f.y, ss[2 * t + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sh[((size_t)pr * 16 + 2 * j) * cv + cq] = s[j];
+    sh[((size_t)pr * 16 + 2 * j + 1) * cv + cq] = ss[j];
+  }
+  __syncthreads();
+  float* chs = sh + (size_t)R * 2 * C;
+  for (int i = threadIdx.x; i < 16 * cv; i += blockDim.x) {
+    const int k = i / cv, c8 = i - k * cv;
+    float a = 0.f;
+    for (int rr = 0; rr < R; ++rr) a += sh[((size_t)rr * 16 + k) * cv + c8];
+    chs[2 * (c8 * 8 + (k >> 1)) + (k & 1)] = a;
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  if (threadIdx.x < 2 * G) {
+    const int gi = threadIdx.x >> 1, which = threadIdx.x & 1;
+    float a = 0.f;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) a += chs[2 * c + which];
+    stats[((long long)n * gridDim.x + blockIdx.x) * 2 * G + threadIdx.x] = a;
+  }
+}
+__global__ void __launch_bounds__(512)
+gn_apply2_kernel(const __half* __restrict__ x, const float* __restrict__ partial, int nslab, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, __half* __restrict__ y, int HW, int C, int G, float eps, int silu, int slab) {
+  __shared__ float st[64];  // mean / rstd per group (G <= 32)
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  {  // finalize (same order as gn_finalize_kernel): 8 threads per group fold slabs t, t+8, ..., then a fixed shuffle tree
+    const int gi = threadIdx.x >> 3, t = threadIdx.x & 7;
+    float s = 0.f, ss = 0.f;
+    if (gi < G) {
+      for (int sl = t; sl < nslab; sl += 8) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(partial + (((long long)n * nslab + sl) * G + gi) * 2));
+        s += v.x;
+        ss += v.y;
+      }
+    }
+    if (threadIdx.x < 256) {  // whole warps: 8 * G <= 256
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      }
+    }
+    if (gi < G && t == 0) {
+      const float cnt = (float)cpg * (float)HW;
+      const float mean = s / cnt;
+      const float var = fmaxf(ss / cnt - mean * mean, 0.f);
+      st[2 * gi] = mean;
+      st[2 * gi + 1] = rsqrtf(var + eps);
+    }
+  }
+  __syncthreads();
+  const int cv = C >> 3;
+  const int R = blockDim.x / cv;
+  const int cq = threadIdx.x % cv, pr = threadIdx.x / cv;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cq * 8 + j;
+    const int gi = c / cpg;
+    a[j] = st[2 * gi + 1] * __ldg(gamma + c);
+    b[j] = __ldg(beta + c) - st[2 * gi] * a[j];
+  }
+  const int p0 = blockIdx.x * slab;
+  const int p1 = min(HW, p0 + slab);
+  const __half* xn = x + (long long)n * HW * C + cq * 8;
+  __half* yn = y + (long long)n * HW * C + cq * 8;
+  for (int pb = p0 + pr; pb < p1; pb += 4 * R) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = pb + k * R;
+      if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * C));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = pb + k * R;
+      if (p < p1) {
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_h2(w[t]);
+          float v0 = fmaf(f.x, a[2 * t], b[2 * t]), v1 = fmaf(f.y, a[2 * t + 1], b[2 * t + 1]);
+          if (silu) v0 = fast_silu(v0), v1 = fast_silu(v1);
+          o[t] = pack_h2(v0, v1);
+        }
+        *reinterpret_cast<uint4*>(yn + (long long)p * C) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
 // Single-launch GroupNorm: the CTAs of one sample (gridDim.x = cluster size, 8 or 16) form a thread-block cluster.  Each CTA reduces its pixel
 // slab (fp32 sums, fixed order), the per-group partials are exchanged through distributed shared memory and folded in
 // rank order (bitwise reproducible and independent of the batch size), then the CTA normalises the slab it has just

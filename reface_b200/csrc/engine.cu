@@ -560,9 +560,10 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
   const int HW = x.h * x.w, C = x.c, cv = C / 8;
   RFB_CHECK(cv <= 512, "GroupNorm: too many channels");
   int R = std::max(1, 512 / cv);
-  // One cluster launch for the UNet's maps; the three-kernel path (whole-grid statistics, finalize, whole-grid apply) for
-  // maps of >= gn_fused_max_elems elements per sample (the VAE's 256^2 / 512^2 levels), where 16 CTAs per sample are too
-  // few to stream from HBM (profiles/r01s2_micro_bench.txt).  The choice depends on the per-sample shape only.
+  // One cluster launch for small and medium maps; the whole-grid two-launch path (statistics, apply with the finalize
+  // folded in) for maps of >= gn_fused_max_elems elements per sample (64^2 x 640 and up, the VAE's 256^2 / 512^2 levels),
+  // where 16 CTAs per sample are too few to stream from HBM (profiles/r01s2_micro_bench.txt).  The choice depends on the
+  // per-sample shape only, so results stay independent of the batch size.
   if (c.gn_fused && (long long)HW * C < c.gn_fused_max_elems) {
     R = std::max(1, std::min(c.gn_threads, 512) / cv);
     // one launch: a cluster of 16 (or 8) CTAs per sample (statistics exchanged through DSMEM), see elem.cuh
@@ -602,6 +603,29 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
     CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const __half*)x.p, gamma, beta, y.p, HW, C, 32, eps,
                                silu ? 1 : 0));
     LAUNCH_CHECK(c);
+    return y;
+  }
+  if (c.gn_split2) {
+    // two launches: whole-grid statistics (8 loads in flight per thread) + apply with the finalize folded in
+    R = std::max(1, 512 / cv);
+    const int slab = std::max(R, (HW + 31) / 32);  // <= 32 slabs per sample, a function of the shape only
+    const int nslab = (HW + slab - 1) / slab;
+    float* partial = c.alloc_t<float>((size_t)x.n * nslab * 32 * 2);
+    static bool attr2 = false;
+    if (!attr2) {
+      CUDA_OK(cudaFuncSetAttribute(gn_stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr2 = true;
+    }
+    dim3 g1((unsigned)nslab, (unsigned)x.n);
+    gn_stats2_kernel<<<g1, cv * R, (size_t)(R + 1) * 2 * C * sizeof(float), c.stream>>>(x.p, partial, HW, C, slab, 32);
+    LAUNCH_CHECK(c);
+    const int want2 = std::max(1, (8 * c.num_sms) / std::max(1, x.n));
+    const int slab2 = std::max(R, (HW + want2 - 1) / want2);
+    dim3 g2((unsigned)((HW + slab2 - 1) / slab2), (unsigned)x.n);
+    RFB_CHECK(cv * R >= 256, "GroupNorm: block too small for the in-kernel finalize");
+    gn_apply2_kernel<<<g2, cv * R, 0, c.stream>>>(x.p, partial, nslab, gamma, beta, y.p, HW, C, 32, eps, silu ? 1 : 0, slab2);
+    LAUNCH_CHECK(c);
+    c.release(mk);
     return y;
   }
   // the slab partition depends on the tensor shape only (never on the batch size): bitwise batch-independence

@@ -91,19 +91,21 @@ def test_conv_generic_im2col(engine, N, C, H, O, k, s, pad, tma_s2):
 @pytest.mark.parametrize("N,C,H,eps,silu", [(2, 320, 16, 1e-5, True), (2, 960, 8, 1e-5, True), (1, 128, 64, 1e-6, True),
                                             (3, 1280, 4, 1e-6, False), (2, 2560, 8, 1e-5, True), (2, 1920, 2, 1e-5, True),
                                             (1, 512, 32, 1e-6, False), (5, 640, 32, 1e-5, True)])
-@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("fused", [1, 0, 2])
 def test_groupnorm(engine, N, C, H, eps, silu, fused):
     """fused=1 (default): one launch, a cluster of 8 CTAs per sample exchanging statistics through DSMEM;
     fused=0: the three-kernel stats / finalize / apply path."""
     x = h(rn(N, C, H, H, seed=1) * 2 + 0.5)
     gam, bet = 1 + 0.1 * rn(C, seed=2), 0.1 * rn(C, seed=3)
-    engine.set_option("gn_fused", fused)
+    engine.set_option("gn_fused", 1 if fused == 1 else 0)   # 2: the two-launch whole-grid path (stats2 / apply2)
+    engine.set_option("gn_split2", 1 if fused == 2 else 0)
     engine.set_option("gn_fused_max_elems", 1 << 40)      # exercise the cluster kernel at every test shape
     try:
         y = engine.op_groupnorm(x, gam, bet, eps, silu)
     finally:
         engine.set_option("gn_fused", 1)
-        engine.set_option("gn_fused_max_elems", 4 << 20)
+        engine.set_option("gn_split2", 1)
+        engine.set_option("gn_fused_max_elems", 2621440)
     ref = F.group_norm(x, 32, gam, bet, eps)
     ref = F.silu(ref) if silu else ref
     assert float((y - ref).abs().max()) < 6e-3
