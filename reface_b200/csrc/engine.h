@@ -88,7 +88,7 @@ struct Ctx {
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)
   int gn_fused = 1;  // single-launch cluster GroupNorm (0: stats / finalize / apply kernels)
   int gn_split2 = 1;  // whole-grid GroupNorm path: 0 = stats / finalize / apply (round 1), 1 = stats2 / apply2 (two launches)
-  long long gn_fused_max_elems = 2621440;  // = 64*64*640:  // per-sample H*W*C above which GroupNorm takes the three-kernel path
+  long long gn_fused_max_elems = 2621440;  // = 64*64*640: per-sample H*W*C from which GroupNorm takes the whole-grid path
   int gn_cluster = 16, gn_threads = 512;  // fused GroupNorm: CTAs per sample (cluster size), threads per CTA
   int ln_vec = 1;    // 16-byte-vectorised LayerNorm (0: one warp per row, 4-byte loads)
   int gemm_epi3_max_nk = 10;  // K <= 640: 3 epilogue warps per TMEM lane quadrant
