@@ -661,6 +661,39 @@ __global__ void softmax_rows_kernel(__half* __restrict__ x, long long rows, int 
     p[i] = (i < L) ? __float2half_rn(__expf(__half2float(p[i]) - mx) * inv) : __float2half_rn(0.f);
 }
 
+// Same contract, one WARP per row with the row held in registers (ld <= 32 * EPL): one read, one exp per element, shuffle
+// reductions instead of three block-wide barriers.  Used for the short rows of the materialised path (L = 64 / 256 at the
+// UNet's 8x8 / 16x16 levels, L = 257 in CLIP).
+template <int EPL>
+__global__ void softmax_rows_warp_kernel(__half* __restrict__ x, long long rows, int L, int ld) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  __half* p = x + row * ld;
+  float v[EPL];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = i < L ? __half2float(p[i]) : -INFINITY;
+    mx = fmaxf(mx, v[k]);
+  }
+  mx = warp_max(mx);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = i < L ? __expf(v[k] - mx) : 0.f;
+    s += v[k];
+  }
+  const float inv = 1.0f / warp_sum(s);
+#pragma unroll
+  for (int k = 0; k < EPL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < ld) p[i] = __float2half_rn(v[k] * inv);  // columns [L, ld) become 0
+  }
+}
+
 // V section of a fused [N, L, ldq] projection -> Vt [N*heads, d, Lp] (keys contiguous), zero padded to Lp
 __global__ void transpose_v_kernel(const __half* __restrict__ v, __half* __restrict__ vt, int N, int L, int heads, int d,
                                    long long ldq, int Lp, int hs) {

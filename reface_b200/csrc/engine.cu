@@ -522,8 +522,16 @@ void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads
     dim3 grid((unsigned)((L + 127) / 128), (unsigned)((L + g.BN - 1) / g.BN), (unsigned)Z);
     launch_gemm(c, tmA, tmB, g, grid, (double)d);
   }
-  softmax_rows_kernel<<<(unsigned)((long long)Z * L), L >= 1024 ? 256 : 128, 0, c.stream>>>(S, (long long)Z * L, L, Lp);
-  LAUNCH_CHECK(c);
+  {
+    const long long rows = (long long)Z * L;
+    if (Lp <= 256)
+      softmax_rows_warp_kernel<8><<<(unsigned)((rows + 7) / 8), 256, 0, c.stream>>>(S, rows, L, Lp);
+    else if (Lp <= 1024)
+      softmax_rows_warp_kernel<32><<<(unsigned)((rows + 7) / 8), 256, 0, c.stream>>>(S, rows, L, Lp);
+    else
+      softmax_rows_kernel<<<(unsigned)rows, 256, 0, c.stream>>>(S, rows, L, Lp);
+    LAUNCH_CHECK(c);
+  }
   {
     dim3 grid((unsigned)((Lp + 31) / 32), (unsigned)((d + 31) / 32), (unsigned)Z), block(32, 8);
     transpose_v_kernel<<<grid, block, 0, c.stream>>>(qkv + v_off, Vt, N, L, heads, d, ldq, Lp, hs);
