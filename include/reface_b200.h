@@ -109,22 +109,33 @@ int rfb_inpaint_from_parsing(rfb_ctx* ctx, const float* img, const uint8_t* seg1
 int rfb_paste_back(rfb_ctx* ctx, const float* x01, const uint8_t* orig, const double* coeffs, int B, int h, int w, int up,
                    int H, int W, uint8_t* out, void* stream);
 /* get_first_stage_encoding(encode_first_stage(x)) (ddpm.py:1402-1439, 850-857; autoencoder.py:324-328;
- * distributions.py:24-37): img [B,3,H,W] -> z = 0.18215*(mean + std*noise) [B,4,H/8,W/8].
+ * distributions.py:24-37): img [B,3,H,W] -> z = scale_factor*(mean + std*noise) [B,4,H/8,W/8] (scale_factor =
+ * LatentDiffusion.scale_factor, 0.18215 in project_ffhq.yaml:20; 1.0 returns the bare posterior.sample()).
  * noise NULL => mode() (z = scaled mean).  mean/logvar outputs optional (NULL). */
-int rfb_vae_encode(rfb_ctx* ctx, const float* img, const float* noise, int B, int H, int W, float* z, float* mean,
-                   float* logvar, void* stream);
-/* decode_first_stage (ddpm.py:1277-1337; autoencoder.py:330-333): z [B,4,h,w] -> img [B,3,8h,8w]. */
-int rfb_vae_decode(rfb_ctx* ctx, const float* z, int B, int h, int w, float* img, void* stream);
+int rfb_vae_encode(rfb_ctx* ctx, const float* img, const float* noise, int B, int H, int W, double scale_factor, float* z,
+                   float* mean, float* logvar, void* stream);
+/* decode_first_stage (ddpm.py:1277-1337; autoencoder.py:330-333): z [B,4,h,w] -> `1/scale_factor * z` (the Python
+ * double rounded to fp32, ddpm.py:1284) -> post_quant_conv -> Decoder -> img [B,3,8h,8w]; scale_factor 1.0 is
+ * AutoencoderKL.decode itself. */
+int rfb_vae_decode(rfb_ctx* ctx, const float* z, int B, int h, int w, double scale_factor, float* img, void* stream);
 /* FrozenCLIPEmbedder.encode (encoders/modules.py:253-264): img [B,3,224,224] -> [B,1,768]. */
 int rfb_clip_encode(rfb_ctx* ctx, const float* img224, int B, float* out768, void* stream);
 /* IDLoss.extract_feats(x)[0] (ddpm.py:112-124 + model_irse.py:44-69): CLIP-normalised [B,3,224,224] -> [B,512]. */
 int rfb_arcface_embed(rfb_ctx* ctx, const float* img224_clipnorm, int B, float* out512, void* stream);
 /* LatentDiffusion.conditioning_with_feat (ddpm.py:872-1045) for the shipped config:
- * c = (w_clip*(proj_src(clip_src)+proj_tgt(clip_tgt)) + w_id*ID_proj(id) + w_lm*landmark_proj(lm136)) / sum(w).
- * clip_src/clip_tgt [B,768], id_feat [B,512], lm136 [B,136] -> c [B,1,768]. Uses the registered
- * proj_out_source/proj_out_target/ID_proj_out/landmark_proj_out parameters. */
+ * c = (w_clip*(proj_src(clip_src)+proj_tgt(clip_tgt)) + w_id*ID_proj(id) + w_lm*LM) / sum(w).
+ * clip_src/clip_tgt [B,768], id_feat [B,512] -> c [B,1,768].  The landmark term LM is given EITHER as raw dlib points
+ * lm136 [B,136] (projected here by landmark_proj_out, ddpm.py:1096) OR already projected, lm_proj768 [B,768] -- what
+ * the reference passes: conditioning_with_feat(ref, landmarks=model.get_landmarks(x), tar=x)
+ * (scripts/inference_test_bench.py:447-448, ddpm.py:1061-1062).  Exactly one of the two must be non-NULL.  Uses the
+ * registered proj_out_source / proj_out_target / ID_proj_out / landmark_proj_out parameters. */
 int rfb_condition_fuse(rfb_ctx* ctx, const float* clip_src, const float* clip_tgt, const float* id_feat,
-                       const float* lm136, int B, float w_clip, float w_id, float w_lm, float* c_out, void* stream);
+                       const float* lm136, const float* lm_proj768, int B, float w_clip, float w_id, float w_lm,
+                       float* c_out, void* stream);
+/* The device half of LatentDiffusion.get_landmarks (ddpm.py:1068-1099): landmark_proj_out(lm136) [B,136] -> [B,768];
+ * rows of zeros are the reference's no-face branch (ddpm.py:1081-1083).  Detection itself (dlib, CPU) stays with the
+ * caller. */
+int rfb_landmark_project(rfb_ctx* ctx, const float* lm136, int B, float* out768, void* stream);
 /* tar -> un_norm -> CLIP normalise -> bilinear 224 (ddpm.py:907-912): [B,3,H,W] in [-1,1] -> [B,3,224,224]. */
 int rfb_target_clip_input(rfb_ctx* ctx, const float* tar, int B, int H, int W, float* out224, void* stream);
 

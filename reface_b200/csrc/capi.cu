@@ -28,6 +28,26 @@ struct rfb_ctx {
     return -2;                                          \
   }
 
+// A model owns the device buffers its builder packed (Ctx::dmalloc): they are moved from Ctx::owned into the model and
+// freed with it, so rebuilding a model does not leak its previous ~GBs of packed fp16 weights.
+template <class M>
+static void drop_model(Ctx& c, M*& slot) {
+  if (!slot) return;
+  cudaDeviceSynchronize();
+  for (void* p : slot->owned) cudaFree(p);
+  delete slot;
+  slot = nullptr;
+}
+template <class M, class F>
+static void rebuild_model(Ctx& c, M*& slot, F build) {
+  drop_model(c, slot);
+  const size_t o0 = c.owned.size();
+  M* m = build();
+  m->owned.assign(c.owned.begin() + o0, c.owned.end());
+  c.owned.resize(o0);
+  slot = m;
+}
+
 extern "C" {
 
 int rfb_init(int device, size_t arena_bytes, rfb_ctx** out) {
@@ -71,13 +91,14 @@ void rfb_destroy(rfb_ctx* h) {
   cudaSetDevice(c.device);
   cudaDeviceSynchronize();
   for (auto& kv : c.params) cudaFree(kv.second.f32);
+  for (void* p : c.retired) cudaFree(p);
   for (void* p : c.owned) cudaFree(p);
+  drop_model(c, c.unet);
+  drop_model(c, c.vae);
+  drop_model(c, c.clip);
+  drop_model(c, c.arc);
+  drop_model(c, c.parser);
   if (c.arena) cudaFree(c.arena);
-  delete c.unet;
-  delete c.vae;
-  delete c.clip;
-  delete c.arc;
-  delete c.parser;
   delete h;
 }
 
@@ -91,9 +112,17 @@ int rfb_set_param(rfb_ctx* h, const char* name, const float* data, int ndim, con
     p.shape.push_back(shape[i]);
     p.numel *= (size_t)shape[i];
   }
+  // Built models keep raw pointers into the fp32 parameter storage (biases, norm affine vectors, the GEMV weights):
+  // a re-registered key is therefore overwritten IN PLACE when its size is unchanged, and otherwise the old buffer is
+  // retired (kept alive until rfb_destroy) instead of freed.  Packed fp16 copies are refreshed by the next rfb_build_*.
   auto it = c.params.find(name);
+  if (it != c.params.end() && it->second.numel == p.numel && it->second.f32) {
+    CUDA_OK(cudaMemcpy(it->second.f32, data, p.numel * sizeof(float), cudaMemcpyDefault));
+    it->second.shape = p.shape;
+    return 0;
+  }
   if (it != c.params.end()) {
-    cudaFree(it->second.f32);
+    if (it->second.f32) c.retired.push_back(it->second.f32);
     c.params.erase(it);
   }
   CUDA_OK(cudaMalloc((void**)&p.f32, std::max<size_t>(p.numel * sizeof(float), 256)));
@@ -105,38 +134,28 @@ int rfb_has_param(rfb_ctx* h, const char* name) { return (h && h->c.has(name)) ?
 
 int rfb_build_unet(rfb_ctx* h, const char* prefix) {
   API_BEGIN(h)
-  delete c.unet;
-  c.unet = nullptr;
-  c.unet = build_unet(c, prefix, UNetCfg());
+  rebuild_model(c, c.unet, [&] { return build_unet(c, prefix, UNetCfg()); });
   API_END
 }
 int rfb_build_vae(rfb_ctx* h, const char* prefix) {
   API_BEGIN(h)
-  delete c.vae;
-  c.vae = nullptr;
-  c.vae = build_vae(c, prefix);
+  rebuild_model(c, c.vae, [&] { return build_vae(c, prefix); });
   API_END
 }
 int rfb_build_clip(rfb_ctx* h, const char* prefix) {
   API_BEGIN(h)
-  delete c.clip;
-  c.clip = nullptr;
-  c.clip = build_clip(c, prefix);
+  rebuild_model(c, c.clip, [&] { return build_clip(c, prefix); });
   API_END
 }
 int rfb_build_arcface(rfb_ctx* h, const char* prefix) {
   API_BEGIN(h)
-  delete c.arc;
-  c.arc = nullptr;
-  c.arc = build_arcface(c, prefix);
+  rebuild_model(c, c.arc, [&] { return build_arcface(c, prefix); });
   API_END
 }
 
 int rfb_build_face_parser(rfb_ctx* h, const char* prefix) {
   API_BEGIN(h)
-  delete c.parser;
-  c.parser = nullptr;
-  c.parser = build_face_parser(c, prefix);
+  rebuild_model(c, c.parser, [&] { return build_face_parser(c, prefix); });
   API_END
 }
 
@@ -162,7 +181,6 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "gemm_splitk") c.gemm_splitk = (int)value;
   else if (k == "conv_tma_stride2") c.conv_tma_stride2 = (int)value;
   else if (k == "ln_vec") c.ln_vec = (int)value;
-  else if (k == "gemm_persistent") c.gemm_persistent = (int)value;
   else if (k == "gemm_pair") c.gemm_pair = (int)value;
   else if (k == "gemm_kmerge") c.gemm_kmerge = (int)value;
   else if (k == "gemm_debug") c.gemm_debug = (int)value;
@@ -303,19 +321,21 @@ int rfb_paste_back(rfb_ctx* h, const float* x01, const uint8_t* orig, const doub
   paste_back(c, x01, orig, coeffs, B, hh, ww, up, H, W, out);
   API_END
 }
-int rfb_vae_encode(rfb_ctx* h, const float* img, const float* noise, int B, int H, int W, float* z, float* mean,
-                   float* logvar, void* stream) {
+int rfb_vae_encode(rfb_ctx* h, const float* img, const float* noise, int B, int H, int W, double scale_factor, float* z,
+                   float* mean, float* logvar, void* stream) {
   API_BEGIN(h)
   RFB_CHECK(c.vae, "rfb_build_vae has not been called");
   c.stream = (cudaStream_t)stream;
-  vae_encode(c, *c.vae, img, noise, B, H, W, z, mean, logvar);
+  vae_encode(c, *c.vae, img, noise, B, H, W, (float)scale_factor, z, mean, logvar);
   API_END
 }
-int rfb_vae_decode(rfb_ctx* h, const float* z, int B, int hh, int ww, float* img, void* stream) {
+int rfb_vae_decode(rfb_ctx* h, const float* z, int B, int hh, int ww, double scale_factor, float* img, void* stream) {
   API_BEGIN(h)
   RFB_CHECK(c.vae, "rfb_build_vae has not been called");
+  RFB_CHECK(scale_factor != 0.0, "scale_factor must be non-zero");
   c.stream = (cudaStream_t)stream;
-  vae_decode(c, *c.vae, z, B, hh, ww, img);
+  // ddpm.py:1284 `z = 1. / self.scale_factor * z`: the Python double 1/s is rounded to fp32 by the tensor multiply
+  vae_decode(c, *c.vae, z, B, hh, ww, (float)(1.0 / scale_factor), img);
   API_END
 }
 int rfb_clip_encode(rfb_ctx* h, const float* img224, int B, float* out768, void* stream) {
@@ -339,10 +359,19 @@ __global__ void fuse_cond_kernel(const float* a, const float* b, const float* id
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = ((a[i] + b[i]) * wc + id[i] * wi + lm[i] * wl) / (wc + wi + wl);
 }
-int rfb_condition_fuse(rfb_ctx* h, const float* clip_src, const float* clip_tgt, const float* id_feat,
-                       const float* lm136, int B, float w_clip, float w_id, float w_lm, float* c_out, void* stream) {
+int rfb_landmark_project(rfb_ctx* h, const float* lm136, int B, float* out768, void* stream) {
   API_BEGIN(h)
   c.stream = (cudaStream_t)stream;
+  Lin32 pl = lin32(c, "landmark_proj_out.weight", "landmark_proj_out.bias");
+  linear_small(c, lm136, 136, B, pl, out768, 768, 0, 0);
+  API_END
+}
+int rfb_condition_fuse(rfb_ctx* h, const float* clip_src, const float* clip_tgt, const float* id_feat,
+                       const float* lm136, const float* lm_proj768, int B, float w_clip, float w_id, float w_lm,
+                       float* c_out, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  RFB_CHECK((lm136 != nullptr) != (lm_proj768 != nullptr), "pass exactly one of lm136 (raw points) / lm_proj768 (projected)");
   const size_t mk = c.mark();
   float* t = c.alloc_t<float>((size_t)4 * B * 768);
   Lin32 ps = lin32(c, "proj_out_source.weight", "proj_out_source.bias");
@@ -354,10 +383,11 @@ int rfb_condition_fuse(rfb_ctx* h, const float* clip_src, const float* clip_tgt,
     linear_small(c, clip_src + (size_t)r0 * 768, 768, R, ps, t + (size_t)r0 * 768, 768, 0, 0);
     linear_small(c, clip_tgt + (size_t)r0 * 768, 768, R, pt, t + (size_t)(B + r0) * 768, 768, 0, 0);
     linear_small(c, id_feat + (size_t)r0 * 512, 512, R, pi, t + (size_t)(2 * B + r0) * 768, 768, 0, 0);
-    linear_small(c, lm136 + (size_t)r0 * 136, 136, R, pl, t + (size_t)(3 * B + r0) * 768, 768, 0, 0);
+    if (lm136) linear_small(c, lm136 + (size_t)r0 * 136, 136, R, pl, t + (size_t)(3 * B + r0) * 768, 768, 0, 0);
   }
   const int n = B * 768;
-  fuse_cond_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(t, t + n, t + 2 * n, t + 3 * n, c_out, n, w_clip, w_id, w_lm);
+  fuse_cond_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(t, t + n, t + 2 * n, lm136 ? t + 3 * n : lm_proj768, c_out, n, w_clip,
+                                                          w_id, w_lm);
   CUDA_OK(cudaGetLastError());
   c.launches++;
   c.release(mk);

@@ -197,15 +197,7 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   stages = std::min(stages, std::max(1, g.nk));
   g.stages = stages;
   g.tmem_cols = g.BN <= 32 ? 32 : g.BN <= 64 ? 64 : g.BN <= 128 ? 128 : 256;
-  const size_t smem = gemm_smem_bytes(stages, g.BN);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  RFB_CHECK(smem <= 227 * 1024, "GEMM smem over budget");
   RFB_CHECK(g.BN % 16 == 0 && g.BN >= 32 && g.BN <= 256, "BN must be a multiple of 16 in [32,256]");
-  RFB_CHECK(g.BN % 32 == 0 || c.gemm_persistent, "tile widths that are not multiples of 32 need the persistent kernel");
   if (g.zdiv <= 0) g.zdiv = 1;
   if (g.rows_per_vec <= 0) g.rows_per_vec = 1;
   if (g.o32_rpn <= 0) g.o32_rpn = 1;
@@ -220,19 +212,15 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     rec.mode = g.a_mode * 100 + (g.geglu ? 10 : 0) + (g.res ? 1 : 0) + (g.rowvec ? 2 : 0) + (g.out32 ? 4 : 0);
     CUDA_OK(cudaEventRecord(rec.a, c.stream));
   }
-  RFB_CHECK(g.a_mode != A_CONV3 || g.cstride == 1 || (c.gemm_persistent && !c.gemm_pair),
-            "strided implicit-GEMM convolutions need the persistent 1-CTA kernel");
-  const bool pair_ok = c.gemm_pair && c.gemm_persistent && Bplain != nullptr && grid.z == 1 && grid.x >= 2 &&
+  const bool pair_ok = c.gemm_pair && g.cstride <= 1 && Bplain != nullptr && grid.z == 1 && grid.x >= 2 &&
                        (g.a_mode == A_PLAIN || g.a_mode == A_CONV3) && g.b_mode == B_PLAIN && g.nk >= c.gemm_pair_min_nk &&
                        (long long)grid.x * grid.y >= c.num_sms / 2;
   if (pair_ok) {
     // 2-CTA pairs (cta_group::2): each CTA loads its 128 A rows and half of the B tile
-    static bool attr3 = false;
-    if (!attr3) {
+    if (c.first_use("gemm_pair")) {
       CUDA_OK(cudaFuncSetAttribute(gemm_pair_kernel<EPI_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       CUDA_OK(cudaFuncSetAttribute(gemm_pair_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       CUDA_OK(cudaFuncSetAttribute(gemm_pair_kernel<EPI_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr3 = true;
     }
     g.kmerge = (c.gemm_kmerge >= 2 && g.nk >= 4) ? 2 : 1;
     const int sb2 = g.kmerge * (GEMM_A_STAGE_BYTES + (g.BN / 2) * 128);
@@ -269,17 +257,15 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
       CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI_FAST>, tmA, tmB2, g, m_pairs, n_tiles, total_pairs));
     else
       CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<EPI_GENERIC>, tmA, tmB2, g, m_pairs, n_tiles, total_pairs));
-  } else if (c.gemm_persistent) {
+  } else {
     // persistent, double-buffered-accumulator kernel: one CTA per SM, deep smem ring
-    static bool attr2 = false;
-    if (!attr2) {
+    if (c.first_use("gemm_persist")) {
       const int mx = 227 * 1024;
       CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_FAST, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
       CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GEGLU, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
       CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GENERIC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
       CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_FAST, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
       CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GEGLU, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-      attr2 = true;
     }
     // short-K GEMMs are epilogue-bound: 3 epilogue warps per lane quadrant (448 threads) instead of 2
     const int np = (g.nk <= c.gemm_epi3_max_nk && g.BN > 64 && g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f) ? 3 : 2;
@@ -301,9 +287,6 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     } else {
       gemm_persist_kernel<EPI_GENERIC, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
     }
-  } else {
-    RFB_CHECK(!g.relu_after_res, "relu_after_res needs the persistent kernel");
-    gemm_tc_kernel<<<grid, GEMM_THREADS, smem, c.stream>>>(tmA, tmB, g);
   }
   LAUNCH_CHECK(c);
   if (c.profile) {
@@ -327,7 +310,7 @@ static void fill_epi(GemmArgs& g, const Epi& e, __half* out, long long ldo) {
 // epilogue.  ks depends on the tile count, i.e. on the batch: unlike everything else in the path a split-K GEMM is
 // reproducible for a given batch size but not bitwise identical ACROSS batch sizes -> opt-in (option gemm_splitk).
 static int pick_ksplit(Ctx& c, long long M, int N, int nk, const Epi& e, long long ldo) {
-  if (!c.gemm_splitk || !c.gemm_persistent || c.force_bn || nk < 64 || e.geglu || e.act || e.out32 || e.alpha != 1.0f ||
+  if (!c.gemm_splitk || c.force_bn || nk < 64 || e.geglu || e.act || e.out32 || e.alpha != 1.0f ||
       e.relu_after_res || (N & 7) || (ldo & 7) || (e.res && (e.ldr & 3)))
     return 1;
   const long long tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + 255) / 256);
@@ -575,9 +558,8 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
   if (c.gn_fused && (long long)HW * C < c.gn_fused_max_elems) {
     R = std::max(1, std::min(c.gn_threads, 512) / cv);
     // one launch: a cluster of 16 (or 8) CTAs per sample (statistics exchanged through DSMEM), see elem.cuh
-    static bool attr = false;
-    static int max_cluster = 16;
-    if (!attr) {
+    int& max_cluster = c.gn_max_cluster;
+    if (c.first_use("gn_fused")) {
       CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       // 16-CTA clusters are a non-portable size: fall back to the portable 8 where the device (e.g. a partitioned
@@ -594,7 +576,6 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
         cudaGetLastError();
         max_cluster = 8;
       }
-      attr = true;
     }
     const int GC = std::min(c.gn_cluster, max_cluster);
     cudaLaunchConfig_t cfg;
@@ -619,11 +600,8 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
     const int slab = std::max(R, (HW + 31) / 32);  // <= 32 slabs per sample, a function of the shape only
     const int nslab = (HW + slab - 1) / slab;
     float* partial = c.alloc_t<float>((size_t)x.n * nslab * 32 * 2);
-    static bool attr2 = false;
-    if (!attr2) {
+    if (c.first_use("gn_stats2"))
       CUDA_OK(cudaFuncSetAttribute(gn_stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr2 = true;
-    }
     dim3 g1((unsigned)nslab, (unsigned)x.n);
     gn_stats2_kernel<<<g1, cv * R, (size_t)(R + 1) * 2 * C * sizeof(float), c.stream>>>(x.p, partial, HW, C, slab, 32);
     LAUNCH_CHECK(c);
@@ -696,11 +674,8 @@ void cross_attn_small(Ctx& c, const __half* q, const float* kc, const float* vc,
   RFB_CHECK(T >= 1 && T <= 16, "cross-attention: context length must be in [1, 16]");
   RFB_CHECK(C % heads == 0 && (C / heads) % 8 == 0, "cross-attention: head dim must be a multiple of 8");
   const size_t smem = (size_t)2 * T * C * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  if (c.first_use("cross_attn_small"))
     CUDA_OK(cudaFuncSetAttribute(cross_attn_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
   RFB_CHECK(smem <= 200 * 1024, "cross-attention: context does not fit shared memory");
   dim3 grid((unsigned)((L * heads + 255) / 256), (unsigned)N);
   cross_attn_small_kernel<16><<<grid, 256, smem, c.stream>>>(q, kc, vc, out, L, T, C, heads,

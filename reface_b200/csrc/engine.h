@@ -68,14 +68,15 @@ struct Ctx {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   std::unordered_map<std::string, Param> params;
-  std::vector<void*> owned;  // packed weights etc. (cudaMalloc'd)
+  std::vector<void*> owned;  // packed weights etc. (cudaMalloc'd); moved into the model that packed them (capi.cu)
+  std::vector<void*> retired;  // fp32 buffers of re-registered parameters whose size changed (freed at destroy)
   char* arena = nullptr;
   size_t arena_cap = 0, arena_off = 0, arena_peak = 0;
   std::string err;
   void* encode_fn = nullptr;  // cuTensorMapEncodeTiled
   long long launches = 0;     // kernels launched by this library (reported by bench)
   int gemm_smem_budget = 110 * 1024;  // per-CTA smem target (2 CTAs/SM)
-  int force_bn = 0, force_stages = 0, attn_flash = 4, gemm_persistent = 1, gemm_kmerge = 1;
+  int force_bn = 0, force_stages = 0, attn_flash = 4, gemm_kmerge = 1;
   // 2-CTA (cta_group::2) kernel: correct and faster on isolated long-K GEMMs (1180 vs 1114 TFLOP/s) but measured
   // ~4 % slower over the whole UNet step than 1-CTA tiles (profiles/r01_gemm_sweep_v2.txt) -> opt-in
   int gemm_pair = 0;
@@ -105,6 +106,11 @@ struct Ctx {
   ArcFace* arc = nullptr;
   FaceParser* parser = nullptr;
 
+  // Kernel attributes (dynamic smem limit, non-portable cluster size) are PER-DEVICE state: every context sets them
+  // once for its own device (a process-wide `static bool` would leave a second Engine(device=1) without them).
+  std::unordered_map<std::string, int> once_flags;
+  bool first_use(const char* key) { return once_flags.emplace(key, 1).second; }
+  int gn_max_cluster = 16;
   void* alloc(size_t bytes);  // arena bump allocation (256 B aligned)
   size_t mark() const { return arena_off; }
   void release(size_t m) { arena_off = m; }

@@ -35,6 +35,7 @@ struct UOp {
   ConvW conv;
 };
 struct UNet {
+  std::vector<void*> owned;  // device buffers packed by the builder (freed with the model)
   UNetCfg cfg;
   std::string pfx;
   std::vector<std::vector<UOp>> inp, out;
@@ -82,6 +83,7 @@ struct VAttnW {
   float* qkv_bias = nullptr;
 };
 struct VAE {
+  std::vector<void*> owned;  // device buffers packed by the builder (freed with the model)
   std::string pfx;
   int ch = 128, z = 4;
   std::vector<int> mult = {1, 2, 4, 4};
@@ -102,9 +104,10 @@ struct VAE {
   const float *d_ng = nullptr, *d_nb = nullptr;
 };
 VAE* build_vae(Ctx& c, const std::string& pfx);
-void vae_encode(Ctx& c, VAE& v, const float* img, const float* noise, int B, int H, int W, float* z, float* mean,
-                float* logvar);
-void vae_decode(Ctx& c, VAE& v, const float* z, int B, int h, int w, float* img);
+// scale: LatentDiffusion.scale_factor (z = scale * sample; 1.0 gives the bare posterior sample); inv_scale: fp32(1/scale)
+void vae_encode(Ctx& c, VAE& v, const float* img, const float* noise, int B, int H, int W, float scale, float* z,
+                float* mean, float* logvar);
+void vae_decode(Ctx& c, VAE& v, const float* z, int B, int h, int w, float inv_scale, float* img);
 
 // ---- conditioning encoders
 struct ClipLayerW {
@@ -117,6 +120,7 @@ struct MapperLayerW {
   Lin32 qkv, proj, fc, fc2;
 };
 struct ClipVision {
+  std::vector<void*> owned;  // device buffers packed by the builder (freed with the model)
   std::string pfx;
   int width = 1024, heads = 16, patch = 14, image = 224, ntok = 257, layers = 24, proj = 768;
   LinW patch_w;
@@ -139,6 +143,7 @@ struct ArcUnitW {
   Lin32 se1, se2;
 };
 struct ArcFace {
+  std::vector<void*> owned;  // device buffers packed by the builder (freed with the model)
   std::string pfx;
   ConvW stem;
   float* stem_bias;
@@ -164,6 +169,7 @@ struct ParseBlock {  // resnet.py BasicBlock
   int stride = 1;
 };
 struct FaceParser {
+  std::vector<void*> owned;  // device buffers packed by the builder (freed with the model)
   std::string pfx;
   ParseCBR stem, arm32, arm16, head32, head16, ffm_blk, out_cbr;
   std::vector<ParseBlock> blocks;

@@ -8,13 +8,11 @@
 
 namespace rfb {
 
-static constexpr float kScaleFactor = 0.18215f;
-
 // raw encoder moments h [M,8] fp32 -> quant_conv (1x1, 8->8) -> mean/logvar(clamped) -> z = s*(mean + std*noise)
 __global__ void vae_quant_sample_kernel(const float* __restrict__ h, const float* __restrict__ Wq,
                                         const float* __restrict__ bq, const float* __restrict__ noise,
                                         float* __restrict__ z, float* __restrict__ mean, float* __restrict__ logvar, int B,
-                                        int HW) {
+                                        int HW, float scale) {
   const long long total = (long long)B * HW;
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
     float in[8], o[8];
@@ -35,20 +33,21 @@ __global__ void vae_quant_sample_kernel(const float* __restrict__ h, const float
       const float lv = fminf(fmaxf(o[4 + ch], -30.0f), 20.0f);
       if (mean) mean[idx] = mu;
       if (logvar) logvar[idx] = lv;
-      if (z) z[idx] = kScaleFactor * (mu + expf(0.5f * lv) * (noise ? noise[idx] : 0.0f));
+      if (z) z[idx] = scale * (mu + expf(0.5f * lv) * (noise ? noise[idx] : 0.0f));
     }
   }
 }
 
 // z NCHW fp32 (first 4 channels) -> (1/scale) -> post_quant_conv (1x1, 4->4) -> NHWC fp16 [B,h,w,4]
 __global__ void vae_post_quant_kernel(const float* __restrict__ z, const float* __restrict__ Wp,
-                                      const float* __restrict__ bp, __half* __restrict__ out, int B, int HW, int zc) {
+                                      const float* __restrict__ bp, __half* __restrict__ out, int B, int HW, int zc,
+                                      float inv_scale) {
   const long long total = (long long)B * HW;
   for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(m / HW), px = (int)(m % HW);
     float in[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) in[j] = (1.0f / kScaleFactor) * z[((long long)b * zc + j) * HW + px];
+    for (int j = 0; j < 4; ++j) in[j] = inv_scale * z[((long long)b * zc + j) * HW + px];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float a = bp[i];
@@ -146,8 +145,8 @@ static Tens run_vattn(Ctx& c, const VAttnW& a, const Tens& x) {  // model.py:178
   return linear_t(c, o, a.proj, e);
 }
 
-void vae_encode(Ctx& c, VAE& v, const float* img, const float* noise, int B, int H, int W, float* z, float* mean,
-                float* logvar) {
+void vae_encode(Ctx& c, VAE& v, const float* img, const float* noise, int B, int H, int W, float scale, float* z,
+                float* mean, float* logvar) {
   const size_t mk = c.mark();
   Tens h = from_nchw_f32(c, img, B, 3, H, W, 3);
   h = conv3x3_t(c, h, v.e_in, Epi());
@@ -166,17 +165,17 @@ void vae_encode(Ctx& c, VAE& v, const float* img, const float* noise, int B, int
   e.out32 = raw, e.o32_sn = 8, e.o32_sp = 0, e.o32_sc = 1, e.o32_rpn = 1;
   conv3x3_t(c, h, v.e_out, e);
   vae_quant_sample_kernel<<<grid_for(M), 256, 0, c.stream>>>(raw, v.quant_w, v.quant_b, noise, z, mean, logvar, B,
-                                                           h.h * h.w);
+                                                           h.h * h.w, scale);
   CUDA_OK(cudaGetLastError());
   c.launches++;
   c.release(mk);
 }
 
-void vae_decode(Ctx& c, VAE& v, const float* z, int B, int hh, int ww, float* img) {
+void vae_decode(Ctx& c, VAE& v, const float* z, int B, int hh, int ww, float inv_scale, float* img) {
   const size_t mk = c.mark();
   Tens h = c.new_tens(B, hh, ww, 4);
   vae_post_quant_kernel<<<grid_for((long long)B * hh * ww), 256, 0, c.stream>>>(z, v.pquant_w, v.pquant_b, h.p, B,
-                                                                               hh * ww, 4);
+                                                                               hh * ww, 4, inv_scale);
   CUDA_OK(cudaGetLastError());
   c.launches++;
   h = conv3x3_t(c, h, v.d_in, Epi());

@@ -15,6 +15,8 @@ Only tensors cross the boundary (PyTorch CUDA tensors in/out); nothing here comp
 from __future__ import annotations
 
 import contextlib
+import sys
+import warnings
 
 import numpy as np
 import torch
@@ -30,37 +32,49 @@ def get_engine(device: int = 0, arena_bytes: int = 0) -> Engine:
     return _ENGINES[device]
 
 
-class _Module:
-    """Minimal nn.Module-like shell (state-dict loading, eval/cuda no-ops) around engine weights."""
-    prefix = ""
+class _Module(torch.nn.Module):
+    """nn.Module shell around engine weights.  It holds no torch parameters: `load_state_dict` -- its own, or the one of
+    a PARENT module such as the reference's LatentDiffusion (scripts/inference_test_bench.py:98-103), which reaches
+    this class through nn.Module._load_from_state_dict -- registers the tensors with the engine under the reference's
+    canonical key names and packs the network.  eval / cuda / to / half are the inherited nn.Module no-ops."""
+    canonical = ""          # engine-side key prefix, e.g. "model.diffusion_model."
 
     def __init__(self, engine=None, device=0):
-        self.engine = engine or get_engine(device)
-        self.device = self.engine.device
+        super().__init__()
+        self._engine, self._device_index = engine, device
         self._built = False
 
-    def load_state_dict(self, sd, strict=True):
-        self.engine.load_state_dict({self.prefix + k: v for k, v in sd.items()})
-        self._build()
-        self._built = True
-        return [], []
+    @property
+    def engine(self):       # created on first use: constructing the shell (instantiate_from_config) needs no GPU
+        if self._engine is None:
+            self._engine = get_engine(self._device_index)
+        return self._engine
 
-    def eval(self):
-        return self
+    @property
+    def device(self):
+        return self.engine.device
 
-    def cuda(self, *a, **k):
-        return self
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        mine = {self.canonical + k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)}
+        if not mine:
+            if strict:
+                missing_keys.append(prefix + "*")
+            return
+        self.engine.load_state_dict(mine)
+        try:
+            self._build()
+            self._built = True
+        except RuntimeError as e:      # e.g. "missing parameter: ..." from the packer
+            error_msgs.append(f"{type(self).__name__}: {e}")
 
-    def to(self, *a, **k):
-        return self
-
-    def parameters(self):
-        return iter(())
+    def _require_built(self):
+        if not self._built:
+            raise RuntimeError(f"{type(self).__name__}: weights have not been loaded (load_state_dict) yet")
 
 
 class UNetModel(_Module):
     """ldm/modules/diffusionmodules/openaimodel.py:528-907 (constructor args :558-588, forward :860)."""
-    prefix = "model.diffusion_model."
+    canonical = "model.diffusion_model."
 
     def __init__(self, image_size=32, in_channels=9, model_channels=320, out_channels=4, num_res_blocks=2,
                  attention_resolutions=(4, 2, 1), channel_mult=(1, 2, 4, 4), num_heads=8, use_spatial_transformer=True,
@@ -76,15 +90,14 @@ class UNetModel(_Module):
         self.dtype = torch.float32
 
     def _build(self):
-        self.engine.build_unet(self.prefix)
+        self.engine.build_unet(self.canonical)
 
     def forward(self, x, timesteps=None, context=None, y=None, return_features=False, **kwargs):
         assert y is None, "must specify y if and only if the model is class-conditional"   # openaimodel.py:870-872
         if return_features:
             raise NotImplementedError("return_features is a training-time option")
+        self._require_built()
         return self.engine.unet_forward(x, timesteps, context)
-
-    __call__ = forward
 
 
 class _Posterior:
@@ -93,6 +106,7 @@ class _Posterior:
     def __init__(self, engine, img):
         self.engine, self.img = engine, img
         self._moments = None
+        self.deterministic = False
 
     def _m(self):
         if self._moments is None:
@@ -100,68 +114,95 @@ class _Posterior:
             self._moments = (mean, logvar)
         return self._moments
 
-    @property
-    def mean(self):
-        return self._m()[0]
+    mean = property(lambda self: self._m()[0])
+    logvar = property(lambda self: self._m()[1])
+    std = property(lambda self: torch.exp(0.5 * self._m()[1]))
+    var = property(lambda self: torch.exp(self._m()[1]))
 
-    @property
-    def logvar(self):
-        return self._m()[1]
-
-    def sample(self, noise=None):
+    def sample(self, noise=None, scale_factor=1.0):
+        """mean + std * randn (distributions.py:35-37); `scale_factor` folds LatentDiffusion.scale_factor into the same
+        kernel (one fp32 multiply, as ddpm.py:857)."""
         if noise is None:
             b, _, h, w = self.img.shape
             noise = torch.randn(b, 4, h // 8, w // 8, device=self.engine.device)
-        z = self.engine.vae_encode(self.img, noise)
-        return z / 0.18215           # unscaled, as the reference's posterior.sample(); scale_factor applied by the caller
+        return self.engine.vae_encode(self.img, noise, scale_factor=scale_factor)
 
     def mode(self):
         return self.mean
 
 
+_POSTERIOR_CLS = {}
+
+
+def _posterior_cls():
+    """Inside the reference tree the posterior must pass `isinstance(.., DiagonalGaussianDistribution)`
+    (get_first_stage_encoding, ddpm.py:850-857): when the reference package is loaded in this process the returned class
+    also derives from its DiagonalGaussianDistribution; stand-alone it is plain _Posterior."""
+    mod = sys.modules.get("ldm.modules.distributions.distributions")
+    base = getattr(mod, "DiagonalGaussianDistribution", None) if mod is not None else None
+    if base not in _POSTERIOR_CLS:
+        _POSTERIOR_CLS[base] = _Posterior if base is None else type("_PosteriorRef", (_Posterior, base), {})
+    return _POSTERIOR_CLS[base]
+
+
 class AutoencoderKL(_Module):
     """ldm/models/autoencoder.py:285-333: encode(x) -> posterior, decode(z) -> image."""
-    prefix = "first_stage_model."
+    canonical = "first_stage_model."
 
     def __init__(self, ddconfig=None, lossconfig=None, embed_dim=4, engine=None, device=0, **unused):
         super().__init__(engine, device)
         self.embed_dim = embed_dim
 
     def _build(self):
-        self.engine.build_vae(self.prefix)
+        self.engine.build_vae(self.canonical)
 
     def encode(self, x):
-        return _Posterior(self.engine, x)
+        self._require_built()
+        return _posterior_cls()(self.engine, x)
 
     def decode(self, z):
-        return self.engine.vae_decode(z * 0.18215)   # engine entry point takes the scaled latent (ddpm.py:1284)
+        self._require_built()
+        return self.engine.vae_decode(z, scale_factor=1.0)   # the caller has applied 1/scale_factor (ddpm.py:1284)
+
+    def forward(self, input, sample_posterior=True):                      # autoencoder.py:335-342
+        posterior = self.encode(input)
+        z = posterior.sample() if sample_posterior else posterior.mode()
+        return self.decode(z), posterior
 
 
 class FrozenCLIPEmbedder(_Module):
     """ldm/modules/encoders/modules.py:211-264: encode(image[B,3,224,224]) -> [B,1,768]."""
-    prefix = "cond_stage_model."
+    canonical = "cond_stage_model."
 
     def __init__(self, version="openai/clip-vit-large-patch14", engine=None, device=0, **unused):
         super().__init__(engine, device)
 
     def _build(self):
-        self.engine.build_clip(self.prefix)
+        self.engine.build_clip(self.canonical)
 
     def encode(self, image):
+        self._require_built()
         return self.engine.clip_encode(image)
 
-    forward = __call__ = encode
+    def forward(self, image):
+        return self.encode(image)
 
 
 class LatentDiffusion:
     """The slice of ldm/models/diffusion/ddpm.py:LatentDiffusion that the inference scripts touch
-    (scripts/inference_test_bench.py:408-493, ldm/models/diffusion/ddim.py:100,113-119,207,345)."""
+    (scripts/inference_test_bench.py:408-493, ldm/models/diffusion/ddim.py:100,113-119,207,345).
+
+    `landmark_detector`: optional callable(uint8 image [H,W,3]) -> 68x2 landmark array or None (no face).  dlib is
+    outside the boundary: pass e.g. `lambda im: dlib_points(detector, predictor, im)` to reproduce
+    get_landmarks (ddpm.py:1068-1099).  Without one, get_landmarks warns once and takes the reference's no-face branch
+    (zeros(136) -> landmark_proj_out, ddpm.py:1081-1083) for every image."""
 
     def __init__(self, state_dict=None, engine=None, device=0, scale_factor=0.18215, linear_start=0.00085,
-                 linear_end=0.012, timesteps=1000, clip_weight=1.0, ID_weight=10.0, Landmarks_weight=0.05, **unused):
+                 linear_end=0.012, timesteps=1000, clip_weight=1.0, ID_weight=10.0, Landmarks_weight=0.05,
+                 landmark_detector=None, **unused):
         self.engine = engine or get_engine(device)
         self.device = self.engine.device
-        self.scale_factor = scale_factor
+        self.scale_factor = float(scale_factor)
         self.num_timesteps = timesteps
         sch = ddim_schedule(50, 0.0, linear_start, linear_end, timesteps)
         ac = sch["alphas_cumprod"]
@@ -172,8 +213,10 @@ class LatentDiffusion:
         self.clip_weight, self.ID_weight, self.Landmarks_weight = clip_weight, ID_weight, Landmarks_weight
         self.stack_feat = self.land_mark_id_seperate_layers = self.sep_head_att = False
         self.Landmark_cond = True
+        self.Landmark_loss_weight = 0.0
+        self.landmark_detector = landmark_detector
         self.learnable_vector = None
-        self._landmark_bias = None
+        self._warned_no_detector = False
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
@@ -186,14 +229,32 @@ class LatentDiffusion:
         e.build_clip()
         e.build_arcface()
         self.learnable_vector = sd["learnable_vector"].to(self.device, torch.float32)
-        self._landmark_bias = sd["landmark_proj_out.bias"].to(self.device, torch.float32)
         return [], []
 
+    # nn.Module conveniences the inference scripts call (inference_test_bench.py:111,334; inference_swap_video.py)
     def eval(self):
         return self
 
-    def cuda(self):
+    def train(self, mode=True):
         return self
+
+    def cuda(self, *a, **k):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def half(self):
+        return self
+
+    def float(self):
+        return self
+
+    def requires_grad_(self, *a, **k):
+        return self
+
+    def parameters(self):
+        return iter(())
 
     @contextlib.contextmanager
     def ema_scope(self, context=None):       # use_ema: false (project_ffhq.yaml:19) -> no-op (ddpm.py:309-322)
@@ -212,7 +273,7 @@ class LatentDiffusion:
 
     def get_first_stage_encoding(self, posterior, noise=None):             # ddpm.py:850-857
         if isinstance(posterior, _Posterior):
-            return self.scale_factor * posterior.sample(noise)
+            return posterior.sample(noise, scale_factor=self.scale_factor)
         return self.scale_factor * posterior
 
     def q_sample(self, x_start, t, noise=None):                            # ddpm.py:412-415
@@ -221,19 +282,39 @@ class LatentDiffusion:
         return self.engine.q_sample(x_start, t, noise, self.linear_start, self.linear_end, self.num_timesteps)
 
     def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):   # ddpm.py:1277-1337
-        return self.engine.vae_decode(z)
+        return self.engine.vae_decode(z, scale_factor=self.scale_factor)
 
     def get_learned_conditioning(self, c):                                 # ddpm.py:859-870
         return self.engine.clip_encode(c)
 
-    def get_landmarks(self, x):
-        """ddpm.py:1068-1099.  dlib is outside the boundary: without a detector every image
-        takes the reference's no-face branch (zeros(136) -> landmark_proj_out), i.e. the projection bias."""
-        return self._landmark_bias[None].repeat(x.shape[0], 1)
+    def get_landmarks(self, x, landmarks136=None):
+        """ddpm.py:1068-1099: x [B,3,H,W] in [-1,1] -> projected landmarks [B,768].  The uint8 conversion and the
+        68-point layout follow the reference; the detector itself is the caller's (`landmark_detector`), or raw points
+        can be handed in directly as `landmarks136` [B,136]."""
+        b = x.shape[0]
+        if landmarks136 is None:
+            if self.landmark_detector is None:
+                if not self._warned_no_detector:
+                    warnings.warn("reface_b200.LatentDiffusion.get_landmarks: no landmark_detector configured -- every "
+                                  "image takes the reference's no-face branch (zeros(136), ddpm.py:1081-1083); pass "
+                                  "landmark_detector=... or landmarks136=... to condition on detected landmarks",
+                                  RuntimeWarning, stacklevel=2)
+                    self._warned_no_detector = True
+                landmarks136 = torch.zeros(b, 136)
+            else:
+                im = (255.0 * ((x + 1.0) / 2.0).permute(0, 2, 3, 1).cpu().numpy()).astype(np.uint8)   # ddpm.py:1077-1078
+                rows = []
+                for i in range(b):
+                    pts = self.landmark_detector(im[i])
+                    rows.append(np.zeros((1, 136)) if pts is None else np.asarray(pts).reshape(1, 136))
+                landmarks136 = torch.tensor(np.concatenate(rows, 0)).float()
+        return self.engine.landmark_project(landmarks136)                  # ddpm.py:1096
 
     def conditioning_with_feat(self, x, landmarks=None, is_train=False, tar=None, tar_mask=None, landmarks136=None):
         """ddpm.py:872-1045 for the shipped config (Source+Target CLIP, ArcFace ID, landmarks, weight_division).
-        `landmarks136` (raw 68x2 dlib points) may be given instead of the projected `landmarks`."""
+        `landmarks` is what the reference passes: the PROJECTED landmarks [B,768] from get_landmarks
+        (scripts/inference_test_bench.py:447-448); raw 68x2 points may be given as `landmarks136` instead.  With
+        neither, the no-face branch (zeros(136)) is used."""
         e = self.engine
         b = x.shape[0]
         # one CLIP pass over [source ; resized target] (the reference encodes them separately, ddpm.py:884,913: same
@@ -241,12 +322,18 @@ class LatentDiffusion:
         c_both = e.clip_encode(torch.cat([x, e.target_clip_input(tar)], 0))
         c_src, c_tgt = c_both[:b], c_both[b:]
         idf = e.arcface_embed(x)
+        return self._fuse(c_src, c_tgt, idf, landmarks, landmarks136, b)
+
+    def _fuse(self, c_src, c_tgt, idf, landmarks, landmarks136, b):
+        if landmarks is not None and landmarks136 is not None:
+            raise ValueError("pass either projected `landmarks` [B,768] or raw `landmarks136` [B,136], not both")
+        if landmarks is not None:
+            return self.engine.condition_fuse(c_src, c_tgt, idf, None, self.clip_weight, self.ID_weight, self.Landmarks_weight,
+                                              lm_proj=landmarks.reshape(b, 768))
         if landmarks136 is None:
             landmarks136 = torch.zeros(b, 136, device=self.device)
-            # a caller-supplied projected landmark vector other than the no-face bias cannot be inverted
-            if landmarks is not None and not torch.allclose(landmarks.reshape(b, -1).to(self.device), self._landmark_bias[None].expand(b, -1)):
-                raise NotImplementedError("pass raw landmarks via landmarks136=...")
-        return e.condition_fuse(c_src, c_tgt, idf, landmarks136, self.clip_weight, self.ID_weight, self.Landmarks_weight)
+        return self.engine.condition_fuse(c_src, c_tgt, idf, landmarks136, self.clip_weight, self.ID_weight,
+                                          self.Landmarks_weight)
 
     def source_features(self, x):
         """CLIP embedding and ArcFace identity of the source face(s): the part of conditioning_with_feat that depends
@@ -254,7 +341,7 @@ class LatentDiffusion:
         for every batch from the repeated source image, scripts/inference_swap_video.py:627-632; same values)."""
         return self.engine.clip_encode(x), self.engine.arcface_embed(x)
 
-    def conditioning_from_source_features(self, src_feats, tar, landmarks136=None):
+    def conditioning_from_source_features(self, src_feats, tar, landmarks136=None, landmarks=None):
         """conditioning_with_feat (ddpm.py:872-1045) with the source terms taken from source_features()."""
         e = self.engine
         b = tar.shape[0]
@@ -262,9 +349,7 @@ class LatentDiffusion:
         if c_src.shape[0] == 1 and b > 1:
             c_src, idf = c_src.repeat(b, 1, 1), idf.repeat(b, 1)
         c_tgt = e.clip_encode(e.target_clip_input(tar))
-        if landmarks136 is None:
-            landmarks136 = torch.zeros(b, 136, device=self.device)
-        return e.condition_fuse(c_src, c_tgt, idf, landmarks136, self.clip_weight, self.ID_weight, self.Landmarks_weight)
+        return self._fuse(c_src, c_tgt, idf, landmarks, landmarks136, b)
 
 
 class DDIMSampler:
@@ -359,19 +444,24 @@ class PLMSSampler(DDIMSampler):
 
 
 def swap_faces(model: LatentDiffusion, ref_img, tar_img, inpaint_img, mask_lat, landmarks136, x_T, enc_noise, S=50,
-               scale=3.5, log_every_t=100):
-    """The per-batch body of scripts/inference_test_bench.py:438-495 through the drop-in classes."""
+               scale=3.5, log_every_t=100, landmarks=None):
+    """The per-batch body of scripts/inference_test_bench.py:438-495 through the drop-in classes.  `landmarks` (projected,
+    [B,768], as model.get_landmarks returns them) may be given instead of the raw `landmarks136`."""
     b = ref_img.shape[0]
     uc = model.learnable_vector.repeat(b, 1, 1)                                                      # :441
-    c = model.conditioning_with_feat(ref_img, tar=tar_img, landmarks136=landmarks136)                 # :447-448
+    if landmarks is not None:
+        c = model.conditioning_with_feat(ref_img, landmarks=landmarks, tar=tar_img)                   # :447-448
+    else:
+        c = model.conditioning_with_feat(ref_img, tar=tar_img, landmarks136=landmarks136)
     z_inpaint = model.get_first_stage_encoding(model.encode_first_stage(inpaint_img), noise=enc_noise)   # :462-463
     sampler = DDIMSampler(model)
-    samples, _ = sampler.sample(S=S, conditioning=c, batch_size=b, shape=[4, x_T.shape[2], x_T.shape[3]], verbose=False,
-                                unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0, x_T=x_T,
-                                log_every_t=log_every_t,
-                                test_model_kwargs={"inpaint_image": z_inpaint, "inpaint_mask": mask_lat})   # :469-479
+    samples, inter = sampler.sample(S=S, conditioning=c, batch_size=b, shape=[4, x_T.shape[2], x_T.shape[3]],
+                                    verbose=False, unconditional_guidance_scale=scale, unconditional_conditioning=uc,
+                                    eta=0.0, x_T=x_T, log_every_t=log_every_t,
+                                    test_model_kwargs={"inpaint_image": z_inpaint, "inpaint_mask": mask_lat})   # :469-479
     x = model.decode_first_stage(samples)                                                              # :493
-    return dict(c=c, z_inpaint=z_inpaint, samples=samples, image=torch.clamp((x + 1.0) / 2.0, 0.0, 1.0))
+    return dict(c=c, z_inpaint=z_inpaint, samples=samples, intermediates=inter,
+                image=torch.clamp((x + 1.0) / 2.0, 0.0, 1.0))
 
 
 def swap_video(model: LatentDiffusion, ref_img, tar_img, inpaint_img, mask_lat, x_T, enc_noise, landmarks136=None, S=30,

@@ -46,11 +46,12 @@ SIGNATURES = {
     "rfb_face_parse": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "rfb_inpaint_from_parsing": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rfb_paste_back": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
-    "rfb_vae_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "rfb_vae_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "rfb_vae_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, C.c_double, _vp, _vp, _vp, _vp]),
+    "rfb_vae_decode": (_i, [_vp, _vp, _i, _i, _i, C.c_double, _vp, _vp]),
     "rfb_clip_encode": (_i, [_vp, _vp, _i, _vp, _vp]),
     "rfb_arcface_embed": (_i, [_vp, _vp, _i, _vp, _vp]),
-    "rfb_condition_fuse": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _vp, _vp]),
+    "rfb_condition_fuse": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _vp, _vp]),
+    "rfb_landmark_project": (_i, [_vp, _vp, _i, _vp, _vp]),
     "rfb_target_clip_input": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "rfb_op_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _vp]),
     "rfb_op_conv2d": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -314,21 +315,23 @@ class Engine:
                                          H, W, _ptr(out), self._stream()))
         return out
 
-    def vae_encode(self, img, noise=None, return_moments=False):
+    def vae_encode(self, img, noise=None, return_moments=False, scale_factor=0.18215):
+        """z = scale_factor * (mean + std * noise) (ddpm.py:850-857); scale_factor=1.0 is posterior.sample() itself."""
         img, noise = self._in(img), self._in(noise)
         B, _, H, W = img.shape
         z, mean, logvar = self._new(B, 4, H // 8, W // 8), self._new(B, 4, H // 8, W // 8), self._new(B, 4, H // 8, W // 8)
-        self._ck(self.lib.rfb_vae_encode(self.h, _ptr(img), _ptr(noise), B, H, W, _ptr(z), _ptr(mean), _ptr(logvar),
-                                         self._stream()))
+        self._ck(self.lib.rfb_vae_encode(self.h, _ptr(img), _ptr(noise), B, H, W, float(scale_factor), _ptr(z), _ptr(mean),
+                                         _ptr(logvar), self._stream()))
         return (z, mean, logvar) if return_moments else z
 
-    def vae_decode(self, z):
+    def vae_decode(self, z, scale_factor=0.18215):
+        """decode_first_stage (ddpm.py:1277-1337): decoder(1/scale_factor * z); scale_factor=1.0 is AutoencoderKL.decode."""
         z = self._in(z)
         if z.shape[1] != 4:
             z = z[:, :4].contiguous()   # ddpm.py:1334-1335
         B, _, h, w = z.shape
         img = self._new(B, 3, 8 * h, 8 * w)
-        self._ck(self.lib.rfb_vae_decode(self.h, _ptr(z), B, h, w, _ptr(img), self._stream()))
+        self._ck(self.lib.rfb_vae_decode(self.h, _ptr(z), B, h, w, float(scale_factor), _ptr(img), self._stream()))
         return img
 
     def clip_encode(self, img224):
@@ -352,13 +355,24 @@ class Engine:
         self._ck(self.lib.rfb_target_clip_input(self.h, _ptr(tar), B, H, W, _ptr(out), self._stream()))
         return out
 
-    def condition_fuse(self, clip_src, clip_tgt, id_feat, lm136, w_clip=1.0, w_id=10.0, w_lm=0.05):
+    def condition_fuse(self, clip_src, clip_tgt, id_feat, lm136=None, w_clip=1.0, w_id=10.0, w_lm=0.05, lm_proj=None):
+        """The landmark term is either raw points `lm136` [B,136] or the already projected `lm_proj` [B,768] (what
+        the reference's get_landmarks returns, ddpm.py:1096)."""
         clip_src, clip_tgt = self._in(clip_src).reshape(-1, 768), self._in(clip_tgt).reshape(-1, 768)
         id_feat, lm136 = self._in(id_feat), self._in(lm136)
+        lm_proj = None if lm_proj is None else self._in(lm_proj).reshape(-1, 768)
         B = clip_src.shape[0]
         out = self._new(B, 1, 768)
-        self._ck(self.lib.rfb_condition_fuse(self.h, _ptr(clip_src), _ptr(clip_tgt), _ptr(id_feat), _ptr(lm136), B,
-                                             float(w_clip), float(w_id), float(w_lm), _ptr(out), self._stream()))
+        self._ck(self.lib.rfb_condition_fuse(self.h, _ptr(clip_src), _ptr(clip_tgt), _ptr(id_feat), _ptr(lm136),
+                                             _ptr(lm_proj), B, float(w_clip), float(w_id), float(w_lm), _ptr(out),
+                                             self._stream()))
+        return out
+
+    def landmark_project(self, lm136):
+        """landmark_proj_out(lm136): [B,136] raw dlib points (zeros = no face) -> [B,768] (ddpm.py:1081-1096)."""
+        lm136 = self._in(lm136).reshape(-1, 136)
+        out = self._new(lm136.shape[0], 768)
+        self._ck(self.lib.rfb_landmark_project(self.h, _ptr(lm136), lm136.shape[0], _ptr(out), self._stream()))
         return out
 
     # ------------------------------------------------------------------ single ops (tests)

@@ -363,6 +363,203 @@ def golden_paste():
     save("paste_64", x01=x01, orig=orig, coeffs=coeffs, up=up, pasted=ref, pillow=np.array(PIL.__version__))
 
 
+def _ref_unet():
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    m = UNetModel(image_size=32, in_channels=9, out_channels=4, model_channels=320, attention_resolutions=[4, 2, 1],
+                  num_res_blocks=2, channel_mult=[1, 2, 4, 4], num_heads=8, use_spatial_transformer=True,
+                  transformer_depth=1, context_dim=768, use_checkpoint=True, legacy=False,
+                  add_conv_in_front_of_unet=False).eval()
+    sd, sub = sub_sd(O.unet_spec(), O.PFX_UNET)
+    m.load_state_dict(sub, strict=True)
+    return m, sd
+
+
+def _ref_vae():
+    from ldm.models.autoencoder import AutoencoderKL
+    dd = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+              num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    m = AutoencoderKL(ddconfig=dd, lossconfig={"target": "torch.nn.Identity"}, embed_dim=4).eval()
+    sd, sub = sub_sd(O.vae_spec(), O.PFX_VAE)
+    m.load_state_dict(sub, strict=True)
+    return m, sd
+
+
+def _fake_ld(unet, split=False):
+    """The attributes DDIMSampler touches on LatentDiffusion (ddim.py:100,113-119,207,345); apply_model as
+    ddpm.py:1519-1617 + DiffusionWrapper.forward :2244-2246.  split=True runs the batch one sample at a time (every
+    sample is independent; keeps the fp32 score matrices of the L=128 level inside this container's memory)."""
+    ac = O.alphas_cumprod_f32()
+
+    class FakeLD:
+        num_timesteps = 1000
+        betas = torch.tensor(O.make_beta_schedule(), dtype=torch.float32)
+        alphas_cumprod = ac
+        alphas_cumprod_prev = torch.tensor(np.append(1.0, ac.double().numpy()[:-1]), dtype=torch.float32)
+        device = torch.device("cpu")
+
+        def apply_model(self, x, t, c):
+            cc = torch.cat([c], 1)
+            if not split:
+                return unet(x, t, context=cc)
+            return torch.cat([unet(x[i:i + 1], t[i:i + 1], context=cc[i:i + 1]) for i in range(x.shape[0])])
+
+    return FakeLD()
+
+
+def golden_unet_L128():
+    """BASELINE configs[3] resolution: ONE forward of the real reference UNetModel at L=128 (1024x1024 images), N=1
+    (openaimodel.py:860-907).  Input regenerated from the seed by the tests."""
+    print("unet L=128 (reference UNetModel, N=1)")
+    m, sd = _ref_unet()
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(1, 9, 128, 128, generator=g)
+    ctx = torch.randn(1, 1, 768, generator=g)
+    t = torch.tensor([601])
+    ref = m(x, t, context=ctx)
+    ora = O.unet_forward(O.Params(sd, O.PFX_UNET), x, t, ctx)
+    check("unet L=128", ref, ora, 2e-5)
+    save("unet_L128", seed=21, t=t, eps=ref)
+
+
+def golden_ddim_video():
+    """The video settings (inference_video_swap.sh:28-29): --ddim_steps 30 => 31 timesteps (util.py:48-49), scale 3."""
+    print("ddim, video settings: S=30 -> 31 steps, scale 3 (reference DDIMSampler + UNet)")
+    from ldm.models.diffusion.ddim import DDIMSampler
+    DDIMSampler.register_buffer = lambda self, n, a: setattr(self, n, a)
+    m, sd = _ref_unet()
+    g = torch.Generator().manual_seed(22)
+    B, L, S, scale = 1, 16, 30, 3.0
+    x_T = torch.randn(B, 4, L, L, generator=g)
+    z = torch.randn(B, 4, L, L, generator=g)
+    mask = (torch.rand(B, 1, L, L, generator=g) > 0.5).float()
+    c = torch.randn(B, 1, 768, generator=g)
+    uc = torch.randn(B, 1, 768, generator=g)
+    smp = DDIMSampler(_fake_ld(m))
+    ref, inter = smp.sample(S=S, conditioning=c, batch_size=B, shape=[4, L, L], verbose=False,
+                            unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0, x_T=x_T,
+                            log_every_t=1, test_model_kwargs={"inpaint_image": z, "inpaint_mask": mask})
+    assert len(smp.ddim_timesteps) == 31 and len(inter["x_inter"]) == 32
+    ora, _ = O.ddim_sample(O.Params(sd, O.PFX_UNET), x_T, z, mask, c, uc, S, scale)
+    check("ddim video x0", ref, ora, 5e-5)
+    save("ddim_S30_L16", x_T=x_T, z=z, mask=mask, c=c, uc=uc, x0=ref, x_inter=torch.stack(inter["x_inter"][1:]),
+         timesteps=np.asarray(smp.ddim_timesteps))
+
+
+def _img_fixture(img):
+    """A decoded image is too large for a fixture: keep every third pixel and one full-resolution centre crop."""
+    H = img.shape[-1]
+    return dict(img_sub=img[..., ::3, ::3].contiguous(), img_crop=img[..., H // 2 - 48:H // 2 + 48, H // 2 - 48:H // 2 + 48].contiguous())
+
+
+def golden_vae_big():
+    """VAE encode / decode at the BASELINE resolutions (512x512: configs[1,2,4]; 1024x1024: configs[3]) through the real
+    reference AutoencoderKL (autoencoder.py:324-333, model.py:434-459,535-568).  Inputs regenerated from the seed."""
+    m, sd = _ref_vae()
+    P = O.Params(sd, O.PFX_VAE)
+    for H, seed in ((512, 31), (1024, 32)):
+        print(f"vae {H}x{H} (reference AutoencoderKL)")
+        g = torch.Generator().manual_seed(seed)
+        L = H // 8
+        x = torch.rand(1, 3, H, H, generator=g) * 2 - 1
+        noise = torch.randn(1, 4, L, L, generator=g)
+        zdec = torch.randn(1, 4, L, L, generator=g) * 0.18215 * 3
+        post = m.encode(x)
+        ref_z = O.SCALE_FACTOR * (post.mean + post.std * noise)
+        check("vae z", ref_z, O.vae_encode(P, x, noise), 2e-5)
+        ref_img = m.decode((1.0 / O.SCALE_FACTOR) * zdec)
+        check("vae decode", ref_img, O.vae_decode(P, zdec), 2e-5)
+        save(f"vae_{H}", seed=seed, mean=post.mean, logvar=post.logvar, z=ref_z, **_img_fixture(ref_img))
+
+
+def _ref_conditioner(landmarks_raw=None):
+    """The reference's conditioning_with_feat (ddpm.py:872-1045) driven through a namespace that carries exactly the
+    attributes it reads; real FrozenCLIPEmbedder / IDLoss / Linear layers with the oracle's seeded weights."""
+    from src.Face_models.encoders.model_irse import Backbone
+    import ldm.models.diffusion.ddpm as ddpm
+    import torchvision.transforms.functional as TF
+    clip_mod = _build_clip_embedder()
+    csd, csub = sub_sd(O.clip_spec(), O.PFX_CLIP)
+    clip_mod.load_state_dict(csub, strict=False)
+    bb = Backbone(input_size=112, num_layers=50, drop_ratio=0.6, mode="ir_se").eval()
+    asd, asub = sub_sd(O.arcface_spec(), O.PFX_ARC)
+    bb.load_state_dict(asub, strict=False)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "arc.pth")
+        torch.save(bb.state_dict(), path)
+        idl = ddpm.IDLoss(types.SimpleNamespace(other_params=types.SimpleNamespace(arcface_path=path))).eval()
+    fsd = O.init_state_dict(O.fusion_spec(), SEED)
+    lin = lambda n, i, o: _mk_linear(fsd, n, i, o)
+    fake = types.SimpleNamespace(
+        training=False, update_weight=False, clip_weight=1.0, ID_weight=10.0, Landmarks_weight=0.05,
+        Source_CLIP_feat=True, Target_CLIP_feat=True, use_3dmm=False, normalize=False, Landmark_cond=True,
+        weight_division=True, concat_feat=False, stack_feat=False, land_mark_id_seperate_layers=False,
+        sep_head_att=False, device=torch.device("cpu"),
+        get_learned_conditioning=lambda x: clip_mod.encode(x), face_ID_model=idl,
+        proj_out_source=lin("proj_out_source", 768, 768), proj_out_target=lin("proj_out_target", 768, 768),
+        ID_proj_out=lin("ID_proj_out", 512, 768))
+    lm_proj = lin("landmark_proj_out", 136, 768)
+    _resize = TF.resize
+
+    def run(ref_img, tar, lm_raw):
+        # torchvision>=0.17 defaults to antialias=True on tensors; the pinned 0.14 does not (SURVEY 8c-iii)
+        ddpm.TF.resize = lambda img, size, *a, **k: _resize(img, list(size), antialias=False)
+        try:
+            lm = lm_proj(lm_raw)                                           # get_landmarks, ddpm.py:1096
+            return ddpm.LatentDiffusion.conditioning_with_feat(fake, ref_img, lm, tar=tar), lm
+        finally:
+            ddpm.TF.resize = _resize
+
+    full = dict(csd); full.update(asd); full.update(fsd)
+    return run, full
+
+
+def golden_cond_landmarks():
+    """conditioning_with_feat with DETECTED landmarks: raw 68x2 dlib pixel coordinates (values up to the image size)
+    projected by landmark_proj_out (ddpm.py:1085-1096), i.e. the call of scripts/inference_test_bench.py:447-448."""
+    print("conditioning with detected (non-zero) landmarks")
+    run, full = _ref_conditioner()
+    g = torch.Generator().manual_seed(41)
+    ref_img = torch.randn(2, 3, 224, 224, generator=g)
+    tar = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    lm_raw = torch.floor(torch.rand(2, 136, generator=g) * 512)           # dlib part coordinates are integers
+    ref_c, lm = run(ref_img, tar, lm_raw)
+    ora_c = O.conditioning_with_feat(O.Params(full), ref_img, tar, lm_raw)
+    check("conditioning (landmarks)", ref_c, ora_c, 5e-5)
+    save("cond_B2_lm", seed=41, lm_raw=lm_raw, lm_proj=lm, c=ref_c)
+
+
+def golden_full(H=512, S=50, scale=3.5, name="full_512_S50"):
+    """The WHOLE path on BASELINE's own configuration through the real reference modules: conditioning_with_feat
+    (CLIP x2 + ArcFace + fusion) -> AutoencoderKL.encode + sample -> DDIMSampler.sample (S steps, CFG) over the
+    reference UNetModel -> AutoencoderKL.decode -> clamp((x+1)/2)  [scripts/inference_test_bench.py:438-495], B=1,
+    inputs = oracle.synthetic_inputs(1, H, seed=42) (regenerated from the seed by the tests)."""
+    import time
+    print(f"full path {H}x{H}, {S} DDIM steps, CFG {scale}, B=1 through the reference modules")
+    from ldm.models.diffusion.ddim import DDIMSampler
+    DDIMSampler.register_buffer = lambda self, n, a: setattr(self, n, a)
+    inp = O.synthetic_inputs(1, H, seed=42)
+    run, full = _ref_conditioner()
+    c, _ = run(inp["ref_img"], inp["tar_img"], inp["landmarks136"])
+    del run
+    vae, vsd = _ref_vae()
+    post = vae.encode(inp["inpaint_img"])
+    z = O.SCALE_FACTOR * (post.mean + post.std * inp["enc_noise"])          # ddpm.py:850-857 with explicit noise
+    unet, usd = _ref_unet()
+    fsd = O.init_state_dict(O.fusion_spec(), SEED)
+    uc = fsd["learnable_vector"].repeat(1, 1, 1)
+    L = H // 8
+    smp = DDIMSampler(_fake_ld(unet, split=(L > 64)))
+    t0 = time.time()
+    x0, inter = smp.sample(S=S, conditioning=c, batch_size=1, shape=[4, L, L], verbose=False,
+                           unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0, x_T=inp["x_T"],
+                           log_every_t=1, test_model_kwargs={"inpaint_image": z, "inpaint_mask": inp["mask_lat"]})
+    print(f"  sampler: {time.time() - t0:.0f} s")
+    img = torch.clamp((vae.decode((1.0 / O.SCALE_FACTOR) * x0) + 1.0) / 2.0, 0.0, 1.0)
+    xi = torch.stack(inter["x_inter"][1:])                                  # [steps,1,4,L,L], x after every step
+    save(name, seed=42, H=H, S=S, scale=scale, c=c, z_inpaint=z, samples=x0, x_inter_sub=xi[..., ::4, ::4].contiguous(),
+         x_inter_absmax=xi.abs().amax(dim=(1, 2, 3, 4)), **_img_fixture(img))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["schedule", "unet", "vae", "clip", "parse", "paste"]
     if "schedule" in which:
@@ -385,4 +582,18 @@ if __name__ == "__main__":
         golden_parse()
     if "paste" in which:
         golden_paste()
+    # round 2: BASELINE's own configurations (run explicitly: minutes of CPU each)
+    if "unet128" in which:
+        golden_unet_L128()
+    if "video" in which:
+        golden_ddim_video()
+    if "vaebig" in which:
+        golden_vae_big()
+    if "condlm" in which:
+        golden_cond_landmarks()
+    if "full512" in which:
+        golden_full(512, 50, 3.5, "full_512_S50")
+    if "full1024" in which:
+        s1024 = int(os.environ.get("RFB_GOLDEN_S1024", 10))
+        golden_full(1024, s1024, 3.5, f"full_1024_S{s1024}")
     print("OK")

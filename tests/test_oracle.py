@@ -106,3 +106,22 @@ def test_concat_and_update_are_exact(oracle):
     g = torch.Generator().manual_seed(0)
     x, z, m = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g), torch.rand(2, 1, 8, 8, generator=g)
     assert torch.equal(oracle.concat9(x, z, m), torch.cat([x, z, m], 1))
+
+
+def test_video_settings_and_landmark_conditioning_match_reference_golden(oracle, unet_sd, clip_sd, arc_sd, fusion_sd):
+    """Round-2 fixtures from the real reference: the 31-step / scale-3 sampler run of the video settings
+    (first 3 steps re-run here; the generating script compared all 31) and conditioning with detected landmarks."""
+    g = _g("ddim_S30_L16")
+    assert len(oracle.make_ddim_timesteps(30)) == 31 and np.array_equal(g["timesteps"].numpy(), oracle.make_ddim_timesteps(30))
+    _, inter = oracle.ddim_sample(oracle.Params(unet_sd, oracle.PFX_UNET), g["x_T"], g["z"], g["mask"], g["c"], g["uc"],
+                                  30, 3.0, log_every_t=1, n_steps_limit=3)
+    for i in range(3):
+        ref = g["x_inter"][i]
+        assert float((inter["x_inter"][1 + i] - ref).abs().max()) <= 5e-5 * float(ref.abs().max())
+    g = _g("cond_B2_lm")
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    ref_img = torch.randn(2, 3, 224, 224, generator=gen)
+    tar = torch.rand(2, 3, 64, 64, generator=gen) * 2 - 1
+    sd = {**clip_sd, **arc_sd, **fusion_sd}
+    c = oracle.conditioning_with_feat(oracle.Params(sd), ref_img, tar, g["lm_raw"])
+    assert float((c - g["c"]).abs().max()) <= 5e-5 * float(g["c"].abs().max())
