@@ -1,8 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- faces/sec of the REFace DDIM face-swap path (BASELINE.json metric) on N B200s.
 
-    python bench.py --gpus 1 --steps 3 --warmup 3            # our arm (hand-written sm_100a kernels)
+    python bench.py --gpus 1 --steps 3 --warmup 3            # our arm (hand-written sm_100a kernels), configs[1]
     python bench.py --impl reference --steps 2 --warmup 1    # the reference algorithm's CPU port (oracle)
+    python bench.py --workload 1024 --steps 5                # configs[3] shape: 1024x1024, B=2 per GPU (16 on 8 GPUs)
+    python bench.py --workload video --steps 3               # configs[4]: 30 frames per GPU per step (240 on 8 GPUs)
+                                                             # through swap_video: 31 timesteps, scale 3, frames/s
 
 One "step" = one batch of B faces through the whole path: conditioning (CLIP x2 + ArcFace + fusion) ->
 VAE encode -> S-step CFG DDIM over the 9-channel UNet -> VAE decode (config[1]: 512x512, 50 steps, CFG 3.5, B=8
@@ -24,6 +27,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_FACE = {(512, 50): 83.65e12, (256, 5): 2.98e12, (1024, 50): 481.4e12}   # SURVEY 8(d), reference-equivalent
+FLOP_PER_VIDEO_FRAME = 53.2e12                                                    # 512^2, 31 timesteps, one CLIP pass
+# BASELINE.json configs -> (size, ddim steps, scale, faces or frames per GPU per step, arena GB)
+WORKLOADS = {"512": dict(size=512, ddim_steps=50, scale=3.5, batch=8, arena_gb=40, config="configs[1] (configs[2] at 8 GPUs)"),
+             "1024": dict(size=1024, ddim_steps=50, scale=3.5, batch=2, arena_gb=48, config="configs[3] at 8 GPUs"),
+             "video": dict(size=512, ddim_steps=30, scale=3.0, batch=30, arena_gb=100, config="configs[4] at 8 GPUs")}
 
 
 def peaks():
@@ -36,14 +44,20 @@ def peaks():
 
 
 def traffic_from_profiles():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, averaged over the launches of
-    the committed `ncu --set full` capture (profiles/r01s2_traffic.json, written by scripts/ncu_summary.py --traffic:
-    the long-K implicit-GEMM conv 640->640 at 32x32, N=16, of scripts/ncu_ops.py)."""
-    for name in ("r01s2_traffic.json", "r01_traffic.json"):       # newest capture first
-        p = os.path.join(ROOT, "profiles", name)
-        if os.path.exists(p):
-            return json.load(open(p)).get("dram_bytes_per_launch")
-    return None
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (the long-K implicit-GEMM conv
+    640->640 at 32x32, N=16) from the NEWEST committed `ncu --set full` capture: profiles/r<round>[s<session>]_traffic.json,
+    written by scripts/ncu_summary.py --traffic.  Returns (bytes_per_launch, file name)."""
+    import glob
+    import re
+
+    def key(path):
+        m = re.match(r"r(\d+)(?:s(\d+))?_traffic\.json", os.path.basename(path))
+        return (int(m.group(1)), int(m.group(2) or 1)) if m else (-1, -1)
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), key=key)
+    if not files:
+        return None, None
+    return json.load(open(files[-1])).get("dram_bytes_per_launch"), "profiles/" + os.path.basename(files[-1])
 
 
 class ClockSampler(threading.Thread):
@@ -74,23 +88,33 @@ class ClockSampler(threading.Thread):
                     samples=len(self.rows))
 
 
-def cpu_baseline(args, steps, warmup):
-    """The reference algorithm (oracle port, fp32, all host cores): bounded sample of the same workload --
-    UNet CFG calls for ONE face (N=2) at the benchmark resolution + one VAE encode/decode + one conditioning pass;
-    faces/s = 1 / (S * t_unet_call + t_enc + t_dec + t_cond)."""
+def n_timesteps(S):
+    return len(range(0, 1000, 1000 // S))           # make_ddim_timesteps (util.py:46-60): S=30 gives 31
+
+
+def cpu_baseline(args, steps, warmup, full_batch_once=False):
+    """The reference algorithm (oracle port: bit-identical to the reference's modules, tests/golden/make_golden.py;
+    fp32, the host's cores): a bounded sample of the same workload -- UNet CFG calls for ONE face (N=2) at the benchmark
+    resolution + one VAE encode/decode + one conditioning pass; units/s = 1 / (T * t_unet_call + t_enc + t_dec + t_cond),
+    T = number of DDIM timesteps.  full_batch_once: also time ONE UNet CFG call at the arm's per-GPU batch (capped at 8)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import reface_oracle as O
     torch.set_grad_enabled(False)
     ncpu = os.cpu_count() or 1
     cores = min(ncpu, int(os.environ.get("RFB_CPU_THREADS", 32)))   # torch CPU ops stop scaling (and regress) beyond ~32 threads
     torch.set_num_threads(cores)
-    H, S = args.size, args.ddim_steps
+    H, T = args.size, n_timesteps(args.ddim_steps)
     L = H // 8
+    video = args.workload == "video"
     sd = O.init_state_dict(O.full_spec(), 0)
     P = O.Params(sd)
     inp = O.synthetic_inputs(1, H)
     t0 = time.time()
-    c = O.conditioning_with_feat(P, inp["ref_img"], inp["tar_img"], inp["landmarks136"])
+    if video:    # the source CLIP / ArcFace features are computed once per video: per frame only the target CLIP pass
+        O.clip_embed(P.sub(O.PFX_CLIP), O.target_clip_input(inp["tar_img"]))
+        c = torch.randn(1, 1, 768)
+    else:
+        c = O.conditioning_with_feat(P, inp["ref_img"], inp["tar_img"], inp["landmarks136"])
     t_cond = time.time() - t0
     t0 = time.time()
     z = O.vae_encode(P.sub(O.PFX_VAE), inp["inpaint_img"], inp["enc_noise"])
@@ -102,18 +126,30 @@ def cpu_baseline(args, steps, warmup):
     ts = []
     for i in range(warmup + steps):
         t0 = time.time()
-        eps = O.unet_forward(P.sub(O.PFX_UNET), x9, tt, cc)
+        O.unet_forward(P.sub(O.PFX_UNET), x9, tt, cc)
         if i >= warmup:
             ts.append(time.time() - t0)
     t_unet = sum(ts) / len(ts)
     t0 = time.time()
     O.vae_decode(P.sub(O.PFX_VAE), inp["x_T"] * 0.18215)
     t_dec = time.time() - t0
-    fps = 1.0 / (S * t_unet + t_enc + t_dec + t_cond)
-    return dict(value=fps, unit="faces/s", cores=cores, kind="port",
-                sample=f"{steps} timed UNet CFG calls (1 face, N=2, L={L}) + 1 VAE encode + 1 decode + 1 conditioning pass; "
+    fps = 1.0 / (T * t_unet + t_enc + t_dec + t_cond)
+    unit = "frames/s" if video else "faces/s"
+    note = ""
+    if full_batch_once and L <= 64:
+        b = min(args.batch, 8)
+        xb, tb = x9[:1].repeat(2 * b, 1, 1, 1), tt[:1].repeat(2 * b)
+        cb = torch.cat([uc.repeat(b, 1, 1), c.repeat(b, 1, 1)])
+        t0 = time.time()
+        O.unet_forward(P.sub(O.PFX_UNET), xb, tb, cb)
+        t_b = time.time() - t0
+        note = f"; one UNet CFG call at the arm's batch (B={b}, N={2 * b}): {t_b:.2f}s = {t_b / b:.2f}s per face"
+    return dict(value=fps, unit=unit, cores=cores, kind="port",
+                sample=f"{steps} timed UNet CFG calls (1 face, N=2, L={L}) + 1 VAE encode + 1 decode + 1 conditioning pass"
+                       f"{' (target CLIP only: source features are per video)' if video else ''}; "
                        f"t_unet={t_unet:.2f}s t_enc={t_enc:.2f}s t_dec={t_dec:.2f}s t_cond={t_cond:.2f}s; "
-                       f"faces/s = 1/({S}*t_unet+t_enc+t_dec+t_cond)"), t_unet * 1e3
+                       f"{unit} = 1/({T}*t_unet+t_enc+t_dec+t_cond){note}; oracle port of the reference (the reference "
+                       f"tree does not travel to the GPU box), extrapolated from one face"), t_unet * 1e3
 
 
 def main():
@@ -122,12 +158,21 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="faces per GPU per step")
-    ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--ddim-steps", type=int, default=50)
-    ap.add_argument("--scale", type=float, default=3.5)
+    ap.add_argument("--workload", default="512", choices=sorted(WORKLOADS),
+                    help="BASELINE.json config: 512 = configs[1]/[2] (default), 1024 = configs[3], video = configs[4]")
+    ap.add_argument("--batch", type=int, default=None, help="faces (video: frames) per GPU per step")
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--ddim-steps", type=int, default=None)
+    ap.add_argument("--scale", type=float, default=None)
+    ap.add_argument("--chunk", type=int, default=30, help="video: frames per streamed chunk (inference_swap_video.py batches)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    for k in ("batch", "size", "ddim_steps", "scale"):
+        if getattr(args, k) is None:
+            setattr(args, k, wl[k])
+    video = args.workload == "video"
+    unit = "frames/s" if video else "faces/s"
 
     # stdout carries exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
     # version banner there on the first collective), so fd 1 is pointed at stderr for the whole run and the JSON line is
@@ -143,27 +188,36 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    config = dict(workload=f"{args.size}x{args.size}, {args.ddim_steps} DDIM steps, CFG {args.scale}, batch={args.batch}/GPU "
-                           f"(BASELINE configs[1]); full path: CLIPx2+ArcFace+fusion, VAE encode, DDIM, VAE decode",
+    T = n_timesteps(args.ddim_steps)
+    is_named = all(getattr(args, k) == wl[k] for k in ("batch", "size", "ddim_steps", "scale"))
+    what = (f"video swap: {args.batch} frames/GPU/step streamed in chunks of {args.chunk} through swap_video (source CLIP/ArcFace "
+            f"once per video, target CLIP per frame), {args.size}x{args.size}, --ddim_steps {args.ddim_steps} = {T} timesteps, CFG {args.scale}"
+            if video else f"{args.size}x{args.size}, {args.ddim_steps} DDIM steps, CFG {args.scale}, batch={args.batch}/GPU")
+    config = dict(workload=f"{what} ({'BASELINE ' + wl['config'] if is_named else 'custom shape'}); full path: "
+                           f"{'target CLIP' if video else 'CLIPx2+ArcFace'}+fusion, VAE encode, DDIM, VAE decode",
                   global_batch=args.batch * world, parallelism=f"dp{world}",
                   l2_policy="per-step working set (activations + 2.7 GB fp16 weights) exceeds the 126 MB L2")
-    metric = "faces/sec @512x512, 50 DDIM steps, CFG 3.5" if (args.size, args.ddim_steps) == (512, 50) else \
-        f"faces/sec @{args.size}x{args.size}, {args.ddim_steps} DDIM steps, CFG {args.scale}"
+    if video:
+        metric = f"frames/sec @{args.size}x{args.size} video, {args.ddim_steps} DDIM steps ({T} timesteps), CFG {args.scale:g}"
+    elif (args.size, args.ddim_steps, args.scale) == (512, 50, 3.5):
+        metric = "faces/sec @512x512, 50 DDIM steps, CFG 3.5"
+    else:
+        metric = f"faces/sec @{args.size}x{args.size}, {args.ddim_steps} DDIM steps, CFG {args.scale}"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        cb, step_ms = cpu_baseline(args, max(1, args.steps), max(0, args.warmup))
-        line = dict(metric=metric, value=cb["value"], unit="faces/s", n_gpus=args.gpus, steps=args.steps,
+        cb, step_ms = cpu_baseline(args, max(1, args.steps), max(0, args.warmup), full_batch_once=True)
+        line = dict(metric=metric, value=cb["value"], unit=unit, n_gpus=args.gpus, steps=args.steps,
                     warmup=args.warmup, ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32", data="synthetic", config=config, impl="reference", cpu_baseline=cb,
-                    e2e=dict(value=cb["value"], unit="faces/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                    e2e=dict(value=cb["value"], unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         emit(line)
         return
 
     import torch.distributed as dist
     from reface_b200 import synth
-    from reface_b200.ldm_api import LatentDiffusion, swap_faces
+    from reface_b200.ldm_api import LatentDiffusion, swap_faces, swap_video
     from reface_b200.runtime import Engine
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -176,7 +230,10 @@ def main():
         flat = torch.empty(synth.flat_layout()[1], dtype=torch.float32, device=dev)
     from reface_b200 import shard
     shard.broadcast_checkpoint(flat, 0)
-    eng = Engine(local)
+    eng = Engine(local, arena_bytes=int(os.environ.get("RFB_ARENA_GB", wl["arena_gb"])) << 30)
+    for k, v in os.environ.items():          # e.g. RFB_GEMM_PAIR=1 to A/B an engine option from the command line
+        if k.startswith("RFB_") and k not in ("RFB_CPU_THREADS", "RFB_ARENA_GB"):
+            eng.set_option(k[4:].lower(), int(v))
     model = LatentDiffusion(synth.state_dict_from_flat(flat), engine=eng)
     del flat
     torch.cuda.empty_cache()
@@ -186,12 +243,23 @@ def main():
     host_in = synth.synthetic_inputs(B, H, dev, seed=42 + rank, pinned_host=True)
     out_host = torch.empty(B, 3, H, H, dtype=torch.float32).pin_memory()
 
+    if video:
+        # configs[4]: this rank's frames (global frame f = chunk k of `--chunk` frames -> rank k % world,
+        # reface_b200.shard.video_segments); ONE source face for the whole video
+        def run(d):
+            frames = swap_video(model, d["ref_img"][:1], d["tar_img"], d["inpaint_img"], d["mask_lat"], d["x_T"],
+                                d["enc_noise"], landmarks136=d["landmarks136"], S=S, scale=args.scale, chunk=args.chunk)
+            return torch.stack([frames[i] for i in range(B)])
+    else:
+        def run(d):
+            return swap_faces(model, S=S, scale=args.scale, **d)["image"]
+
     def step_resident():
-        return swap_faces(model, S=S, scale=args.scale, **dev_in)["image"]
+        return run(dev_in)
 
     def step_e2e():
         d = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
-        img = swap_faces(model, S=S, scale=args.scale, **d)["image"]
+        img = run(d)
         out_host.copy_(img, non_blocking=True)
         return img
 
@@ -236,16 +304,18 @@ def main():
     achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
     h2d = sum(v.numel() * v.element_size() for v in host_in.values())
     d2h = out_host.numel() * out_host.element_size()
-    fpf = FLOP_PER_FACE.get((H, S))
-    line = dict(metric=metric, value=value, unit="faces/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+    fpf = FLOP_PER_VIDEO_FRAME if (video and (H, S) == (512, 30)) else (None if video else FLOP_PER_FACE.get((H, S)))
+    traffic, traffic_src = traffic_from_profiles()
+    line = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",
                 data="synthetic", config=config,
-                e2e=dict(value=e2e_val, unit="faces/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                e2e=dict(value=e2e_val, unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches),
                 roofline=dict(bound="tensor", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s",
-                              frac=achieved / pk["tflops"], traffic=traffic_from_profiles(),
+                              frac=achieved / pk["tflops"], traffic=traffic, traffic_source=traffic_src,
                               kernel="gemm_persist_kernel (tcgen05 GEMM / implicit-GEMM conv) + attn_flash4/3_kernel (fused attention)",
+                              alg_flop_per_unit=fpf,
                               launches_per_step=int(g_n), kernel_ms_per_step=g_ms, alg_tflop_per_step=g_flops / 1e12,
                               share_of_step=g_ms / (ms / args.steps), peak_source=pk["source"] + ", sustained bf16",
                               whole_path_frac=(value / world) * fpf / (pk["tflops"] * 1e12) if fpf else None),

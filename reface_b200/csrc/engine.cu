@@ -303,21 +303,19 @@ static void fill_epi(GemmArgs& g, const Epi& e, __half* out, long long ldo) {
   g.o32_rpn = e.o32_rpn;
 }
 
-// Split-K for long-K GEMMs with too few output tiles for the machine (the 8x8 level of the UNet at batch 8: M = 1024,
-// N = 1280, K = 11520 is 40 tiles of 128x256; narrower tiles fill the SMs but are L2-bandwidth bound on operand re-reads,
-// profiles/r01s2_gemm_shapes_per_launch.txt).  K is cut into `ks` equal slices (tile x slice units fill one wave), every
-// unit writes its raw fp32 accumulators, and splitk_reduce_kernel folds the slices in a fixed order and applies the
-// epilogue.  ks depends on the tile count, i.e. on the batch: unlike everything else in the path a split-K GEMM is
-// reproducible for a given batch size but not bitwise identical ACROSS batch sizes -> opt-in (option gemm_splitk).
-static int pick_ksplit(Ctx& c, long long M, int N, int nk, const Epi& e, long long ldo) {
-  if (!c.gemm_splitk || c.force_bn || nk < 64 || e.geglu || e.act || e.out32 || e.alpha != 1.0f ||
-      e.relu_after_res || (N & 7) || (ldo & 7) || (e.res && (e.ldr & 3)))
+// Split-K for the long-K 3x3 convolutions of the smallest maps (<= 8x8 output pixels per sample: the deepest UNet level,
+// M = 64 rows per sample).  At batch 8 that is M = 1024, N = 1280, K = 11520-23040: 40 tiles of 128x256 leave most SMs idle,
+// narrower tiles fill them but are L2-bandwidth bound on operand re-reads (555 TFLOP/s,
+// profiles/r01s2_gemm_shapes_per_launch.txt).  K is cut into 3 equal slices of 128x256 tiles; every unit writes its raw fp32
+// accumulators and splitk_reduce_kernel folds the slices in a fixed order and applies the epilogue.  The slice count is
+// a function of the PER-SAMPLE shape only (never of the batch or the SM count), so the K order of every output element's
+// accumulation -- and therefore every bit of the result -- is independent of the batch size, like everything else in
+// the path (test_batch_independence).  Option gemm_splitk = 0 switches it off.
+static int pick_ksplit(Ctx& c, int rows_per_sample, int N, int nk, const Epi& e, long long ldo) {
+  if (!c.gemm_splitk || c.force_bn || nk < 90 || nk % 3 || rows_per_sample > 64 || e.geglu || e.act || e.out32 ||
+      e.alpha != 1.0f || e.relu_after_res || (N & 7) || (ldo & 7) || (e.res && (e.ldr & 3)))
     return 1;
-  const long long tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + 255) / 256);
-  if (tiles * 2 > c.num_sms) return 1;
-  int ks = (int)std::min<long long>(8, c.num_sms / tiles);
-  while (ks > 1 && nk % ks) --ks;
-  return ks;
+  return 3;
 }
 static void splitk_finish(Ctx& c, const float* part, int ks, long long M, int N, const Epi& e, __half* out, long long ldo) {
   splitk_reduce_kernel<<<grid_for(M * (N / 4)), 256, 0, c.stream>>>(part, ks, M, N, e.bias, e.rowvec,
@@ -331,29 +329,6 @@ void gemm(Ctx& c, const __half* A, long long lda, long long M, int K, const __ha
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M = (int)M, g.N = N, g.nk = (K + 63) / 64;
-  const int ks = force_bn ? 1 : pick_ksplit(c, M, N, g.nk, e, ldo);
-  if (ks > 1) {
-    const size_t mk = c.mark();
-    float* part = c.alloc_t<float>((size_t)ks * M * N);
-    g.nk /= ks, g.ksplit = 1, g.BN = 256;
-    g.a_mode = A_PLAIN, g.b_mode = B_PLAIN;
-    Epi raw;
-    raw.out32 = part;
-    fill_epi(g, raw, nullptr, 0);
-    const uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
-    const uint64_t sa[1] = {(uint64_t)lda * 2};
-    const uint32_t ba[2] = {64, 128};
-    const uint64_t db[2] = {(uint64_t)kp, (uint64_t)round_up(N, 32)};
-    const uint64_t sb[1] = {(uint64_t)kp * 2};
-    const uint32_t bb[2] = {64, 256};
-    CUtensorMap tmA = make_tmap(c, A, 2, da, sa, ba);
-    CUtensorMap tmB = make_tmap(c, W, 2, db, sb, bb);
-    dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + 255) / 256), (unsigned)ks);
-    launch_gemm(c, tmA, tmB, g, grid, (double)(kalg > 0 ? kalg : K) / ks);
-    splitk_finish(c, part, ks, M, N, e, out, ldo);
-    c.release(mk);
-    return;
-  }
   const bool vec_epi = e.out32 == nullptr && (N & 7) == 0 && (ldo & 7) == 0 && (!e.res || (e.ldr & 7) == 0);
   g.BN = force_bn ? force_bn : pick_bn(c, M, N, e.geglu != 0, K, vec_epi);
   g.a_mode = A_PLAIN, g.b_mode = B_PLAIN;
@@ -419,7 +394,7 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.M = (int)M, g.N = w.cout, g.cblocks = w.cin / 64, g.nk = 9 * g.cblocks;
-    const int ks = pick_ksplit(c, M, w.cout, g.nk, e, y.c);
+    const int ks = pick_ksplit(c, Ho * Wo, w.cout, g.nk, e, y.c);
     float* part = nullptr;
     size_t mk_split = 0;
     Epi e_full = e;

@@ -85,7 +85,7 @@ struct Ctx {
   int attn_poly = 0;     // attention v3/v4: exponentials per 8 evaluated on the FMA pipe (measured slower: off)
   int cfg_share = 1;     // samplers: compute the context-independent head of the UNet once per CFG pair
   int conv_tma_stride2 = 1;  // stride-2 3x3 convs as implicit GEMM through strided TMA boxes (0: explicit im2col)
-  int gemm_splitk = 0;   // split-K for long-K GEMMs with few output tiles (not bitwise batch-independent: opt-in)
+  int gemm_splitk = 1;   // 3-way split-K for the long-K 3x3 convs of <= 8x8 maps (slice count from the per-sample shape only)
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)
   int gn_fused = 1;  // single-launch cluster GroupNorm (0: stats / finalize / apply kernels)
   int gn_split2 = 1;  // whole-grid GroupNorm path: 0 = stats / finalize / apply (round 1), 1 = stats2 / apply2 (two launches)

@@ -1,0 +1,33 @@
+#!/bin/bash
+# One parametrised entry point for everything that is run on the GPU box through gpurun:
+#   gpurun --timeout 900 -- 'bash scripts/gpu.sh tests bench stages'
+# Tasks (any number, run in order; outputs under gpurun_out/, the tail of each is echoed):
+#   tests[:expr]     pytest -m gpu (optionally -k expr)          smoke          __graft_entry__.smoke()
+#   bench            bench.py default (configs[1])                bench1024 / benchvideo   the other workloads
+#   ref              bench.py --impl reference                    stages         per-stage times of one step
+#   shapes           per-launch tensor-core table of one UNet forward (scripts/gemm_shapes.py)
+#   ab:"o=v,o=v;..." scripts/unet_ab.py A/B of engine options     micro          scripts/micro_bench.py
+#   launches         ncu launch list (gpu__time_duration) of a bench window -> gpurun_out/launches.txt
+#   env: TAG names the output files (default r02), RFB_* are forwarded to the engine as options
+mkdir -p gpurun_out
+TAG=${TAG:-r02}
+for task in "$@"; do
+  name=${task%%:*}; arg=""; [[ "$task" == *:* ]] && arg=${task#*:}
+  echo "=== $task"
+  case $name in
+    tests) timeout 1700 python -m pytest tests -m gpu -q -x --timeout 900 --timeout-method=thread ${arg:+-k "$arg"} -s > gpurun_out/${TAG}_pytest.log 2>&1
+           echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log; grep -E "rel err|drift|decoded pixel|full path|vae (512|1024)|cond \(|passed|failed|Error|error|rc=" gpurun_out/${TAG}_pytest.log | tail -40 ;;
+    smoke) timeout 600 python __graft_entry__.py smoke 2>&1 | tail -2 ;;
+    bench) timeout 900 python bench.py --steps ${STEPS:-5} --warmup 3 $arg > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 3000 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err ;;
+    bench1024) timeout 1200 python bench.py --workload 1024 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_1024.json 2> gpurun_out/${TAG}_bench_1024.err; tail -c 2500 gpurun_out/${TAG}_bench_1024.json; tail -3 gpurun_out/${TAG}_bench_1024.err ;;
+    benchvideo) timeout 1200 python bench.py --workload video --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_video.json 2> gpurun_out/${TAG}_bench_video.err; tail -c 2500 gpurun_out/${TAG}_bench_video.json; tail -3 gpurun_out/${TAG}_bench_video.err ;;
+    ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; tail -c 1500 gpurun_out/${TAG}_bench_ref.json ;;
+    stages) timeout 600 python scripts/stage_times.py > gpurun_out/${TAG}_stages.log 2>&1; tail -1 gpurun_out/${TAG}_stages.log ;;
+    shapes) timeout 600 python scripts/gemm_shapes.py > gpurun_out/${TAG}_shapes${arg:+_$arg}.log 2>&1; head -45 gpurun_out/${TAG}_shapes${arg:+_$arg}.log; tail -1 gpurun_out/${TAG}_shapes${arg:+_$arg}.log ;;
+    ab) IFS=';' read -ra SPECS <<< "$arg"; timeout 900 python scripts/unet_ab.py "${SPECS[@]}" > gpurun_out/${TAG}_ab.log 2>&1; tail -20 gpurun_out/${TAG}_ab.log ;;
+    micro) timeout 900 python scripts/micro_bench.py > gpurun_out/${TAG}_micro.log 2>&1; tail -40 gpurun_out/${TAG}_micro.log ;;
+    launches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip ${SKIP:-30000} -c ${COUNT:-9000} --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
+              python scripts/agg_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches.txt; head -34 gpurun_out/${TAG}_launches.txt; rm -f gpurun_out/${TAG}_launches.csv ;;
+    *) echo "unknown task $name" ;;
+  esac
+done

@@ -169,25 +169,23 @@ def test_concat9_bit_exact_and_ddim_update(engine, oracle):
         assert torch.equal(xp.cpu(), rxp) and torch.equal(p0.cpu(), rp0)   # same fp32 op order: bit exact
 
 
-@pytest.mark.parametrize("kind", ["linear", "conv"])
-def test_split_k(engine, kind):
-    """Option gemm_splitk: long-K GEMMs with few output tiles are cut into K slices (fp32 partial tiles, fixed-order
-    reduction that also applies bias / residual).  Same tolerance as the single-pass kernels."""
-    engine.set_option("gemm_splitk", 1)
-    try:
-        if kind == "linear":
-            M, K, N = 1024, 5120, 1280
-            x, w, b = h(rn(M, K, seed=1)), h(rn(N, K, seed=2) / math.sqrt(K)), rn(N, seed=3)
-            r = h(rn(M, N, seed=4))
-            y = engine.op_linear(x, w, b, residual=r)
-            ref = F.linear(x, w, b) + r
-        else:
-            x, w, b = h(rn(16, 1280, 8, 8, seed=1)), h(rn(1280, 1280, 3, 3, seed=2) / math.sqrt(9 * 1280)), rn(1280, seed=3)
-            y = engine.op_conv2d(x, w, b)
-            ref = F.conv2d(x, w, b, padding=1)
-    finally:
-        engine.set_option("gemm_splitk", 0)
+@pytest.mark.parametrize("batch", [1, 8, 30])
+def test_split_k_is_batch_independent(engine, batch):
+    """The long-K 3x3 convolutions of <= 8x8 maps run as 3 K-slices of 128x256 tiles (fp32 partial tiles, fixed-order
+    reduction that also applies the bias).  The slice count depends on the per-sample shape only: sample 0 of any batch
+    is bitwise the batch-1 result; switching the option off gives the single-pass kernel within the usual tolerance."""
+    x, w, b = h(rn(batch, 1280, 8, 8, seed=1)), h(rn(1280, 1280, 3, 3, seed=2) / math.sqrt(9 * 1280)), rn(1280, seed=3)
+    y = engine.op_conv2d(x, w, b)
+    ref = F.conv2d(x, w, b, padding=1)
     assert rel(y, ref) < 4e-3, rel(y, ref)
+    y1 = engine.op_conv2d(x[:1], w, b)
+    assert torch.equal(y[:1], y1)
+    engine.set_option("gemm_splitk", 0)
+    try:
+        y0 = engine.op_conv2d(x, w, b)
+    finally:
+        engine.set_option("gemm_splitk", 1)
+    assert rel(y0, ref) < 4e-3 and not torch.equal(y0, y)
 
 
 def test_paste_back_bit_exact(engine, oracle):
