@@ -140,12 +140,18 @@ int rfb_landmark_project(rfb_ctx* ctx, const float* lm136, int B, float* out768,
 int rfb_target_clip_input(rfb_ctx* ctx, const float* tar, int B, int H, int W, float* out224, void* stream);
 
 /* ---- single-op entry points (kernel-level parity tests; fp32 in/out, converted internally) ------ */
+/* x2 != NULL: out = [x | x2] w^T with x2 [M2,K2] read at row (m mod M2) -- the channel concatenation of the UNet skip
+ * connections (openaimodel.py:897-899) as one K loop over two TMA descriptors; w is [N, K+K2]. */
 int rfb_op_linear(rfb_ctx* ctx, const float* x, const float* w, const float* bias, const float* residual, long long M,
-                  int K, int N, int act, int geglu, float* out, void* stream);
+                  int K, int N, int act, int geglu, const float* x2, int K2, long long M2, float* out, void* stream);
+/* Upsample.forward (openaimodel.py:109-119): conv3x3(nearest_2x(x)), x [N,C,H,W], w [O,C,3,3] -> [N,O,2H,2W]. */
+int rfb_op_upconv(rfb_ctx* ctx, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int O,
+                  float* out, void* stream);
 int rfb_op_conv2d(rfb_ctx* ctx, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int O,
                   int ksz, int stride, int pad_t, int pad_l, int pad_b, int pad_r, float* out, void* stream);
+/* x2 != NULL: GroupNorm(32) over the channel concatenation [x | x2], x2 [N2,C2,H,W] read at sample (n mod N2). */
 int rfb_op_groupnorm(rfb_ctx* ctx, const float* x, const float* gamma, const float* beta, int N, int C, int H, int W,
-                     float eps, int silu, float* out, void* stream);
+                     float eps, int silu, const float* x2, int C2, int N2, float* out, void* stream);
 int rfb_op_layernorm(rfb_ctx* ctx, const float* x, const float* gamma, const float* beta, long long rows, int C,
                      float eps, float* out, void* stream);
 int rfb_op_attention(rfb_ctx* ctx, const float* qkv, int N, int L, int heads, int d, float scale, float* out,

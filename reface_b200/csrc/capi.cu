@@ -171,7 +171,6 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "gn_fused") c.gn_fused = (int)value;
   else if (k == "cfg_share") c.cfg_share = (int)value;
   else if (k == "gn_cluster") c.gn_cluster = (int)value;
-  else if (k == "gn_split2") c.gn_split2 = (int)value;
   else if (k == "gn_fused_max_elems") c.gn_fused_max_elems = value;
   else if (k == "gn_threads") c.gn_threads = (int)value;
   else if (k == "attn_poly") c.attn_poly = (int)value;
@@ -470,13 +469,13 @@ __global__ void f16_to_f32_kernel(const __half* s, float* d, long long n) {
 }
 
 int rfb_op_linear(rfb_ctx* h, const float* x, const float* w, const float* bias, const float* residual, long long M,
-                  int K, int N, int act, int geglu, float* out, void* stream) {
+                  int K, int N, int act, int geglu, const float* x2, int K2, long long M2, float* out, void* stream) {
   API_BEGIN(h)
   c.stream = (cudaStream_t)stream;
   const size_t mk = c.mark();
   {
     TempParams tp(c);
-    tp.add("__op.w", w, {N, K});
+    tp.add("__op.w", w, {N, K + (x2 ? K2 : 0)});
     if (bias) tp.add("__op.b", bias, {N});
     const int NO = geglu ? N / 2 : N;
     Tens xt = c.new_tens(1, 1, (int)M, K);
@@ -491,16 +490,43 @@ int rfb_op_linear(rfb_ctx* h, const float* x, const float* w, const float* bias,
     }
     LinW lw;
     if (geglu) {
-      RFB_CHECK(bias, "geglu needs a bias");
+      RFB_CHECK(bias && !x2, "geglu needs a bias and a single source");
       int bn = 256;
       while (N % bn) bn /= 2;
       lw = pack_geglu(c, "__op.w", "__op.b", bn);
     } else {
       lw = pack_linear(c, "__op.w", bias ? "__op.b" : "");
     }
-    Tens y = linear_t(c, xt, lw, e);
+    Tens y;
+    if (x2) {  // [x | x2] W^T through two TMA descriptors (x2 has M2 rows, read modulo)
+      Tens x2t = c.new_tens(1, 1, (int)M2, K2);
+      f32_to_f16_kernel<<<grid_for(M2 * K2), 256, 0, c.stream>>>(x2, x2t.p, M2 * K2);
+      y = c.new_tens(1, 1, (int)M, N);
+      e.bias = lw.b;
+      gemm2(c, xt.p, K, K, x2t.p, K2, K2, M2 == M ? 0 : M2, M, lw.w, lw.kp, N, y.p, N, e);
+    } else {
+      y = linear_t(c, xt, lw, e);
+    }
     f16_to_f32_kernel<<<grid_for(M * NO), 256, 0, c.stream>>>(y.p, out, M * NO);
     CUDA_OK(cudaGetLastError());
+  }
+  c.release(mk);
+  API_END
+}
+
+int rfb_op_upconv(rfb_ctx* h, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int O,
+                  float* out, void* stream) {
+  API_BEGIN(h)
+  c.stream = (cudaStream_t)stream;
+  const size_t mk = c.mark();
+  {
+    TempParams tp(c);
+    tp.add("__op.w", w, {O, C, 3, 3});
+    if (bias) tp.add("__op.b", bias, {O});
+    ConvW cw = pack_upconv(c, "__op.w", bias ? "__op.b" : "");
+    Tens xt = from_nchw_f32(c, x, N, C, H, W, C);
+    Tens y = upconv3x3_t(c, xt, cw, Epi());
+    to_nchw_f32(c, y, out);
   }
   c.release(mk);
   API_END
@@ -525,12 +551,14 @@ int rfb_op_conv2d(rfb_ctx* h, const float* x, const float* w, const float* bias,
 }
 
 int rfb_op_groupnorm(rfb_ctx* h, const float* x, const float* gamma, const float* beta, int N, int C, int H, int W,
-                     float eps, int silu, float* out, void* stream) {
+                     float eps, int silu, const float* x2, int C2, int N2, float* out, void* stream) {
   API_BEGIN(h)
   c.stream = (cudaStream_t)stream;
   const size_t mk = c.mark();
   Tens xt = from_nchw_f32(c, x, N, C, H, W, C);
-  Tens y = groupnorm(c, xt, gamma, beta, eps, silu != 0);
+  Tens x2t;
+  if (x2) x2t = from_nchw_f32(c, x2, N2, C2, H, W, C2);   // GroupNorm over the channel concatenation [x | x2]
+  Tens y = groupnorm2(c, xt, x2t, gamma, beta, eps, silu != 0);
   to_nchw_f32(c, y, out);
   c.release(mk);
   API_END

@@ -130,144 +130,31 @@ __global__ void concat_c_kernel(const __half* __restrict__ a, const __half* __re
 }
 
 // ------------------------------------------------------------------ GroupNorm (fp32 statistics)
-// Phase 1: per-(n, channel) sum / sum of squares over a slab of pixels -> atomics into stats[n][C][2].
-// blockDim = (C/8) * R; thread (pr, cq) owns 8 channels and pixel rows pr, pr+R, ...
-__global__ void gn_stats_kernel(const __half* __restrict__ x, float* __restrict__ stats, int HW, int C, int slab,
-                                int G) {
-  extern __shared__ float sh[];  // [R][2*C] + [2*C]
-  const int cv = C >> 3;
-  const int R = blockDim.x / cv;
-  const int cq = threadIdx.x % cv, pr = threadIdx.x / cv;
-  const int n = blockIdx.y;
-  const int p0 = blockIdx.x * slab;
-  const int p1 = min(HW, p0 + slab);
-  float s[8], ss[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
-  if (pr < R) {
-#pragma unroll 4
-    for (int p = p0 + pr; p < p1; p += R) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((long long)n * HW + p) * C + cq * 8));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = unpack_h2(w[t]);
-        s[2 * t] += f.x;
-        ss[2 * t] += f.x * f.x;
-        s[2 * t + 1] += f.y;
-        ss[2 * t + 1] += f.y * f.y;
-      }
-    }
+// All GroupNorm kernels read their input through GnSrc: one NHWC tensor [N, HW, C], or the channel concatenation of
+// two ([.., C1] ++ [.., C - C1], torch.cat of the UNet skip connections) without materialising it; the second source
+// may hold only n2mod samples (sample n reads n mod n2mod: a tensor shared by the two CFG halves).
+struct GnSrc {
+  const __half* x1;
+  const __half* x2;  // nullptr: single source (C1 == C)
+  int C1, n2mod;
+};
+// base pointer / row stride (in elements) of the 8-channel vector `cq` of sample n
+__device__ __forceinline__ const __half* gn_src_ptr(const GnSrc& s, int n, int HW, int C, int cq, int& stride) {
+  const int cv1 = s.C1 >> 3;
+  if (s.x2 == nullptr || cq < cv1) {
+    stride = s.C1;
+    return s.x1 + (long long)n * HW * s.C1 + cq * 8;
   }
-  // deterministic in-block reduction over the R pixel rows (fixed order, no atomics): results must not depend
-  // on the batch size or on scheduling (multi-GPU shards have to reproduce the single-GPU bits)
-  float* shp = sh + (size_t)pr * 2 * C + (size_t)cq * 16;  // sh: [R][2*C]
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    shp[2 * j] = s[j];
-    shp[2 * j + 1] = ss[j];
-  }
-  __syncthreads();
-  float* chs = sh + (size_t)R * 2 * C;  // [2*C] per-channel sums of this slab
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    float a = 0.f;
-    for (int rr = 0; rr < R; ++rr) a += sh[(size_t)rr * 2 * C + i];
-    chs[i] = a;
-  }
-  __syncthreads();
-  // partial[n][slab][G][2]: channels of a group folded in channel order
-  const int cpg = C / G;
-  if (threadIdx.x < 2 * G) {
-    const int gi = threadIdx.x >> 1, which = threadIdx.x & 1;
-    float a = 0.f;
-    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) a += chs[2 * c + which];
-    stats[((long long)n * gridDim.x + blockIdx.x) * 2 * G + threadIdx.x] = a;
-  }
-}
-// Phase 1b: fold the per-slab partials in a fixed order -> mean / rstd per (n, group): out[n][G][2]
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int nslab, int HW, int C,
-                                   int G, float eps) {
-  const int n = blockIdx.x;
-  const int cpg = C / G;
-  // 8 threads per group (blockDim = 8*G): thread t folds slabs t, t+8, ...; the 8 partials are then combined by a
-  // fixed shuffle tree -> bitwise reproducible
-  const int gi = threadIdx.x >> 3, t = threadIdx.x & 7;
-  float s = 0.f, ss = 0.f;
-  if (gi < G) {
-    for (int sl = t; sl < nslab; sl += 8) {
-      const float2 v = *reinterpret_cast<const float2*>(partial + (((long long)n * nslab + sl) * G + gi) * 2);
-      s += v.x;
-      ss += v.y;
-    }
-  }
-#pragma unroll
-  for (int o = 4; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  }
-  if (gi < G && t == 0) {
-    const float cnt = (float)cpg * (float)HW;
-    const float mean = s / cnt;
-    const float var = fmaxf(ss / cnt - mean * mean, 0.f);
-    out[((long long)n * G + gi) * 2] = mean;
-    out[((long long)n * G + gi) * 2 + 1] = rsqrtf(var + eps);
-  }
-}
-// Phase 2: y = x*a[n,c] + b[n,c] [* sigmoid] with a = rstd*gamma, b = beta - mean*rstd*gamma staged in smem.
-// blockDim = (C/8)*R like phase 1: a thread keeps its 8 channels (a/b in registers) and walks over pixels.
-__global__ void gn_apply_kernel(const __half* __restrict__ x, const float* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ y,
-                                int N, int HW, int C, int G, float eps, int silu, int slab) {
-  extern __shared__ float sh[];  // [2*G] mean/rstd
-  const int n = blockIdx.y;
-  const int cpg = C / G;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = stats[(long long)n * 2 * G + i];  // mean, rstd
-  __syncthreads();
-  const int cv = C >> 3;
-  const int R = blockDim.x / cv;
-  const int cq = threadIdx.x % cv, pr = threadIdx.x / cv;
-  float a[8], b[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cq * 8 + j;
-    const int gi = c / cpg;
-    a[j] = sh[2 * gi + 1] * __ldg(gamma + c);
-    b[j] = __ldg(beta + c) - sh[2 * gi] * a[j];
-  }
-  const int p0 = blockIdx.x * slab;
-  const int p1 = min(HW, p0 + slab);
-#pragma unroll 4
-  for (int p = p0 + pr; p < p1; p += R) {
-    const long long off = ((long long)n * HW + p) * C + cq * 8;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + off));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    float v[8];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 f = unpack_h2(w[t]);
-      v[2 * t] = f.x;
-      v[2 * t + 1] = f.y;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = v[j] * a[j] + b[j];
-      if (silu) t = fast_silu(t);
-      v[j] = t;
-    }
-    uint4 o;
-    o.x = pack_h2(v[0], v[1]);
-    o.y = pack_h2(v[2], v[3]);
-    o.z = pack_h2(v[4], v[5]);
-    o.w = pack_h2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(y + off) = o;
-  }
+  stride = C - s.C1;
+  const int n2 = s.n2mod > 0 ? n % s.n2mod : n;
+  return s.x2 + (long long)n2 * HW * stride + (cq - cv1) * 8;
 }
 
-// Two-launch GroupNorm (whole-grid): gn_stats2 = gn_stats with 8 batched 16-byte loads in flight per thread and
-// bank-conflict-free partial sums; gn_apply2 = gn_apply with the finalize step (fixed-order fold of the per-slab partials,
-// same arithmetic as gn_finalize_kernel) done by every CTA for its own sample instead of a separate launch.
+// Two-launch GroupNorm (whole-grid): gn_stats2 = per-slab statistics with 8 batched 16-byte loads in flight per thread
+// and bank-conflict-free partial sums; gn_apply2 = normalise (+SiLU) with the finalize step (fixed-order fold of the
+// per-slab partials) done by every CTA for its own sample instead of a separate launch.
 __global__ void __launch_bounds__(512)
-gn_stats2_kernel(const __half* __restrict__ x, float* __restrict__ stats, int HW, int C, int slab, int G) {
+gn_stats2_kernel(const GnSrc src, float* __restrict__ stats, int HW, int C, int slab, int G) {
   extern __shared__ float sh[];  // [R][16][cv] + [2*C]
   const int cv = C >> 3;
   const int R = blockDim.x / cv;
@@ -275,7 +162,8 @@ gn_stats2_kernel(const __half* __restrict__ x, float* __restrict__ stats, int HW
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * slab;
   const int p1 = min(HW, p0 + slab);
-  const __half* xn = x + (long long)n * HW * C + cq * 8;
+  int xs;
+  const __half* xn = gn_src_ptr(src, n, HW, C, cq, xs);
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
@@ -285,7 +173,7 @@ gn_stats2_kernel(const __half* __restrict__ x, float* __restrict__ stats, int HW
     for (int k = 0; k < 8; ++k) {
       const int p = pb + k * R;
       u[k] = make_uint4(0u, 0u, 0u, 0u);
-      if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * C));
+      if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * xs));
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -323,7 +211,7 @@ gn_stats2_kernel(const __half* __restrict__ x, float* __restrict__ stats, int HW
   }
 }
 __global__ void __launch_bounds__(512)
-gn_apply2_kernel(const __half* __restrict__ x, const float* __restrict__ partial, int nslab, const float* __restrict__ gamma,
+gn_apply2_kernel(const GnSrc src, const float* __restrict__ partial, int nslab, const float* __restrict__ gamma,
                  const float* __restrict__ beta, __half* __restrict__ y, int HW, int C, int G, float eps, int silu, int slab) {
   __shared__ float st[64];  // mean / rstd per group (G <= 32)
   const int n = blockIdx.y;
@@ -367,14 +255,15 @@ gn_apply2_kernel(const __half* __restrict__ x, const float* __restrict__ partial
   }
   const int p0 = blockIdx.x * slab;
   const int p1 = min(HW, p0 + slab);
-  const __half* xn = x + (long long)n * HW * C + cq * 8;
+  int xs;
+  const __half* xn = gn_src_ptr(src, n, HW, C, cq, xs);
   __half* yn = y + (long long)n * HW * C + cq * 8;
   for (int pb = p0 + pr; pb < p1; pb += 4 * R) {
     uint4 u[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int p = pb + k * R;
-      if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * C));
+      if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * xs));
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -414,7 +303,7 @@ __device__ __forceinline__ float dsmem_ld_f32(uint32_t saddr, uint32_t cta) {
   return v;
 }
 __global__ void __launch_bounds__(512, 2)
-gn_fused_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+gn_fused_kernel(const GnSrc src, const float* __restrict__ gamma, const float* __restrict__ beta,
                 __half* __restrict__ y, int HW, int C, int G, float eps, int silu) {
   extern __shared__ float sh[];
   const int cv = C >> 3;
@@ -429,7 +318,8 @@ gn_fused_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, c
   float* chs = sh + max(R * 2 * C, 2 * G * S);  // [2C], behind the reduction scratch / the gathered cluster partials
   float* part = chs + 2 * C;            // [2G] this CTA's per-group sums (read by the whole cluster)
   float* stat = part + 2 * G;           // [2G] mean / rstd
-  const __half* xn = x + (long long)n * HW * C + cq * 8;
+  int xs;
+  const __half* xn = gn_src_ptr(src, n, HW, C, cq, xs);
   constexpr int UB = 4;  // 16-byte loads in flight per thread (two CTAs per SM: 64 registers)
   {
     float s[8], ss[8];
@@ -441,7 +331,7 @@ gn_fused_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, c
       for (int k = 0; k < UB; ++k) {
         const int p = pb + k * R;
         u[k] = make_uint4(0u, 0u, 0u, 0u);  // zeros add nothing to either sum
-        if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * C));
+        if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * xs));
       }
 #pragma unroll
       for (int k = 0; k < UB; ++k) {
@@ -513,7 +403,7 @@ gn_fused_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, c
 #pragma unroll
       for (int k = 0; k < UB; ++k) {
         const int p = pb + k * R;
-        if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * C));
+        if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * xs));
       }
 #pragma unroll
       for (int k = 0; k < UB; ++k) {

@@ -191,7 +191,11 @@ int pick_bn(Ctx& c, long long M, int N, bool geglu, int K, bool allow16) {
 
 // Bplain/kp/nrows_w: the plain 2-D weight operand (lets the 2-CTA kernel rebuild the B map with a half-height box)
 static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, dim3 grid, double kalg,
-                        const __half* Bplain = nullptr, int kp = 0, int nrows_w = 0) {
+                        const __half* Bplain = nullptr, int kp = 0, int nrows_w = 0, const CUtensorMap* tmA2p = nullptr) {
+  const CUtensorMap& tmA2 = tmA2p ? *tmA2p : tmA;
+  if (g.ctw <= 0) g.ctw = 3;
+  RFB_CHECK(!g.up || (!g.res && !g.rowvec && !g.out32 && !g.ksplit), "folded upsample conv: plain fp16 epilogue only");
+  RFB_CHECK(!g.nk1 || (g.a_mode == A_PLAIN && tmA2p), "two-source A needs the plain operand mode");
   const int stage_bytes = GEMM_A_STAGE_BYTES + g.BN * 128;
   int stages = c.force_stages ? c.force_stages : std::max(2, std::min(6, c.gemm_smem_budget / stage_bytes));
   stages = std::min(stages, std::max(1, g.nk));
@@ -212,7 +216,7 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     rec.mode = g.a_mode * 100 + (g.geglu ? 10 : 0) + (g.res ? 1 : 0) + (g.rowvec ? 2 : 0) + (g.out32 ? 4 : 0);
     CUDA_OK(cudaEventRecord(rec.a, c.stream));
   }
-  const bool pair_ok = c.gemm_pair && g.cstride <= 1 && Bplain != nullptr && grid.z == 1 && grid.x >= 2 &&
+  const bool pair_ok = c.gemm_pair && g.cstride <= 1 && !g.up && !g.nk1 && Bplain != nullptr && grid.z == 1 && grid.x >= 2 &&
                        (g.a_mode == A_PLAIN || g.a_mode == A_CONV3) && g.b_mode == B_PLAIN && g.nk >= c.gemm_pair_min_nk &&
                        (long long)grid.x * grid.y >= c.num_sms / 2;
   if (pair_ok) {
@@ -279,13 +283,13 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     const int ctas = std::min(total, c.num_sms);
     const int thr = 64 + np * 128;
     if (g.geglu) {
-      if (np == 3) gemm_persist_kernel<EPI_GEGLU, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
-      else gemm_persist_kernel<EPI_GEGLU, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
+      if (np == 3) gemm_persist_kernel<EPI_GEGLU, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
+      else gemm_persist_kernel<EPI_GEGLU, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
     } else if (g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f) {
-      if (np == 3) gemm_persist_kernel<EPI_FAST, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
-      else gemm_persist_kernel<EPI_FAST, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
+      if (np == 3) gemm_persist_kernel<EPI_FAST, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
+      else gemm_persist_kernel<EPI_FAST, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
     } else {
-      gemm_persist_kernel<EPI_GENERIC, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, g, m_tiles, n_tiles, total);
+      gemm_persist_kernel<EPI_GENERIC, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
     }
   }
   LAUNCH_CHECK(c);
@@ -299,6 +303,7 @@ static void fill_epi(GemmArgs& g, const Epi& e, __half* out, long long ldo) {
   g.alpha = e.alpha, g.bias = e.bias, g.rowvec = e.rowvec, g.rows_per_vec = e.rows_per_vec, g.ldv = e.ldv;
   g.act_param = e.act_param, g.act = e.act, g.geglu = e.geglu, g.res = e.res, g.ldr = e.ldr;
   g.relu_after_res = e.relu_after_res;
+  g.res_mod = e.res_mod;
   g.out = out, g.ldo = ldo, g.out32 = e.out32, g.o32_sn = e.o32_sn, g.o32_sp = e.o32_sp, g.o32_sc = e.o32_sc;
   g.o32_rpn = e.o32_rpn;
 }
@@ -344,6 +349,37 @@ void gemm(Ctx& c, const __half* A, long long lda, long long M, int K, const __ha
   CUtensorMap tmB = make_tmap(c, W, 2, db, sb, bb);
   dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + g.BN - 1) / g.BN), 1);
   launch_gemm(c, tmA, tmB, g, grid, (double)(kalg > 0 ? kalg : K), W, kp, nrows_w);
+}
+
+// out = [A1 | A2] W^T (+ epilogue): the channel concatenation of two row-aligned activations as ONE K loop over two TMA
+// descriptors (torch.cat of the UNet skip connections, openaimodel.py:897-899, without materialising the copy).
+// K1 % 64 == 0; a2_rows > 0: A2 has only a2_rows rows and row m reads A2[m mod a2_rows] (a2_rows % 128 == 0).
+void gemm2(Ctx& c, const __half* A1, long long lda1, int K1, const __half* A2, long long lda2, int K2, long long a2_rows,
+           long long M, const __half* W, int kp, int N, __half* out, long long ldo, const Epi& e) {
+  RFB_CHECK(K1 % 64 == 0 && K2 > 0, "two-source GEMM: the first source must be a multiple of 64 channels wide");
+  RFB_CHECK(a2_rows == 0 || (a2_rows % GEMM_BM == 0 && M % a2_rows == 0), "two-source GEMM: bad row period of source 2");
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  const int K = K1 + K2;
+  g.M = (int)M, g.N = N, g.nk = (K + 63) / 64, g.nk1 = K1 / 64, g.a2_mod = (int)a2_rows;
+  const bool vec_epi = e.out32 == nullptr && (N & 7) == 0 && (ldo & 7) == 0 && (!e.res || (e.ldr & 7) == 0);
+  g.BN = pick_bn(c, M, N, e.geglu != 0, K, vec_epi);
+  g.a_mode = A_PLAIN, g.b_mode = B_PLAIN;
+  fill_epi(g, e, out, ldo);
+  const uint64_t d1[2] = {(uint64_t)K1, (uint64_t)M};
+  const uint64_t s1[1] = {(uint64_t)lda1 * 2};
+  const uint64_t d2[2] = {(uint64_t)K2, (uint64_t)(a2_rows ? a2_rows : M)};
+  const uint64_t s2[1] = {(uint64_t)lda2 * 2};
+  const uint32_t ba[2] = {64, 128};
+  const int nrows_w = round_up(N, 32);
+  const uint64_t db[2] = {(uint64_t)kp, (uint64_t)nrows_w};
+  const uint64_t sb[1] = {(uint64_t)kp * 2};
+  const uint32_t bb[2] = {64, (uint32_t)g.BN};
+  CUtensorMap tmA = make_tmap(c, A1, 2, d1, s1, ba);
+  CUtensorMap tmA2 = make_tmap(c, A2, 2, d2, s2, ba);
+  CUtensorMap tmB = make_tmap(c, W, 2, db, sb, bb);
+  dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + g.BN - 1) / g.BN), 1);
+  launch_gemm(c, tmA, tmB, g, grid, (double)K, nullptr, 0, 0, &tmA2);
 }
 
 Tens linear_t(Ctx& c, const Tens& x, const LinW& w, Epi e) {
@@ -448,6 +484,86 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
   return y;
 }
 
+// ------------------------------------------------------------------------------------------ folded upsample conv
+// Upsample.forward = nearest-2x interpolation followed by a 3x3 convolution (openaimodel.py:109-119, model.py:53-66).
+// Output pixel (2y+py, 2x+px) only ever sees the 2x2 input neighbourhood {y-1+py, y+py} x {x-1+px, x+px}: the three kernel
+// rows collapse onto two input rows (py = 0: {W0} on y-1, {W1+W2} on y; py = 1: {W0+W1} on y, {W2} on y+1), likewise the
+// columns.  The layer is therefore FOUR 2x2 convolutions over the low-resolution input (one per output phase) with
+// pre-summed weights: 4/9 of the multiply-adds, no up-sampled tensor in HBM, zero fill at the border identical to the
+// padding of the original formulation.  Weights: [4 phases][cout_p][4 taps * cin] fp16, summed in fp32 before rounding.
+__global__ void pack_upconv_w_kernel(const float* __restrict__ src, __half* __restrict__ dst, int O, int Op, int I, int Kp) {
+  const long long total = 4ll * Op * Kp;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % Kp);
+    const int o = (int)((idx / Kp) % Op);
+    const int ph = (int)(idx / ((long long)Kp * Op));
+    const int tap = k / I, i = k % I;
+    float v = 0.f;
+    if (o < O && tap < 4) {
+      const int py = ph >> 1, px = ph & 1, a = tap >> 1, b = tap & 1;
+      // kernel rows / columns that land on input row a (column b) for this phase
+      const int ky0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), ky1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+      const int kx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), kx1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+      const float* w = src + ((long long)o * I + i) * 9;
+      for (int ky = ky0; ky <= ky1; ++ky)
+        for (int kx = kx0; kx <= kx1; ++kx) v += w[ky * 3 + kx];
+    }
+    dst[idx] = __float2half_rn(v);
+  }
+}
+ConvW pack_upconv(Ctx& c, const std::string& wname, const std::string& bname) {
+  const Param& p = c.param(wname);
+  RFB_CHECK(p.shape.size() == 4 && p.shape[2] == 3 && p.shape[3] == 3, "upsample conv weight must be [O,I,3,3]");
+  ConvW w;
+  w.cout = (int)p.shape[0], w.cin = (int)p.shape[1], w.ksz = 3, w.taps = 4, w.cin_p = w.cin, w.up = 1;
+  RFB_CHECK(w.cin % 64 == 0, "folded upsample conv needs Cin % 64 == 0");
+  w.kp = 4 * w.cin;
+  const int cout_p = round_up(w.cout, 32);
+  w.w = (__half*)c.dmalloc((size_t)4 * cout_p * w.kp * sizeof(__half));
+  pack_upconv_w_kernel<<<grid_for(4ll * cout_p * w.kp), 256, 0, c.stream>>>(p.f32, w.w, w.cout, cout_p, w.cin, w.kp);
+  LAUNCH_CHECK(c);
+  w.b = bname.empty() ? nullptr : c.pf(bname);
+  return w;
+}
+static int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return (1 << l) == v ? l : -1;
+}
+// conv3x3(nearest_2x(x)) with the folded weights of pack_upconv: x [n,h,w,cin] -> [n,2h,2w,cout]
+Tens upconv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e) {
+  RFB_CHECK(w.up && x.c == w.cin, "upconv: weights were not packed by pack_upconv / channel mismatch");
+  const int wl = ilog2_exact(x.w), hwl = ilog2_exact(x.h * x.w);
+  RFB_CHECK(wl >= 0 && hwl >= 0 && conv_tma_ok(c, x, w, 1, 1, 1, 1, 1, x.h, x.w), "upconv: map size not supported");
+  Tens y = c.new_tens(x.n, 2 * x.h, 2 * x.w, w.cout);
+  if (!e.bias) e.bias = w.b;
+  const long long M = x.rows();
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = (int)M, g.N = w.cout, g.cblocks = w.cin / 64, g.nk = 4 * g.cblocks;
+  g.BN = pick_bn(c, M, w.cout, false, 4 * w.cin, (w.cout & 7) == 0);
+  g.a_mode = A_CONV3, g.b_mode = B_BATCH3;
+  g.bw = std::min(x.w, 128);
+  g.bh = std::min(x.h, 128 / g.bw);
+  g.bimg = 128 / (g.bw * g.bh);
+  g.tiles_w = x.w / g.bw, g.tiles_h = x.h / g.bh;
+  g.cstride = 1, g.cpad_l = 1, g.cpad_t = 1, g.ctw = 2, g.up = 1, g.up_wlog2 = wl, g.up_hwlog2 = hwl;
+  fill_epi(g, e, y.p, y.c);
+  g.zdiv = 1, g.zs_outer = 0, g.zs_inner = 0;
+  const int cout_p = round_up(w.cout, 32);
+  const uint64_t da[4] = {(uint64_t)x.c, (uint64_t)x.w, (uint64_t)x.h, (uint64_t)x.n};
+  const uint64_t sa[3] = {(uint64_t)x.c * 2, (uint64_t)x.w * x.c * 2, (uint64_t)x.h * x.w * x.c * 2};
+  const uint32_t ba[4] = {64, (uint32_t)g.bw, (uint32_t)g.bh, (uint32_t)g.bimg};
+  const uint64_t db[3] = {(uint64_t)w.kp, (uint64_t)cout_p, 4};
+  const uint64_t sb[2] = {(uint64_t)w.kp * 2, (uint64_t)cout_p * w.kp * 2};
+  const uint32_t bb[3] = {64, (uint32_t)g.BN, 1};
+  CUtensorMap tmA = make_tmap(c, x.p, 4, da, sa, ba);
+  CUtensorMap tmB = make_tmap(c, w.w, 3, db, sb, bb);
+  dim3 grid((unsigned)((M + 127) / 128), (unsigned)((w.cout + g.BN - 1) / g.BN), 4);
+  launch_gemm(c, tmA, tmB, g, grid, 4.0 * w.cin);
+  return y;
+}
+
 // ------------------------------------------------------------------------------------------ attention (materialised)
 // qkv: fused projection rows [N*L, ldq]; q/k/v start at column offsets q_off/k_off/v_off, head h at +h*d.
 // S = scale * Q K^T (fp16, [N*heads, L, Lp]) -> row softmax -> O = P V written to out[N*L, ldo] at column h*d.
@@ -520,10 +636,18 @@ void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads
 
 // ------------------------------------------------------------------------------------------ normalisation etc.
 Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps, bool silu) {
-  RFB_CHECK(x.c % 32 == 0 && x.c % 8 == 0, "GroupNorm(32) needs C % 32 == 0");
-  Tens y = c.new_tens(x.n, x.h, x.w, x.c);
+  return groupnorm2(c, x, Tens(), gamma, beta, eps, silu);
+}
+// GroupNorm(32) of the channel concatenation [x1 | x2] (x2.p == nullptr: of x1 alone) -> one contiguous NHWC tensor.
+// x2 may hold fewer samples than x1 (x1.n % x2.n == 0): sample n reads x2[n mod x2.n].
+Tens groupnorm2(Ctx& c, const Tens& x1, const Tens& x2, const float* gamma, const float* beta, float eps, bool silu) {
+  const int C = x1.c + (x2.p ? x2.c : 0), N = x1.n, HW = x1.h * x1.w;
+  RFB_CHECK(C % 32 == 0 && x1.c % 8 == 0 && C % 8 == 0, "GroupNorm(32) needs C % 32 == 0 and 8-channel aligned sources");
+  RFB_CHECK(!x2.p || (x2.h == x1.h && x2.w == x1.w && x2.n > 0 && x1.n % x2.n == 0), "GroupNorm: sources do not line up");
+  GnSrc src{x1.p, x2.p, x1.c, (x2.p && x2.n != x1.n) ? x2.n : 0};
+  Tens y = c.new_tens(N, x1.h, x1.w, C);
   const size_t mk = c.mark();
-  const int HW = x.h * x.w, C = x.c, cv = C / 8;
+  const int cv = C / 8;
   RFB_CHECK(cv <= 512, "GroupNorm: too many channels");
   int R = std::max(1, 512 / cv);
   // One cluster launch for small and medium maps; the whole-grid two-launch path (statistics, apply with the finalize
@@ -538,7 +662,7 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
       CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       CUDA_OK(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       // 16-CTA clusters are a non-portable size: fall back to the portable 8 where the device (e.g. a partitioned
-      // GPU) cannot co-schedule them.  The choice is fixed per process, so results stay reproducible.
+      // GPU) cannot co-schedule them.  The choice is fixed per context, so results stay reproducible.
       cudaLaunchConfig_t q;
       memset(&q, 0, sizeof(q));
       q.gridDim = dim3(16, 1), q.blockDim = dim3(512), q.dynamicSmemBytes = 48 * 1024;
@@ -555,7 +679,7 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
     const int GC = std::min(c.gn_cluster, max_cluster);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)GC, (unsigned)x.n);
+    cfg.gridDim = dim3((unsigned)GC, (unsigned)N);
     cfg.blockDim = dim3((unsigned)(cv * R));
     cfg.dynamicSmemBytes = ((size_t)std::max(R * 2 * C, 64 * GC) + 2 * C + 4 * 32) * sizeof(float);
     cfg.stream = c.stream;
@@ -564,46 +688,24 @@ Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, flo
     at[0].val.clusterDim.x = GC, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
     cfg.attrs = at, cfg.numAttrs = 1;
     RFB_CHECK(cfg.dynamicSmemBytes <= 96 * 1024, "GroupNorm: smem over budget");
-    CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const __half*)x.p, gamma, beta, y.p, HW, C, 32, eps,
-                               silu ? 1 : 0));
+    CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel, src, gamma, beta, y.p, HW, C, 32, eps, silu ? 1 : 0));
     LAUNCH_CHECK(c);
     return y;
   }
-  if (c.gn_split2) {
-    // two launches: whole-grid statistics (8 loads in flight per thread) + apply with the finalize folded in
-    R = std::max(1, 512 / cv);
-    const int slab = std::max(R, (HW + 31) / 32);  // <= 32 slabs per sample, a function of the shape only
-    const int nslab = (HW + slab - 1) / slab;
-    float* partial = c.alloc_t<float>((size_t)x.n * nslab * 32 * 2);
-    if (c.first_use("gn_stats2"))
-      CUDA_OK(cudaFuncSetAttribute(gn_stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    dim3 g1((unsigned)nslab, (unsigned)x.n);
-    gn_stats2_kernel<<<g1, cv * R, (size_t)(R + 1) * 2 * C * sizeof(float), c.stream>>>(x.p, partial, HW, C, slab, 32);
-    LAUNCH_CHECK(c);
-    const int want2 = std::max(1, (8 * c.num_sms) / std::max(1, x.n));
-    const int slab2 = std::max(R, (HW + want2 - 1) / want2);
-    dim3 g2((unsigned)((HW + slab2 - 1) / slab2), (unsigned)x.n);
-    RFB_CHECK(cv * R >= 256, "GroupNorm: block too small for the in-kernel finalize");
-    gn_apply2_kernel<<<g2, cv * R, 0, c.stream>>>(x.p, partial, nslab, gamma, beta, y.p, HW, C, 32, eps, silu ? 1 : 0, slab2);
-    LAUNCH_CHECK(c);
-    c.release(mk);
-    return y;
-  }
-  // the slab partition depends on the tensor shape only (never on the batch size): bitwise batch-independence
-  const int slab = std::max(R, (HW + 63) / 64);
+  // two launches: whole-grid statistics (8 loads in flight per thread) + apply with the finalize folded in
+  const int slab = std::max(R, (HW + 31) / 32);  // <= 32 slabs per sample, a function of the shape only
   const int nslab = (HW + slab - 1) / slab;
-  float* partial = c.alloc_t<float>((size_t)x.n * nslab * 32 * 2);
-  float* stats = c.alloc_t<float>((size_t)x.n * 32 * 2);
-  dim3 g1((unsigned)nslab, (unsigned)x.n);
-  gn_stats_kernel<<<g1, cv * R, (size_t)(R + 1) * 2 * C * sizeof(float), c.stream>>>(x.p, partial, HW, C, slab, 32);
+  float* partial = c.alloc_t<float>((size_t)N * nslab * 32 * 2);
+  if (c.first_use("gn_stats2"))
+    CUDA_OK(cudaFuncSetAttribute(gn_stats2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  dim3 g1((unsigned)nslab, (unsigned)N);
+  gn_stats2_kernel<<<g1, cv * R, (size_t)(R + 1) * 2 * C * sizeof(float), c.stream>>>(src, partial, HW, C, slab, 32);
   LAUNCH_CHECK(c);
-  gn_finalize_kernel<<<(unsigned)x.n, 8 * 32, 0, c.stream>>>(partial, stats, nslab, HW, C, 32, eps);
-  LAUNCH_CHECK(c);
-  const int want2 = std::max(1, (8 * c.num_sms) / std::max(1, x.n));
+  const int want2 = std::max(1, (8 * c.num_sms) / std::max(1, N));
   const int slab2 = std::max(R, (HW + want2 - 1) / want2);
-  dim3 g2((unsigned)((HW + slab2 - 1) / slab2), (unsigned)x.n);
-  gn_apply_kernel<<<g2, cv * R, 2 * 32 * sizeof(float), c.stream>>>(x.p, stats, gamma, beta, y.p, x.n, HW, C, 32, eps,
-                                                                  silu ? 1 : 0, slab2);
+  dim3 g2((unsigned)((HW + slab2 - 1) / slab2), (unsigned)N);
+  RFB_CHECK(cv * R >= 256, "GroupNorm: block too small for the in-kernel finalize");
+  gn_apply2_kernel<<<g2, cv * R, 0, c.stream>>>(src, partial, nslab, gamma, beta, y.p, HW, C, 32, eps, silu ? 1 : 0, slab2);
   LAUNCH_CHECK(c);
   c.release(mk);
   return y;

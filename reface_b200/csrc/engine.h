@@ -28,6 +28,7 @@ struct ConvW {  // packed [cout_p, kp] fp16, k = tap*cin_p + c
   __half* w = nullptr;
   const float* b = nullptr;
   int cin = 0, cout = 0, cin_p = 0, taps = 0, kp = 0, ksz = 0;
+  int up = 0;  // packed by pack_upconv: [4 phases][cout_p][4 taps * cin] (nearest-2x upsample folded into the 3x3 conv)
 };
 struct LinW {  // packed [out_p, kp] fp16
   __half* w = nullptr;
@@ -50,6 +51,7 @@ struct Epi {
   int relu_after_res = 0;  // ReLU after the residual add (needs the generic epilogue)
   const __half* res = nullptr;
   long long ldr = 0;
+  long long res_mod = 0;  // residual has only res_mod rows and is read at row (m mod res_mod) (CFG halves sharing a tensor)
   float alpha = 1.0f;
   float* out32 = nullptr;
   long long o32_sn = 0, o32_sp = 0, o32_sc = 0;
@@ -88,7 +90,6 @@ struct Ctx {
   int gemm_splitk = 1;   // 3-way split-K for the long-K 3x3 convs of <= 8x8 maps (slice count from the per-sample shape only)
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)
   int gn_fused = 1;  // single-launch cluster GroupNorm (0: stats / finalize / apply kernels)
-  int gn_split2 = 1;  // whole-grid GroupNorm path: 0 = stats / finalize / apply (round 1), 1 = stats2 / apply2 (two launches)
   long long gn_fused_max_elems = 2621440;  // = 64*64*640: per-sample H*W*C from which GroupNorm takes the whole-grid path
   int gn_cluster = 16, gn_threads = 512;  // fused GroupNorm: CTAs per sample (cluster size), threads per CTA
   int ln_vec = 1;    // 16-byte-vectorised LayerNorm (0: one warp per row, 4-byte loads)
@@ -165,6 +166,10 @@ void conv3x3(Ctx& c, const Tens& x, const ConvW& w, __half* out, long long ldo, 
              int pad_l = 1, int Ho = -1, int Wo = -1);
 Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride = 1, int pad_t = 1, int pad_l = 1,
                int pad_b = 1, int pad_r = 1);
+void gemm2(Ctx& c, const __half* A1, long long lda1, int K1, const __half* A2, long long lda2, int K2, long long a2_rows,
+           long long M, const __half* W, int kp, int N, __half* out, long long ldo, const Epi& e);
+ConvW pack_upconv(Ctx& c, const std::string& wname, const std::string& bname);
+Tens upconv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e);
 Tens linear_t(Ctx& c, const Tens& x, const LinW& w, Epi e);
 void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads, int d, __half* out, long long ldo,
                float scale, int q_off, int k_off, int v_off, int hs = 0);
@@ -172,6 +177,7 @@ void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads
 void cross_attn_small(Ctx& c, const __half* q, const float* kc, const float* vc, __half* out, int N, int L, int T, int C,
                       int heads);
 Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps, bool silu);
+Tens groupnorm2(Ctx& c, const Tens& x1, const Tens& x2, const float* gamma, const float* beta, float eps, bool silu);
 Tens layernorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps);
 Tens upsample2x(Ctx& c, const Tens& x);
 Tens concat_c(Ctx& c, const Tens& a, const Tens& b);

@@ -68,9 +68,19 @@ __device__ __forceinline__ void sts32f(uint32_t a, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
 
+// Row of the OUTPUT tensor that accumulator row gm is written to: the identity, except for the folded upsample
+// convolution, whose tile rows are input pixels (n, y, x) and whose results belong to output pixel (2y+py, 2x+px).
+__device__ __forceinline__ long long epi_out_row(const GemmArgs& g, long long gm, int z) {
+  if (!g.up) return gm;
+  const long long n = gm >> g.up_hwlog2;
+  const int r = (int)(gm & ((1ll << g.up_hwlog2) - 1));
+  const int y = r >> g.up_wlog2, x = r & ((1 << g.up_wlog2) - 1);
+  return (n << (g.up_hwlog2 + 2)) + ((long long)(2 * y + (z >> 1)) << (g.up_wlog2 + 1)) + (2 * x + (z & 1));
+}
+
 struct EpiTile {  // warp-uniform description of one output tile for one epilogue warp
   int ncols, NO, ocol_tile, halfN, z;
-  long long m_base, zoff;
+  long long m_base, zoff, r_base;  // r_base: first row of the residual tensor for this warp (m_base unless res_mod)
   bool vec_ok;
 };
 
@@ -82,6 +92,7 @@ __device__ __forceinline__ EpiTile epi_tile_info(const GemmArgs& g, int q, int m
   t.NO = (MODE == EPI_GEGLU) ? (g.N >> 1) : g.N;
   t.ocol_tile = (MODE == EPI_GEGLU) ? n_tile * t.halfN : n_tile * g.BN;
   t.m_base = (long long)m_tile * GEMM_BM + q * 32;
+  t.r_base = g.res_mod > 0 ? t.m_base % g.res_mod : t.m_base;
   t.z = z;
   t.zoff = (g.zdiv == 1) ? (long long)z * g.zs_outer  // plain / conv / per-sample batches: no division per tile
                          : (long long)(z / g.zdiv) * g.zs_outer + (long long)(z % g.zdiv) * g.zs_inner;
@@ -108,7 +119,7 @@ __device__ __forceinline__ void epilogue_lookahead(const GemmArgs& g, const EpiT
     }
     if (g.res && t.vec_ok && ocol0 < t.NO) {
       const long long gm = t.m_base + lane;
-      if (gm < g.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.res + t.zoff + gm * g.ldr + ocol0));
+      if (gm < g.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.res + t.zoff + (t.r_base + lane) * g.ldr + ocol0));
     }
   }
 }
@@ -138,7 +149,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmArgs& g, const EpiTi
         const int row = i * 4 + (lane >> 3), unit = lane & 7;
         const long long gm = t.m_base + row;
         const bool ok = gm < g.M && unit * 8 < cvalid;
-        const __half* src = g.res + t.zoff + gm * g.ldr + ocol0 + unit * 8;
+        const __half* src = g.res + t.zoff + (t.r_base + row) * g.ldr + ocol0 + unit * 8;
         if (ci == 0) {
           uint4 val = make_uint4(0u, 0u, 0u, 0u);
           if (ok) val = __ldg(reinterpret_cast<const uint4*>(src));
@@ -181,7 +192,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile&
         const long long gm = t.m_base + row;
         uint4 val = make_uint4(0u, 0u, 0u, 0u);
         if (gm < g.M && unit * 8 < cvalid)
-          val = __ldg(reinterpret_cast<const uint4*>(g.res + t.zoff + gm * g.ldr + ocol0 + unit * 8));
+          val = __ldg(reinterpret_cast<const uint4*>(g.res + t.zoff + (t.r_base + row) * g.ldr + ocol0 + unit * 8));
         sts128(stage + (uint32_t)row * 128u + (uint32_t)((unit ^ (row & 7)) << 4), val);
       }
       __syncwarp();
@@ -296,7 +307,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile&
       } else if (row_ok) {
         // scalar fallback (odd widths / strides, fp32 strided outputs)
         if (g.res) {
-          const __half* rp = g.res + t.zoff + m * g.ldr + oc;
+          const __half* rp = g.res + t.zoff + (t.r_base + lane) * g.ldr + oc;
           for (int j = 0; j < 32; ++j)
             if (oc + j < t.NO) v[j] += __half2float(rp[j]);
         }
@@ -305,7 +316,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile&
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (g.out) {
-          __half* op = g.out + t.zoff + m * g.ldo + oc;
+          __half* op = g.out + t.zoff + epi_out_row(g, m, t.z) * g.ldo + oc;
           for (int j = 0; j < 32; ++j)
             if (oc + j < t.NO) op[j] = __float2half_rn(v[j]);
         }
@@ -331,7 +342,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile&
         const int row = i * 4 + (lane >> 3), unit = lane & 7;
         const long long gm = t.m_base + row;
         if (gm < g.M && unit * 8 < cvalid)
-          *reinterpret_cast<uint4*>(g.out + t.zoff + gm * g.ldo + ocol0 + unit * 8) = val[i];
+          *reinterpret_cast<uint4*>(g.out + t.zoff + epi_out_row(g, gm, t.z) * g.ldo + ocol0 + unit * 8) = val[i];
       }
     }
   }

@@ -48,8 +48,9 @@ struct TileIter {
 
 template <int MODE, int NP>
 __global__ void __launch_bounds__(64 + NP * 128, 1)
-gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g,
-                    const int m_tiles, const int n_tiles, const int total_tiles) {
+gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmA2, const GemmArgs g, const int m_tiles, const int n_tiles,
+                    const int total_tiles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -79,6 +80,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.nk1) tma_prefetch_desc(&tmA2);
   }
   if (warp == 1) tmem_alloc(tptr, 512);
   tc_fence_before();
@@ -108,6 +110,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       const int m0 = m_tile * GEMM_BM, n0 = n_tile * BN;
+      const int m0b = g.a2_mod ? m0 % g.a2_mod : m0;  // row of the second A source (tiles never straddle its end)
+      const int py = z >> 1, px = z & 1;              // output phase of the folded upsample convolution
       for (int kb = 0; kb < g.nk; ++kb) {
         const uint32_t s = st, ph = sp;
         if (++st == (uint32_t)S) st = 0, sp ^= 1u;
@@ -119,11 +123,16 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t dB = sB + s * b_stage_bytes;
           const int kg = g.ksplit ? z * g.nk + kb : kb;  // split-K: this unit's slice of the K range
           switch (g.a_mode) {
-            case A_PLAIN: tma_load_2d(dA, &tmA, full, kg * GEMM_BK, m0); break;
+            case A_PLAIN:
+              if (g.nk1 && kg >= g.nk1) tma_load_2d(dA, &tmA2, full, (kg - g.nk1) * GEMM_BK, m0b);
+              else tma_load_2d(dA, &tmA, full, kg * GEMM_BK, m0);
+              break;
             case A_CONV3: {
               const int tap = kg / g.cblocks;
               const int cb = kg - tap * g.cblocks;
-              const int dy = tap / 3 - g.cpad_t, dx = tap % 3 - g.cpad_l;
+              int dy, dx;
+              if (g.up) dy = (tap >> 1) - 1 + py, dx = (tap & 1) - 1 + px;
+              else dy = tap / 3 - g.cpad_t, dx = tap % 3 - g.cpad_l;
               tma_load_4d(dA, &tmA, full, cb * GEMM_BK, cw * g.cstride + dx, ch * g.cstride + dy, cn);
             } break;
             case A_BATCH3: tma_load_3d(dA, &tmA, full, kb * GEMM_BK, m0, z); break;

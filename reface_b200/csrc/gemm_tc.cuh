@@ -21,6 +21,13 @@ struct GemmArgs {
   // A_CONV3 geometry: tile = bimg images x bh rows x bw cols (=128 output pixels), K = taps x cblocks x 64
   int cblocks, bw, bh, bimg, tiles_w, tiles_h;
   int cstride, cpad_l, cpad_t;  // conv stride (1 or 2) and left / top padding: input coordinate = stride * out + tap - pad
+  // taps per kernel row: 3 for a 3x3 convolution; 2 for the FOLDED nearest-2x-upsample + 3x3 convolution (`up` = 1): the
+  // grid's z is the output phase (py, px) = (z >> 1, z & 1), tap (a, b) reads input pixel (y + a - 1 + py, x + b - 1 + px)
+  // and the tile's rows are written to output pixels (2y + py, 2x + px) (input map: 2^up_wlog2 wide, 2^up_hwlog2 pixels)
+  int ctw, up, up_wlog2, up_hwlog2;
+  // A_PLAIN over TWO row-aligned sources (channel concatenation without the copy): k-blocks [0, nk1) come from tmA, the
+  // rest from tmA2; a2_mod > 0: source 2 has only a2_mod rows and is read at row (m mod a2_mod) (CFG halves sharing a tensor)
+  int nk1, a2_mod;
   int heads;  // *_HEADS4: z = n*heads + head
   // epilogue
   float alpha;
@@ -32,6 +39,7 @@ struct GemmArgs {
   int relu_after_res;  // ReLU applied AFTER the residual add (ResNet BasicBlock: relu(shortcut + bn(conv)))
   const __half* res;  // residual [M, ldr] added after activation
   long long ldr;
+  long long res_mod;  // > 0: the residual tensor has only res_mod rows, row m reads res[m mod res_mod] (multiple of 128)
   __half* out;  // fp16 [M, ldo]
   long long ldo;
   float* out32;  // optional fp32 strided output: (m / o32_rpn) * o32_sn + (m % o32_rpn) * o32_sp + col * o32_sc

@@ -136,7 +136,7 @@ UNet* build_unet(Ctx& c, const std::string& pfx, const UNetCfg& cfg) {
         UOp up;
         up.kind = OP_UP;
         const std::string cp = bp + std::to_string(j++) + ".conv.";
-        up.conv = pack_conv(c, cp + "weight", cp + "bias");
+        up.conv = pack_upconv(c, cp + "weight", cp + "bias");  // nearest-2x folded into the conv (engine.cu)
         ops.push_back(up);
         ds /= 2;
       }
@@ -175,16 +175,29 @@ UNet* build_unet(Ctx& c, const std::string& pfx, const UNetCfg& cfg) {
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-static Tens run_res(Ctx& c, const ResW& r, const Tens& x, const float* emb_all, int emb_rows, int emb_ld) {
+// x2.p != nullptr: the block's input is torch.cat([x, x2], 1) (openaimodel.py:897-899), never materialised: GroupNorm
+// reads both tensors, the 1x1 skip_connection conv runs one K loop over two TMA descriptors.  x2 may hold half the
+// samples of x (the conv_in output shared by the two CFG halves).
+static Tens run_res(Ctx& c, const ResW& r, const Tens& x, const float* emb_all, int emb_rows, int emb_ld,
+                    const Tens& x2 = Tens()) {
   // emb_out = Linear(SiLU(emb)) [openaimodel.py:264] was computed for all blocks at once (emb_all: [rows, emb_ld]);
   // emb_rows == 1 when every sample shares the timestep
-  Tens h = groupnorm(c, x, r.g1, r.b1, 1e-5f, true);
+  Tens h = groupnorm2(c, x, x2, r.g1, r.b1, 1e-5f, true);
   Epi e1;
   e1.rowvec = emb_all + r.emb_off, e1.ldv = emb_rows == 1 ? 0 : emb_ld;
   Tens h1 = conv3x3_t(c, h, r.c1, e1);
   Tens h2 = groupnorm(c, h1, r.g2, r.b2, 1e-5f, true);
   Tens skip = x;
-  if (r.skip) skip = conv3x3_t(c, x, r.skipw, Epi(), 1, 0, 0, 0, 0);
+  if (x2.p) {
+    RFB_CHECK(r.skip && r.skipw.ksz == 1, "a ResBlock over a concatenated input has a 1x1 skip_connection");
+    skip = c.new_tens(x.n, x.h, x.w, r.cout);
+    Epi es;
+    es.bias = r.skipw.b;
+    gemm2(c, x.p, x.c, x.c, x2.p, x2.c, x2.c, x2.n != x.n ? x2.rows() : 0, x.rows(), r.skipw.w, r.skipw.kp, r.cout, skip.p,
+          r.cout, es);
+  } else if (r.skip) {
+    skip = conv3x3_t(c, x, r.skipw, Epi(), 1, 0, 0, 0, 0);
+  }
   Epi e2;
   e2.res = skip.p, e2.ldr = skip.c;
   return conv3x3_t(c, h2, r.c2, e2);
@@ -198,15 +211,6 @@ static float* cross_vec(Ctx& c, const STW& s, const float* ctx, int N) {
   linear_small(c, ctx, s.ctx_dim, N, s.v2, v, s.c, 0, 0);
   linear_small(c, v, s.c, N, s.o2, vec, s.c, 0, 0);
   return vec;
-}
-
-// [n, h, w, c] -> [2n, h, w, c]: both CFG halves of a tensor that was computed once
-static Tens dup2(Ctx& c, const Tens& x) {
-  Tens y = c.new_tens(2 * x.n, x.h, x.w, x.c);
-  const size_t bytes = (size_t)x.rows() * x.c * sizeof(__half);
-  CUDA_OK(cudaMemcpyAsync(y.p, x.p, bytes, cudaMemcpyDeviceToDevice, c.stream));
-  CUDA_OK(cudaMemcpyAsync(y.p + (size_t)x.rows() * x.c, x.p, bytes, cudaMemcpyDeviceToDevice, c.stream));
-  return y;
 }
 
 // share_halves: x holds ONE copy of the N/2 distinct samples of a CFG batch (UNetAux::cfg_dup); GroupNorm, proj_in,
@@ -224,7 +228,7 @@ static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T,
   Tens a = c.new_tens(x.n, x.h, x.w, C);
   attention(c, qkv.p, 3 * C, x.n, L, s.heads, s.d, a.p, C, 1.0f / sqrtf((float)s.d), 0, C, 2 * C);
   Tens h1;
-  Tens xres = x;  // residual of proj_out
+  long long xres_mod = 0;  // residual of proj_out: x itself; shared halves read it modulo its rows
   if (share_halves) {
     RFB_CHECK(T == 1 && N == 2 * x.n, "shared CFG halves need the single-token context path");
     const float* vec = vec_pre ? vec_pre : cross_vec(c, s, ctx, N);
@@ -235,7 +239,7 @@ static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T,
       e.bias = s.o1.b, e.res = h.p, e.ldr = C, e.rowvec = vec + (size_t)half * x.n * C, e.ldv = C, e.rows_per_vec = L;
       gemm(c, a.p, C, Mh, C, s.o1.w, s.o1.kp, s.o1.out, h1.p + (size_t)half * Mh * C, C, e);
     }
-    xres = dup2(c, x);
+    xres_mod = x.rows();
   } else if (T == 1) {
     // --- attn2 (degenerate, see cross_vec) folded into attn1's out-projection epilogue
     const float* vec = vec_pre ? vec_pre : cross_vec(c, s, ctx, N);
@@ -257,7 +261,7 @@ static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T,
   e2.res = h1.p, e2.ldr = C;
   Tens h2 = linear_t(c, ff, s.ff2, e2);
   Epi e3;
-  e3.res = xres.p, e3.ldr = C;
+  e3.res = x.p, e3.ldr = C, e3.res_mod = xres_mod;
   return conv3x3_t(c, h2, s.proj_out, e3, 1, 0, 0, 0, 0);
 }
 
@@ -288,17 +292,21 @@ struct RunState {
   int st_idx;
 };
 
-static Tens run_ops(Ctx& c, const std::vector<UOp>& ops, Tens h, RunState& rs) {
+// cat.p != nullptr: the first op (a ResBlock) consumes torch.cat([h, cat], 1)
+static Tens run_ops(Ctx& c, const std::vector<UOp>& ops, Tens h, RunState& rs, Tens cat = Tens()) {
   for (const UOp& op : ops) {
     switch (op.kind) {
-      case OP_RES: h = run_res(c, op.res, h, rs.emb, rs.emb_rows, rs.emb_ld); break;
+      case OP_RES:
+        h = run_res(c, op.res, h, rs.emb, rs.emb_rows, rs.emb_ld, cat);
+        cat = Tens();
+        break;
       case OP_ATTN: {
         const float* pre = (rs.aux && rs.st_idx < (int)rs.aux->crossvec.size()) ? rs.aux->crossvec[rs.st_idx] : nullptr;
         h = run_st(c, op.st, h, rs.ctx, rs.T, rs.N, pre);
         ++rs.st_idx;
       } break;
       case OP_DOWN: h = conv3x3_t(c, h, op.conv, Epi(), 2, 1, 1, 1, 1); break;
-      case OP_UP: h = conv3x3_t(c, upsample2x(c, h), op.conv, Epi()); break;
+      case OP_UP: h = upconv3x3_t(c, h, op.conv, Epi()); break;
       case OP_CONV_IN: h = conv3x3_t(c, h, op.conv, Epi()); break;
     }
   }
@@ -344,7 +352,7 @@ void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const fl
     // CFG batch: the two halves only differ in the context, which first enters in attn2 of input_blocks.1
     Tens x8 = from_nchw_f32(c, x9, N / 2, u.cfg.in_channels, L, L, u.cfg.in_channels);
     Tens h0 = conv3x3_t(c, x8, u.inp[0][0].conv, Epi());
-    hs.push_back(dup2(c, h0));
+    hs.push_back(h0);  // N/2 samples: the consumers (last output block) read it modulo its sample count
     Tens r = run_res(c, u.inp[1][0].res, h0, rs.emb, rs.emb_rows, rs.emb_ld);
     const float* pre = !aux->crossvec.empty() ? aux->crossvec[0] : nullptr;
     h = run_st(c, u.inp[1][1].st, r, ctx, T, N, pre, true);
@@ -360,9 +368,10 @@ void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const fl
   }
   h = run_ops(c, u.mid, h, rs);
   for (auto& ops : u.out) {
-    Tens cat = concat_c(c, h, hs.back());
+    RFB_CHECK(!ops.empty() && ops[0].kind == OP_RES, "output blocks start with a ResBlock");
+    const Tens skip = hs.back();
     hs.pop_back();
-    h = run_ops(c, ops, cat, rs);
+    h = run_ops(c, ops, h, rs, skip);
   }
   Tens hn = groupnorm(c, h, u.out_g, u.out_b, 1e-5f, true);
   Epi e;

@@ -115,7 +115,7 @@ VAE* build_vae(Ctx& c, const std::string& pfx) {
     for (int j = 0; j < 3; ++j) v->d_up[l].push_back(build_vres(c, d + "up." + std::to_string(l) + ".block." + std::to_string(j) + "."));
     if (l != 0) {
       const std::string p = d + "up." + std::to_string(l) + ".upsample.conv.";
-      v->d_us[l] = pack_conv(c, p + "weight", p + "bias");
+      v->d_us[l] = pack_upconv(c, p + "weight", p + "bias");  // model.py:53-66: nearest-2x folded into the conv
     }
   }
   v->d_ng = c.pf(d + "norm_out.weight"), v->d_nb = c.pf(d + "norm_out.bias");
@@ -185,7 +185,7 @@ void vae_decode(Ctx& c, VAE& v, const float* z, int B, int hh, int ww, float inv
   const int nlev = (int)v.mult.size();
   for (int l = nlev - 1; l >= 0; --l) {
     for (auto& r : v.d_up[l]) h = run_vres(c, r, h);
-    if (l != 0) h = conv3x3_t(c, upsample2x(c, h), v.d_us[l], Epi());
+    if (l != 0) h = upconv3x3_t(c, h, v.d_us[l], Epi());
   }
   h = groupnorm(c, h, v.d_ng, v.d_nb, 1e-6f, true);
   const long long HW = (long long)h.h * h.w;

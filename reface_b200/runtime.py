@@ -53,9 +53,10 @@ SIGNATURES = {
     "rfb_condition_fuse": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _vp, _vp]),
     "rfb_landmark_project": (_i, [_vp, _vp, _i, _vp, _vp]),
     "rfb_target_clip_input": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
-    "rfb_op_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _vp]),
+    "rfb_op_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _i, _ll, _vp, _vp]),
+    "rfb_op_upconv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "rfb_op_conv2d": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
-    "rfb_op_groupnorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp]),
+    "rfb_op_groupnorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _i, _i, _vp, _vp]),
     "rfb_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _vp, _vp]),
     "rfb_op_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "rfb_bench_norm": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_double), _vp]),
@@ -376,13 +377,24 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ single ops (tests)
-    def op_linear(self, x, w, bias=None, residual=None, act=0, geglu=False):
-        x, w, bias, residual = self._in(x), self._in(w), self._in(bias), self._in(residual)
+    def op_linear(self, x, w, bias=None, residual=None, act=0, geglu=False, x2=None):
+        """x2 [M2,K2]: out = [x | x2] w^T with x2 read at row (m mod M2) (two-descriptor K loop, no concatenation)."""
+        x, w, bias, residual, x2 = self._in(x), self._in(w), self._in(bias), self._in(residual), self._in(x2)
         M, K = x.shape
         N = w.shape[0]
+        M2, K2 = (x2.shape if x2 is not None else (0, 0))
         out = self._new(M, N // 2 if geglu else N)
         self._ck(self.lib.rfb_op_linear(self.h, _ptr(x), _ptr(w), _ptr(bias), _ptr(residual), M, K, N, int(act),
-                                        int(geglu), _ptr(out), self._stream()))
+                                        int(geglu), _ptr(x2), K2, M2, _ptr(out), self._stream()))
+        return out
+
+    def op_upconv(self, x, w, bias=None):
+        """conv3x3(nearest_2x(x)) through the folded four-phase kernel."""
+        x, w, bias = self._in(x), self._in(w), self._in(bias)
+        N, Cc, H, W = x.shape
+        O = w.shape[0]
+        out = self._new(N, O, 2 * H, 2 * W)
+        self._ck(self.lib.rfb_op_upconv(self.h, _ptr(x), _ptr(w), _ptr(bias), N, Cc, H, W, O, _ptr(out), self._stream()))
         return out
 
     def op_conv2d(self, x, w, bias=None, stride=1, pad=(1, 1, 1, 1)):
@@ -396,12 +408,14 @@ class Engine:
                                         _ptr(out), self._stream()))
         return out
 
-    def op_groupnorm(self, x, gamma, beta, eps, silu=False):
-        x, gamma, beta = self._in(x), self._in(gamma), self._in(beta)
+    def op_groupnorm(self, x, gamma, beta, eps, silu=False, x2=None):
+        """x2 [N2,C2,H,W]: GroupNorm(32) over the channel concatenation [x | x2] (sample n reads x2[n mod N2])."""
+        x, gamma, beta, x2 = self._in(x), self._in(gamma), self._in(beta), self._in(x2)
         N, Cc, H, W = x.shape
-        out = torch.empty_like(x)
+        N2, C2 = (x2.shape[:2] if x2 is not None else (0, 0))
+        out = self._new(N, Cc + C2, H, W)
         self._ck(self.lib.rfb_op_groupnorm(self.h, _ptr(x), _ptr(gamma), _ptr(beta), N, Cc, H, W, float(eps), int(silu),
-                                           _ptr(out), self._stream()))
+                                           _ptr(x2), C2, N2, _ptr(out), self._stream()))
         return out
 
     def op_layernorm(self, x, gamma, beta, eps=1e-5):

@@ -57,16 +57,15 @@ for (N, Cc, H) in [(16, 320, 64), (16, 640, 64), (16, 960, 64), (16, 640, 32), (
     row = {"N": N, "C": Cc, "H": H}
     gb = 2.0 * N * Cc * H * H * 2 / 1e9
     txt = []
-    for name, fused, cl, th in (("split", 0, 8, 512), ("split2", 2, 8, 512), ("c16t512", 1, 16, 512)):
-        eng.set_option("gn_fused", 1 if fused == 1 else 0); eng.set_option("gn_cluster", cl); eng.set_option("gn_threads", th)
-        eng.set_option("gn_split2", 1 if fused == 2 else 0)
+    for name, fused, cl, th in (("split2", 0, 8, 512), ("c16t512", 1, 16, 512)):
+        eng.set_option("gn_fused", fused); eng.set_option("gn_cluster", cl); eng.set_option("gn_threads", th)
         eng.set_option("gn_fused_max_elems", 1 << 40)
         ms = eng.bench_norm(0, N, Cc, H, H)
         row[name] = ms * 1e3
         txt.append(f"{name} {ms*1e3:6.1f} us ({gb / (ms * 1e-3) / HBM:.2f})")
     print(f"groupnorm N={N} C={Cc} H={H}: " + "  ".join(txt), flush=True)
     out["groupnorm"].append(row)
-eng.set_option("gn_cluster", 16); eng.set_option("gn_threads", 512); eng.set_option("gn_fused_max_elems", 2621440); eng.set_option("gn_fused", 1); eng.set_option("gn_split2", 1)
+eng.set_option("gn_cluster", 16); eng.set_option("gn_threads", 512); eng.set_option("gn_fused_max_elems", 2621440); eng.set_option("gn_fused", 1)
 eng.set_option("gn_fused", 1)
 
 for (N, Cc, H) in [(16, 320, 64), (16, 640, 32), (16, 1280, 16), (16, 1280, 8), (8, 1024, 16)]:

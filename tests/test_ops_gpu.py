@@ -91,24 +91,70 @@ def test_conv_generic_im2col(engine, N, C, H, O, k, s, pad, tma_s2):
 @pytest.mark.parametrize("N,C,H,eps,silu", [(2, 320, 16, 1e-5, True), (2, 960, 8, 1e-5, True), (1, 128, 64, 1e-6, True),
                                             (3, 1280, 4, 1e-6, False), (2, 2560, 8, 1e-5, True), (2, 1920, 2, 1e-5, True),
                                             (1, 512, 32, 1e-6, False), (5, 640, 32, 1e-5, True)])
-@pytest.mark.parametrize("fused", [1, 0, 2])
+@pytest.mark.parametrize("fused", [1, 0])
 def test_groupnorm(engine, N, C, H, eps, silu, fused):
-    """fused=1 (default): one launch, a cluster of 8 CTAs per sample exchanging statistics through DSMEM;
-    fused=0: the three-kernel stats / finalize / apply path."""
+    """fused=1 (default for small / medium maps): one launch, a cluster of 16 CTAs per sample exchanging statistics
+    through DSMEM; fused=0: the two-launch whole-grid path (statistics, then apply with the finalize folded in)."""
     x = h(rn(N, C, H, H, seed=1) * 2 + 0.5)
     gam, bet = 1 + 0.1 * rn(C, seed=2), 0.1 * rn(C, seed=3)
-    engine.set_option("gn_fused", 1 if fused == 1 else 0)   # 2: the two-launch whole-grid path (stats2 / apply2)
-    engine.set_option("gn_split2", 1 if fused == 2 else 0)
+    engine.set_option("gn_fused", fused)
     engine.set_option("gn_fused_max_elems", 1 << 40)      # exercise the cluster kernel at every test shape
     try:
         y = engine.op_groupnorm(x, gam, bet, eps, silu)
     finally:
         engine.set_option("gn_fused", 1)
-        engine.set_option("gn_split2", 1)
         engine.set_option("gn_fused_max_elems", 2621440)
     ref = F.group_norm(x, 32, gam, bet, eps)
     ref = F.silu(ref) if silu else ref
     assert float((y - ref).abs().max()) < 6e-3
+
+
+@pytest.mark.parametrize("N,N2,C1,C2,H", [(2, 2, 1280, 640, 8), (4, 2, 320, 320, 16), (2, 2, 640, 320, 32), (2, 1, 1280, 1280, 8),
+                                          (2, 2, 640, 320, 64)])
+@pytest.mark.parametrize("fused", [1, 0])
+def test_groupnorm_of_concat(engine, N, N2, C1, C2, H, fused):
+    """GroupNorm(32) over torch.cat([h, skip], 1) (openaimodel.py:897-899 + ResBlock in_layers) read from the two
+    tensors in place; the second source may hold N2 < N samples (sample n reads n mod N2: the tensor the two CFG halves
+    share).  Groups straddle the seam (e.g. 960 channels = 640 + 320: 30 per group)."""
+    a = h(rn(N, C1, H, H, seed=1) * 1.5 + 0.3)
+    b = h(rn(N2, C2, H, H, seed=2) * 0.7 - 0.2)
+    C = C1 + C2
+    gam, bet = 1 + 0.1 * rn(C, seed=3), 0.1 * rn(C, seed=4)
+    engine.set_option("gn_fused", fused)
+    try:
+        y = engine.op_groupnorm(a, gam, bet, 1e-5, True, x2=b)
+    finally:
+        engine.set_option("gn_fused", 1)
+    cat = torch.cat([a, b.repeat(N // N2, 1, 1, 1)], 1)
+    ref = F.silu(F.group_norm(cat, 32, gam, bet, 1e-5))
+    assert float((y - ref).abs().max()) < 6e-3
+    assert torch.equal(y, engine.op_groupnorm(cat, gam, bet, 1e-5, True)) or fused == 1   # same slab partition: same bits
+
+
+@pytest.mark.parametrize("M,M2,K1,K2,N", [(4096, 4096, 1280, 640, 1280), (8192, 4096, 320, 320, 320), (1024, 1024, 1280, 1280, 1280),
+                                          (2048, 2048, 640, 320, 640)])
+def test_linear_of_concat(engine, M, M2, K1, K2, N):
+    """1x1 skip_connection conv of a ResBlock whose input is torch.cat([h, skip], 1): one K loop over two TMA descriptors,
+    bitwise equal to the GEMM over the materialised concatenation (same K order)."""
+    a, b = h(rn(M, K1, seed=1)), h(rn(M2, K2, seed=2))
+    w, bias = h(rn(N, K1 + K2, seed=3) / math.sqrt(K1 + K2)), rn(N, seed=4)
+    y = engine.op_linear(a, w, bias, x2=b)
+    cat = torch.cat([a, b.repeat(M // M2, 1)], 1)
+    ref = F.linear(cat, w, bias)
+    assert rel(y, ref) < 4e-3, rel(y, ref)
+    assert torch.equal(y, engine.op_linear(cat, w, bias))
+
+
+@pytest.mark.parametrize("N,C,O,H", [(2, 1280, 1280, 8), (2, 1280, 1280, 16), (1, 640, 640, 32), (1, 512, 512, 64), (1, 256, 256, 256),
+                                     (3, 128, 64, 4)])
+def test_upsample_conv_folded(engine, N, C, O, H):
+    """Upsample.forward (openaimodel.py:109-119; model.py:53-66): conv3x3(nearest_2x(x)) as four phase-wise 2x2
+    convolutions over the low-resolution input with pre-summed weights (4/9 of the MACs, no up-sampled tensor)."""
+    x, w, b = h(rn(N, C, H, H, seed=1)), h(rn(O, C, 3, 3, seed=2) / math.sqrt(9 * C)), rn(O, seed=3)
+    y = engine.op_upconv(x, w, b)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, b, padding=1)
+    assert y.shape == ref.shape
+    assert rel(y, ref) < 4e-3, rel(y, ref)
 
 
 @pytest.mark.parametrize("rows,C", [(100, 320), (4096, 640), (17, 1280), (257, 1024), (5, 768)])
