@@ -45,7 +45,10 @@ int rfb_build_arcface(rfb_ctx* ctx, const char* prefix);
 int rfb_build_face_parser(rfb_ctx* ctx, const char* prefix);
 /* Tunables ("gemm_bn", "gemm_stages", "gemm_smem_budget", "attn_flash", "profile"); returns 0 if known. */
 int rfb_set_option(rfb_ctx* ctx, const char* key, long long value);
-long long rfb_launch_count(rfb_ctx* ctx); /* kernels launched by this library so far */
+long long rfb_launch_count(rfb_ctx* ctx); /* kernels launched by this library so far (graph replays count their kernels) */
+/* rfb_ddim_sample captures its whole S-step loop into a CUDA graph the second time it sees a (shape, schedule, scale)
+ * and replays it afterwards (option "use_graph", default 1); this counts the replays. */
+long long rfb_graph_replays(rfb_ctx* ctx);
 /* With option "profile"=1 every tensor-core (tcgen05 GEMM / implicit-GEMM conv / attention) launch is bracketed
  * by CUDA events on the launching stream; this drains them: summed device time [ms], summed ALGORITHMIC FLOPs
  * (2*M*N*K of the reference-equivalent contraction, no padding) and the number of launches. */

@@ -34,6 +34,7 @@ template <class M>
 static void drop_model(Ctx& c, M*& slot) {
   if (!slot) return;
   cudaDeviceSynchronize();
+  c.drop_graphs();  // captured launches hold pointers into the packed weights
   for (void* p : slot->owned) cudaFree(p);
   delete slot;
   slot = nullptr;
@@ -90,6 +91,8 @@ void rfb_destroy(rfb_ctx* h) {
   Ctx& c = h->c;
   cudaSetDevice(c.device);
   cudaDeviceSynchronize();
+  c.drop_graphs();
+  if (c.gstream) cudaStreamDestroy(c.gstream);
   for (auto& kv : c.params) cudaFree(kv.second.f32);
   for (void* p : c.retired) cudaFree(p);
   for (void* p : c.owned) cudaFree(p);
@@ -115,6 +118,7 @@ int rfb_set_param(rfb_ctx* h, const char* name, const float* data, int ndim, con
   // Built models keep raw pointers into the fp32 parameter storage (biases, norm affine vectors, the GEMV weights):
   // a re-registered key is therefore overwritten IN PLACE when its size is unchanged, and otherwise the old buffer is
   // retired (kept alive until rfb_destroy) instead of freed.  Packed fp16 copies are refreshed by the next rfb_build_*.
+  c.drop_graphs();
   auto it = c.params.find(name);
   if (it != c.params.end() && it->second.numel == p.numel && it->second.f32) {
     CUDA_OK(cudaMemcpy(it->second.f32, data, p.numel * sizeof(float), cudaMemcpyDefault));
@@ -163,7 +167,9 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   if (!h) return -1;
   Ctx& c = h->c;
   const std::string k = key;
-  if (k == "gemm_bn") c.force_bn = (int)value;
+  if (k != "profile") c.drop_graphs();  // captured launches bake the options in
+  if (k == "use_graph") c.use_graph = (int)value;
+  else if (k == "gemm_bn") c.force_bn = (int)value;
   else if (k == "gemm_stages") c.force_stages = (int)value;
   else if (k == "gemm_smem_budget") c.gemm_smem_budget = (int)value;
   else if (k == "attn_flash") c.attn_flash = (int)value;
@@ -189,6 +195,7 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   return 0;
 }
 long long rfb_launch_count(rfb_ctx* h) { return h ? h->c.launches : 0; }
+long long rfb_graph_replays(rfb_ctx* h) { return h ? h->c.graph_replays : 0; }
 int rfb_debug_read(rfb_ctx* h, unsigned long long* out, int n) {
   API_BEGIN(h)
   RFB_CHECK(c.dbg_buf, "option gemm_debug was never enabled");

@@ -101,6 +101,19 @@ struct Ctx {
   unsigned long long* dbg_buf = nullptr;    // [num_sms * 8]
   struct ProfRec { cudaEvent_t a, b; double flops; int kind; int M = 0, N = 0, K = 0, BN = 0, mode = 0, z = 1; };
   std::vector<ProfRec> prof;
+  // CUDA graphs of whole sampling loops (unet.cu: ddim_sample), keyed by shape / schedule / arena mark / graph_epoch
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; bool failed = false; long long launches = 0; };
+  std::unordered_map<std::string, GraphEntry> graphs;
+  cudaStream_t gstream = nullptr;  // capture stream (the caller's stream may be the legacy default stream)
+  int use_graph = 1;               // option "use_graph"
+  long long graph_epoch = 0;       // bumped by every option / weight change: invalidates the cached graphs
+  long long graph_replays = 0;
+  void drop_graphs() {
+    for (auto& kv : graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs.clear();
+    ++graph_epoch;
+  }
   UNet* unet = nullptr;
   VAE* vae = nullptr;
   ClipVision* clip = nullptr;

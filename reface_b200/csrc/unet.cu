@@ -382,6 +382,45 @@ void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const fl
 }
 
 // ---------------------------------------------------------------------------------------------- DDIM loop
+// DDIMSampler.ddim_sampling + p_sample_ddim (ddim.py:200-251, 323-375).  The loop body works on arena-resident buffers
+// only (inputs are staged in, results staged out), so that the WHOLE S-step loop -- every kernel of every step with its
+// own schedule scalars -- can be captured once into a CUDA graph and replayed by later calls with the same shape /
+// schedule: arena addresses are a deterministic function of the arena mark at entry, which is part of the
+// cache key.  First call with a key: eager; second call: capture + instantiate + launch; afterwards: one cudaGraphLaunch.
+struct DdimBufs {
+  float *xa, *xb, *p0, *x9, *eps, *ctx, *z, *mask, *o_x0, *o_ix, *o_ip;
+  long long* ts;
+};
+
+static int ddim_body(Ctx& c, UNet& u, DdimBufs b, int B, int L, int T, const DdimSchedule& s, float scale, bool cfg,
+                     const float* noise, int log_every_t) {
+  const long long HW = (long long)L * L, cnt = (long long)B * 4 * HW;
+  const int dup = cfg ? 2 : 1, N = dup * B;
+  // step-invariant terms, computed once per sampling run (SURVEY 8f-1): the cross-attention vectors depend on
+  // the context only; every sample shares the step's timestep, so one time-embedding row serves the batch.
+  UNetAux aux;
+  aux.uniform_t = 1;
+  aux.cfg_dup = cfg ? 1 : 0;
+  aux.crossvec = unet_cross_vectors(c, u, b.ctx, N, T);
+  int n_inter = 0;
+  float *xa = b.xa, *xb = b.xb;
+  for (int i = 0; i < s.n; ++i) {
+    const int index = s.n - 1 - i;
+    concat9(c, xa, b.z, b.mask, b.x9, B, (int)HW, dup);
+    unet_forward(c, u, b.x9, b.ts + (size_t)index * N, b.ctx, N, L, T, b.eps, &aux);
+    cfg_ddim_update(c, xa, b.eps, noise ? noise + (size_t)i * cnt : nullptr, xb, b.p0, cnt, scale, s.a_t[index],
+                    s.a_prev[index], s.sigma[index], s.sqrt_one_minus_a[index], cfg ? 1 : 0);
+    std::swap(xa, xb);
+    if (log_every_t > 0 && (index % log_every_t == 0 || index == s.n - 1)) {  // ddim.py:247-249
+      CUDA_OK(cudaMemcpyAsync(b.o_ix + (size_t)n_inter * cnt, xa, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+      CUDA_OK(cudaMemcpyAsync(b.o_ip + (size_t)n_inter * cnt, b.p0, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+      ++n_inter;
+    }
+  }
+  CUDA_OK(cudaMemcpyAsync(b.o_x0, xa, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  return n_inter;
+}
+
 void ddim_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, const float* mask, const float* cond,
                  const float* uncond, int B, int L, int T, const DdimSchedule& s, float scale, const float* noise,
                  float* x0_out, float* inter_x, float* inter_p0, int log_every_t) {
@@ -389,53 +428,92 @@ void ddim_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, cons
   const long long HW = (long long)L * L, cnt = (long long)B * 4 * HW;
   const bool cfg = uncond != nullptr && scale != 1.0f;  // ddim.py:335
   const int dup = cfg ? 2 : 1, N = dup * B;
-  float* xa = c.alloc_t<float>(cnt);
-  float* xb = c.alloc_t<float>(cnt);
-  float* p0 = c.alloc_t<float>(cnt);
-  float* x9 = c.alloc_t<float>((size_t)N * 9 * HW);
-  float* eps = c.alloc_t<float>((size_t)N * 4 * HW);
-  float* ctx = c.alloc_t<float>((size_t)N * T * 768);
-  long long* ts = c.alloc_t<long long>((size_t)s.n * N);
+  int K = 0;  // logged intermediates
+  for (int index = 0; index < s.n; ++index)
+    if (log_every_t > 0 && (index % log_every_t == 0 || index == s.n - 1)) ++K;
+  DdimBufs b;
+  b.xa = c.alloc_t<float>(cnt), b.xb = c.alloc_t<float>(cnt), b.p0 = c.alloc_t<float>(cnt);
+  b.x9 = c.alloc_t<float>((size_t)N * 9 * HW), b.eps = c.alloc_t<float>((size_t)N * 4 * HW);
+  b.ctx = c.alloc_t<float>((size_t)N * T * 768);
+  b.z = c.alloc_t<float>(cnt), b.mask = c.alloc_t<float>((size_t)B * HW);
+  b.o_x0 = c.alloc_t<float>(cnt);
+  b.o_ix = c.alloc_t<float>((size_t)std::max(K, 1) * cnt), b.o_ip = c.alloc_t<float>((size_t)std::max(K, 1) * cnt);
+  b.ts = c.alloc_t<long long>((size_t)s.n * N);
+  // ---- prologue on the caller's stream: stage the inputs into the arena
   {
     std::vector<long long> h((size_t)s.n * N);
     for (int i = 0; i < s.n; ++i)
       for (int j = 0; j < N; ++j) h[(size_t)i * N + j] = s.timesteps[i];
-    CUDA_OK(cudaMemcpyAsync(ts, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+    CUDA_OK(cudaMemcpyAsync(b.ts, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
     CUDA_OK(cudaStreamSynchronize(c.stream));  // h goes out of scope
   }
   const size_t cb = (size_t)B * T * 768 * sizeof(float);
   if (cfg) {  // c_in = cat([uc, c])  ddim.py:344
-    CUDA_OK(cudaMemcpyAsync(ctx, uncond, cb, cudaMemcpyDeviceToDevice, c.stream));
-    CUDA_OK(cudaMemcpyAsync(ctx + (size_t)B * T * 768, cond, cb, cudaMemcpyDeviceToDevice, c.stream));
+    CUDA_OK(cudaMemcpyAsync(b.ctx, uncond, cb, cudaMemcpyDeviceToDevice, c.stream));
+    CUDA_OK(cudaMemcpyAsync(b.ctx + (size_t)B * T * 768, cond, cb, cudaMemcpyDeviceToDevice, c.stream));
   } else {
-    CUDA_OK(cudaMemcpyAsync(ctx, cond, cb, cudaMemcpyDeviceToDevice, c.stream));
+    CUDA_OK(cudaMemcpyAsync(b.ctx, cond, cb, cudaMemcpyDeviceToDevice, c.stream));
   }
-  CUDA_OK(cudaMemcpyAsync(xa, x_T, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
-  // step-invariant terms, computed once per sampling run (SURVEY 8f-1): the cross-attention vectors depend on
-  // the context only; every sample shares the step's timestep, so one time-embedding row serves the batch.
-  UNetAux aux;
-  aux.uniform_t = 1;
-  aux.cfg_dup = cfg ? 1 : 0;
-  aux.crossvec = unet_cross_vectors(c, u, ctx, N, T);
-  int n_inter = 0;
-  for (int i = 0; i < s.n; ++i) {
-    const int index = s.n - 1 - i;
-    concat9(c, xa, z_inpaint, mask, x9, B, (int)HW, dup);
-    unet_forward(c, u, x9, ts + (size_t)index * N, ctx, N, L, T, eps, &aux);
-    cfg_ddim_update(c, xa, eps, noise ? noise + (size_t)i * cnt : nullptr, xb, p0, cnt, scale, s.a_t[index],
-                    s.a_prev[index], s.sigma[index], s.sqrt_one_minus_a[index], cfg ? 1 : 0);
-    std::swap(xa, xb);
-    if (log_every_t > 0 && (index % log_every_t == 0 || index == s.n - 1)) {  // ddim.py:247-249
-      if (inter_x)
-        CUDA_OK(cudaMemcpyAsync(inter_x + (size_t)n_inter * cnt, xa, cnt * sizeof(float), cudaMemcpyDeviceToDevice,
-                                c.stream));
-      if (inter_p0)
-        CUDA_OK(cudaMemcpyAsync(inter_p0 + (size_t)n_inter * cnt, p0, cnt * sizeof(float), cudaMemcpyDeviceToDevice,
-                                c.stream));
-      ++n_inter;
+  CUDA_OK(cudaMemcpyAsync(b.xa, x_T, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  CUDA_OK(cudaMemcpyAsync(b.z, z_inpaint, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  CUDA_OK(cudaMemcpyAsync(b.mask, mask, (size_t)B * HW * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+
+  // ---- the loop: eager, or one graph launch
+  bool done = false;
+  if (c.use_graph && !c.profile && !c.gemm_debug && noise == nullptr) {
+    // key: everything the captured launches depend on besides the staged buffer contents
+    std::string key = "ddim";
+    auto add = [&](const void* p, size_t n) { key.append(reinterpret_cast<const char*>(p), n); };
+    const long long dims[8] = {B, L, T, s.n, log_every_t, cfg ? 1 : 0, (long long)mk, c.graph_epoch};
+    add(dims, sizeof(dims));
+    add(&scale, sizeof(scale));
+    add(s.timesteps.data(), s.timesteps.size() * sizeof(long long));
+    add(s.a_t.data(), s.a_t.size() * sizeof(float));
+    add(s.a_prev.data(), s.a_prev.size() * sizeof(float));
+    add(s.sigma.data(), s.sigma.size() * sizeof(float));
+    add(s.sqrt_one_minus_a.data(), s.sqrt_one_minus_a.size() * sizeof(float));
+    Ctx::GraphEntry& ge = c.graphs[key];
+    ++ge.seen;
+    if (!ge.exec && !ge.failed && ge.seen >= 2) {
+      if (!c.gstream) CUDA_OK(cudaStreamCreateWithFlags(&c.gstream, cudaStreamNonBlocking));
+      cudaStream_t user = c.stream;
+      const long long l0 = c.launches;
+      const size_t mk2 = c.mark();
+      c.stream = c.gstream;
+      cudaGraph_t graph = nullptr;
+      try {
+        CUDA_OK(cudaStreamBeginCapture(c.gstream, cudaStreamCaptureModeRelaxed));
+        ddim_body(c, u, b, B, L, T, s, scale, cfg, nullptr, log_every_t);
+        CUDA_OK(cudaStreamEndCapture(c.gstream, &graph));
+        CUDA_OK(cudaGraphInstantiate(&ge.exec, graph, 0));
+      } catch (const std::exception&) {
+        cudaGraph_t junk = nullptr;
+        cudaStreamEndCapture(c.gstream, &junk);  // leave capture mode whatever happened
+        if (junk) cudaGraphDestroy(junk);
+        cudaGetLastError();
+        ge.exec = nullptr, ge.failed = true;
+      }
+      if (graph) cudaGraphDestroy(graph);
+      c.stream = user;
+      c.release(mk2);
+      ge.launches = c.launches - l0;
+      c.launches = l0;
+    }
+    if (ge.exec) {
+      CUDA_OK(cudaGraphLaunch(ge.exec, c.stream));
+      c.launches += ge.launches;
+      c.graph_replays++;
+      done = true;
     }
   }
-  CUDA_OK(cudaMemcpyAsync(x0_out, xa, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  if (!done) ddim_body(c, u, b, B, L, T, s, scale, cfg, noise, log_every_t);
+
+  // ---- epilogue: results to the caller's buffers
+  CUDA_OK(cudaMemcpyAsync(x0_out, b.o_x0, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  if (K > 0 && inter_x)
+    CUDA_OK(cudaMemcpyAsync(inter_x, b.o_ix, (size_t)K * cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+  if (K > 0 && inter_p0)
+    CUDA_OK(cudaMemcpyAsync(inter_p0, b.o_ip, (size_t)K * cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
   c.release(mk);
 }
 

@@ -32,6 +32,7 @@ SIGNATURES = {
     "rfb_build_face_parser": (_i, [_vp, C.c_char_p]),
     "rfb_set_option": (_i, [_vp, C.c_char_p, _ll]),
     "rfb_launch_count": (_ll, [_vp]),
+    "rfb_graph_replays": (_ll, [_vp]),
     "rfb_arena_peak": (_sz, [_vp]),
     "rfb_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
     "rfb_debug_read": (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
@@ -180,6 +181,11 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.lib.rfb_launch_count(self.h))
+
+    @property
+    def graph_replays(self):
+        """How many sampling loops ran as ONE CUDA-graph launch (rfb_ddim_sample, option use_graph)."""
+        return int(self.lib.rfb_graph_replays(self.h))
 
     def profile_read(self):
         """(ms, algorithmic_flops, n_launches) of the tensor-core launches since option 'profile' was set."""

@@ -94,6 +94,39 @@ def test_ddim_loop_vs_reference_golden(unet_engine):
     assert perr < 5e-2, perr
 
 
+def test_sampling_loop_cuda_graph_replays_are_bit_exact(unet_engine):
+    """rfb_ddim_sample captures the whole S-step loop (every kernel of every step with its own schedule scalars) into ONE
+    CUDA graph the second time it sees a (shape, schedule, scale) and replays it afterwards.  Replays must be
+    the bits of the eager loop -- also for NEW inputs (inputs are staged into arena buffers the graph reads) -- and a
+    different schedule / option must not hit a stale graph."""
+    g = _g("ddim_S5_L16")
+    eng = unet_engine
+    args = (g["x_T"], g["z"], g["mask"], g["c"], g["uc"])
+    eng.set_option("use_graph", 0)
+    eager = [t.clone() for t in eng.ddim_sample(*args, S=5, scale=3.5, log_every_t=2)]
+    x2 = g["x_T"] * 0.5 + 0.1
+    eager2 = eng.ddim_sample(x2, g["z"], g["mask"], g["c"], g["uc"], S=5, scale=3.5, log_every_t=2)[0].clone()
+    eager_s6 = eng.ddim_sample(*args, S=6, scale=3.0, log_every_t=2)[0].clone()
+    eng.set_option("use_graph", 1)
+    r0 = eng.graph_replays
+    for i in range(3):                                   # 1st eager, 2nd capture + launch, 3rd replay
+        out = eng.ddim_sample(*args, S=5, scale=3.5, log_every_t=2)
+        for a, b in zip(out, eager):
+            assert torch.equal(a, b), i
+    assert eng.graph_replays - r0 == 2
+    l0 = eng.launch_count
+    assert torch.equal(eng.ddim_sample(x2, g["z"], g["mask"], g["c"], g["uc"], S=5, scale=3.5, log_every_t=2)[0], eager2)
+    assert eng.graph_replays - r0 == 3 and eng.launch_count - l0 > 1000      # replays count their kernels
+    assert torch.equal(eng.ddim_sample(*args, S=6, scale=3.0, log_every_t=2)[0], eager_s6)      # new key: eager again
+    assert eng.graph_replays - r0 == 3
+    eng.set_option("cfg_share", 0)                       # any option change drops the cached graphs
+    try:
+        assert torch.equal(eng.ddim_sample(*args, S=5, scale=3.5, log_every_t=2)[0], eager[0])
+        assert eng.graph_replays - r0 == 3
+    finally:
+        eng.set_option("cfg_share", 1)
+
+
 def test_cfg_head_sharing_is_bit_exact(unet_engine):
     """Inside the samplers the two CFG halves share their input and timestep (ddim.py:338-344): conv_in, the first
     ResBlock and attn1 of the first SpatialTransformer are computed once per pair (option cfg_share).  The results
