@@ -150,8 +150,11 @@ int rfb_op_linear(rfb_ctx* ctx, const float* x, const float* w, const float* bia
 /* Upsample.forward (openaimodel.py:109-119): conv3x3(nearest_2x(x)), x [N,C,H,W], w [O,C,3,3] -> [N,O,2H,2W]. */
 int rfb_op_upconv(rfb_ctx* ctx, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int O,
                   float* out, void* stream);
+/* gn_gamma/gn_beta != NULL: followed by GroupNorm(32, eps 1e-5) + SiLU (ResBlock in_layers / out_layers,
+ * openaimodel.py:202-206,226-230) whose statistics come out of the convolution's epilogue. */
 int rfb_op_conv2d(rfb_ctx* ctx, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int O,
-                  int ksz, int stride, int pad_t, int pad_l, int pad_b, int pad_r, float* out, void* stream);
+                  int ksz, int stride, int pad_t, int pad_l, int pad_b, int pad_r, const float* gn_gamma,
+                  const float* gn_beta, float* out, void* stream);
 /* x2 != NULL: GroupNorm(32) over the channel concatenation [x | x2], x2 [N2,C2,H,W] read at sample (n mod N2). */
 int rfb_op_groupnorm(rfb_ctx* ctx, const float* x, const float* gamma, const float* beta, int N, int C, int H, int W,
                      float eps, int silu, const float* x2, int C2, int N2, float* out, void* stream);

@@ -175,6 +175,7 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "attn_flash") c.attn_flash = (int)value;
   else if (k == "profile") c.profile = (int)value;
   else if (k == "gn_fused") c.gn_fused = (int)value;
+  else if (k == "gn_epi_stats") c.gn_epi_stats = (int)value;
   else if (k == "cfg_share") c.cfg_share = (int)value;
   else if (k == "gn_cluster") c.gn_cluster = (int)value;
   else if (k == "gn_fused_max_elems") c.gn_fused_max_elems = value;
@@ -540,7 +541,8 @@ int rfb_op_upconv(rfb_ctx* h, const float* x, const float* w, const float* bias,
 }
 
 int rfb_op_conv2d(rfb_ctx* h, const float* x, const float* w, const float* bias, int N, int C, int H, int W, int O,
-                  int ksz, int stride, int pad_t, int pad_l, int pad_b, int pad_r, float* out, void* stream) {
+                  int ksz, int stride, int pad_t, int pad_l, int pad_b, int pad_r, const float* gn_gamma,
+                  const float* gn_beta, float* out, void* stream) {
   API_BEGIN(h)
   c.stream = (cudaStream_t)stream;
   const size_t mk = c.mark();
@@ -550,7 +552,10 @@ int rfb_op_conv2d(rfb_ctx* h, const float* x, const float* w, const float* bias,
     if (bias) tp.add("__op.b", bias, {O});
     ConvW cw = pack_conv(c, "__op.w", bias ? "__op.b" : "");
     Tens xt = from_nchw_f32(c, x, N, C, H, W, C);
-    Tens y = conv3x3_t(c, xt, cw, Epi(), stride, pad_t, pad_l, pad_b, pad_r);
+    Epi e;
+    e.want_stats = gn_gamma != nullptr;  // conv -> GroupNorm(32) + SiLU chain: statistics from the conv epilogue
+    Tens y = conv3x3_t(c, xt, cw, e, stride, pad_t, pad_l, pad_b, pad_r);
+    if (gn_gamma) y = groupnorm(c, y, gn_gamma, gn_beta, 1e-5f, true);
     to_nchw_f32(c, y, out);
   }
   c.release(mk);

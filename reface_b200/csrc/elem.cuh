@@ -284,6 +284,97 @@ gn_apply2_kernel(const GnSrc src, const float* __restrict__ partial, int nslab, 
   }
 }
 
+// GroupNorm from PRODUCER statistics: the GEMM / conv epilogue that wrote the tensor also left per-(32 rows, channel)
+// partial sums (gemm_epilogue.cuh, GemmArgs::stats: [rows / 32][C][2]).  gn_finalize3 folds them per (sample, group) in a
+// fixed order -> mean / rstd [N][G][2]; gn_apply3 is then a pure streaming pass (one read, one write).
+struct GnStatSrc {
+  const float* s1;
+  const float* s2;  // partials of the second concatenated tensor (nullptr: single source)
+  int C1, n2mod;
+};
+__global__ void gn_finalize3_kernel(const GnStatSrc st, float* __restrict__ out, int P, int HW, int C, int G, float eps) {
+  // grid (G, N); P = partial rows per sample (HW / 32); blockDim = 128
+  __shared__ float red[2][128];
+  const int gi = blockIdx.x, n = blockIdx.y;
+  const int cpg = C / G;
+  const int total = P * cpg;
+  float s = 0.f, ss = 0.f;
+  for (int i = threadIdx.x; i < total; i += 128) {
+    const int pr = i / cpg, ch = gi * cpg + (i - pr * cpg);
+    const float2 v = (st.s2 == nullptr || ch < st.C1)
+                         ? __ldg(reinterpret_cast<const float2*>(st.s1) + ((long long)n * P + pr) * st.C1 + ch)
+                         : __ldg(reinterpret_cast<const float2*>(st.s2) +
+                                 ((long long)(st.n2mod > 0 ? n % st.n2mod : n) * P + pr) * (C - st.C1) + (ch - st.C1));
+    s += v.x, ss += v.y;
+  }
+  red[0][threadIdx.x] = s, red[1][threadIdx.x] = ss;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + o];
+      red[1][threadIdx.x] += red[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float cnt = (float)cpg * (float)HW;
+    const float mean = red[0][0] / cnt;
+    const float var = fmaxf(red[1][0] / cnt - mean * mean, 0.f);
+    out[((long long)n * G + gi) * 2] = mean;
+    out[((long long)n * G + gi) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+__global__ void __launch_bounds__(512)
+gn_apply3_kernel(const GnSrc src, const float* __restrict__ stats, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, __half* __restrict__ y, int HW, int C, int G, int silu, int slab) {
+  __shared__ float st[64];  // mean / rstd per group (G <= 32)
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  if (threadIdx.x < 2 * G) st[threadIdx.x] = __ldg(stats + (long long)n * 2 * G + threadIdx.x);
+  __syncthreads();
+  const int cv = C >> 3;
+  const int R = blockDim.x / cv;
+  const int cq = threadIdx.x % cv, pr = threadIdx.x / cv;
+  if (pr >= R) return;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cq * 8 + j;
+    const int gi = c / cpg;
+    a[j] = st[2 * gi + 1] * __ldg(gamma + c);
+    b[j] = __ldg(beta + c) - st[2 * gi] * a[j];
+  }
+  const int p0 = blockIdx.x * slab;
+  const int p1 = min(HW, p0 + slab);
+  int xs;
+  const __half* xn = gn_src_ptr(src, n, HW, C, cq, xs);
+  __half* yn = y + (long long)n * HW * C + cq * 8;
+  for (int pb = p0 + pr; pb < p1; pb += 4 * R) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = pb + k * R;
+      if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * xs));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = pb + k * R;
+      if (p < p1) {
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_h2(w[t]);
+          float v0 = fmaf(f.x, a[2 * t], b[2 * t]), v1 = fmaf(f.y, a[2 * t + 1], b[2 * t + 1]);
+          if (silu) v0 = fast_silu(v0), v1 = fast_silu(v1);
+          o[t] = pack_h2(v0, v1);
+        }
+        *reinterpret_cast<uint4*>(yn + (long long)p * C) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
 // Single-launch GroupNorm: the CTAs of one sample (gridDim.x = cluster size, 8 or 16) form a thread-block cluster.  Each CTA reduces its pixel
 // slab (fp32 sums, fixed order), the per-group partials are exchanged through distributed shared memory and folded in
 // rank order (bitwise reproducible and independent of the batch size), then the CTA normalises the slab it has just

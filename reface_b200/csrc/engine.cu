@@ -299,11 +299,17 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   }
 }
 
+// The epilogue can leave GroupNorm partial statistics only on its vectorised fp16 path (gemm_epilogue.cuh, EPI_FAST).
+static bool epi_stats_ok(const Ctx& c, const Epi& e, int N, long long ldo, long long rows_per_sample) {
+  return c.gn_epi_stats && e.want_stats && !e.geglu && e.act == 0 && !e.relu_after_res && e.out32 == nullptr &&
+         e.alpha == 1.0f && (N & 7) == 0 && ldo == N && (!e.res || (e.ldr & 7) == 0) && rows_per_sample % 32 == 0;
+}
 static void fill_epi(GemmArgs& g, const Epi& e, __half* out, long long ldo) {
   g.alpha = e.alpha, g.bias = e.bias, g.rowvec = e.rowvec, g.rows_per_vec = e.rows_per_vec, g.ldv = e.ldv;
   g.act_param = e.act_param, g.act = e.act, g.geglu = e.geglu, g.res = e.res, g.ldr = e.ldr;
   g.relu_after_res = e.relu_after_res;
   g.res_mod = e.res_mod;
+  g.stats = e.stats_out;
   g.out = out, g.ldo = ldo, g.out32 = e.out32, g.o32_sn = e.o32_sn, g.o32_sp = e.o32_sp, g.o32_sc = e.o32_sc;
   g.o32_rpn = e.o32_rpn;
 }
@@ -387,6 +393,9 @@ Tens linear_t(Ctx& c, const Tens& x, const LinW& w, Epi e) {
   const int out_c = e.geglu ? w.out / 2 : w.out;
   Tens y = c.new_tens(x.n, x.h, x.w, out_c);
   if (!e.bias) e.bias = w.b;
+  e.stats_out = nullptr;
+  if (epi_stats_ok(c, e, w.out, out_c, (long long)x.h * x.w))
+    e.stats_out = y.stats = c.alloc_t<float>((size_t)(y.rows() / 32) * out_c * 2);
   gemm(c, x.p, x.c, x.rows(), x.c, w.w, w.kp, w.out, y.p, out_c, e);
   return y;
 }
@@ -422,11 +431,16 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
   if (!e.bias) e.bias = w.b;
   if (e.rowvec && e.rows_per_vec <= 1) e.rows_per_vec = Ho * Wo;
   const long long M = y.rows();
+  const bool tma_path = !(w.ksz == 1 && stride == 1) && conv_tma_ok(c, x, w, stride, pad_t, pad_l, pad_b, pad_r, Ho, Wo);
+  const bool split = tma_path && pick_ksplit(c, Ho * Wo, w.cout, 9 * (w.cin / 64), e, y.c) > 1;
+  e.stats_out = nullptr;
+  if (f16_out && !split && epi_stats_ok(c, e, w.cout, y.c, (long long)Ho * Wo))
+    e.stats_out = y.stats = c.alloc_t<float>((size_t)(M / 32) * y.c * 2);
   if (w.ksz == 1 && stride == 1) {
     gemm(c, x.p, x.c, M, x.c, w.w, w.kp, w.cout, y.p, y.c, e);
     return y;
   }
-  if (conv_tma_ok(c, x, w, stride, pad_t, pad_l, pad_b, pad_r, Ho, Wo)) {
+  if (tma_path) {
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.M = (int)M, g.N = w.cout, g.cblocks = w.cin / 64, g.nk = 9 * g.cblocks;
@@ -538,6 +552,9 @@ Tens upconv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e) {
   Tens y = c.new_tens(x.n, 2 * x.h, 2 * x.w, w.cout);
   if (!e.bias) e.bias = w.b;
   const long long M = x.rows();
+  e.stats_out = nullptr;
+  if (epi_stats_ok(c, e, w.cout, y.c, (long long)x.h * x.w))
+    e.stats_out = y.stats = c.alloc_t<float>((size_t)(y.rows() / 32) * y.c * 2);
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M = (int)M, g.N = w.cout, g.cblocks = w.cin / 64, g.nk = 4 * g.cblocks;
@@ -650,6 +667,21 @@ Tens groupnorm2(Ctx& c, const Tens& x1, const Tens& x2, const float* gamma, cons
   const int cv = C / 8;
   RFB_CHECK(cv <= 512, "GroupNorm: too many channels");
   int R = std::max(1, 512 / cv);
+  if (c.gn_epi_stats && x1.stats && (!x2.p || x2.stats) && HW % 32 == 0) {
+    // statistics came with the tensor(s) from the producing epilogue: fold them per (sample, group), then ONE streaming
+    // pass (the tensor is read once instead of twice)
+    float* st = c.alloc_t<float>((size_t)N * 32 * 2);
+    GnStatSrc ss{x1.stats, x2.p ? x2.stats : nullptr, x1.c, src.n2mod};
+    gn_finalize3_kernel<<<dim3(32, (unsigned)N), 128, 0, c.stream>>>(ss, st, HW / 32, HW, C, 32, eps);
+    LAUNCH_CHECK(c);
+    const int want = std::max(1, (8 * c.num_sms) / std::max(1, N));
+    const int slab = std::max(R, (HW + want - 1) / want);
+    dim3 g3((unsigned)((HW + slab - 1) / slab), (unsigned)N);
+    gn_apply3_kernel<<<g3, cv * R, 0, c.stream>>>(src, st, gamma, beta, y.p, HW, C, 32, silu ? 1 : 0, slab);
+    LAUNCH_CHECK(c);
+    c.release(mk);
+    return y;
+  }
   // One cluster launch for small and medium maps; the whole-grid two-launch path (statistics, apply with the finalize
   // folded in) for maps of >= gn_fused_max_elems elements per sample (64^2 x 640 and up, the VAE's 256^2 / 512^2 levels),
   // where 16 CTAs per sample are too few to stream from HBM (profiles/r01s2_micro_bench.txt).  The choice depends on the

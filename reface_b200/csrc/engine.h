@@ -21,6 +21,9 @@ struct Param {
 struct Tens {  // NHWC fp16 activation
   __half* p = nullptr;
   int n = 0, h = 0, w = 0, c = 0;
+  // GroupNorm partial statistics left by the producing GEMM / conv epilogue: [rows / 32][c][2] (sum, sum of squares of
+  // the fp16 values per 32-row chunk and channel); nullptr when the producer did not write them
+  float* stats = nullptr;
   long long rows() const { return (long long)n * h * w; }
 };
 
@@ -51,6 +54,8 @@ struct Epi {
   int relu_after_res = 0;  // ReLU after the residual add (needs the generic epilogue)
   const __half* res = nullptr;
   long long ldr = 0;
+  bool want_stats = false;  // ask the conv / linear launcher to leave GroupNorm partial statistics with the output (Tens::stats)
+  float* stats_out = nullptr;  // (set by the launcher)
   long long res_mod = 0;  // residual has only res_mod rows and is read at row (m mod res_mod) (CFG halves sharing a tensor)
   float alpha = 1.0f;
   float* out32 = nullptr;
@@ -89,6 +94,7 @@ struct Ctx {
   int conv_tma_stride2 = 1;  // stride-2 3x3 convs as implicit GEMM through strided TMA boxes (0: explicit im2col)
   int gemm_splitk = 1;   // 3-way split-K for the long-K 3x3 convs of <= 8x8 maps (slice count from the per-sample shape only)
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)
+  int gn_epi_stats = 1;  // GroupNorm from the producer epilogue's partial statistics where available (finalize + streaming apply)
   int gn_fused = 1;  // single-launch cluster GroupNorm (0: stats / finalize / apply kernels)
   long long gn_fused_max_elems = 2621440;  // = 64*64*640: per-sample H*W*C from which GroupNorm takes the whole-grid path
   int gn_cluster = 16, gn_threads = 512;  // fused GroupNorm: CTAs per sample (cluster size), threads per CTA

@@ -344,6 +344,41 @@ __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile&
         if (gm < g.M && unit * 8 < cvalid)
           *reinterpret_cast<uint4*>(g.out + t.zoff + epi_out_row(g, gm, t.z) * g.ldo + ocol0 + unit * 8) = val[i];
       }
+      if (MODE == EPI_FAST && g.stats) {
+        // GroupNorm statistics of the tile this warp has just produced (the consumer's first read of the tensor is gone):
+        // every lane holds 8 rows x 8 channels of the FINAL fp16 values; per-channel sum / sum of squares over those rows,
+        // then over the 4 lanes that share the channel unit (fixed order: bitwise reproducible, batch independent).
+        float cs[8], cq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[j] = cq[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + (lane >> 3);
+          if (t.m_base + row < g.M) {
+            const uint32_t w[4] = {val[i].x, val[i].y, val[i].z, val[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_h2(w[e]);
+              cs[2 * e] += f.x, cq[2 * e] = fmaf(f.x, f.x, cq[2 * e]);
+              cs[2 * e + 1] += f.y, cq[2 * e + 1] = fmaf(f.y, f.y, cq[2 * e + 1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+          cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 8);
+          cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+          cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 16);
+        }
+        const int unit = lane & 7;
+        if (lane < 8 && unit * 8 < cvalid) {
+          const long long prow = g.up ? (t.m_base >> 5) * 4 + t.z : (t.m_base >> 5);
+          float4* sp = reinterpret_cast<float4*>(g.stats + (prow * g.N + ocol0 + unit * 8) * 2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sp[j] = make_float4(cs[2 * j], cq[2 * j], cs[2 * j + 1], cq[2 * j + 1]);
+        }
+      }
     }
   }
   __syncwarp();  // staging tiles / bias strip may be refilled by the next tile's prefetch

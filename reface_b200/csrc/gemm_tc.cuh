@@ -25,6 +25,10 @@ struct GemmArgs {
   // grid's z is the output phase (py, px) = (z >> 1, z & 1), tap (a, b) reads input pixel (y + a - 1 + py, x + b - 1 + px)
   // and the tile's rows are written to output pixels (2y + py, 2x + px) (input map: 2^up_wlog2 wide, 2^up_hwlog2 pixels)
   int ctw, up, up_wlog2, up_hwlog2;
+  // GroupNorm statistics from the epilogue: per 32 output rows (one epilogue warp's accumulator rows) and channel the sum
+  // and the sum of squares of the fp16 results, stats[(prow * N + col) * 2 + {0,1}], prow = m / 32 (folded upsample conv:
+  // (m / 32) * 4 + phase, which keeps every sample's partial rows contiguous).  nullptr: off.
+  float* stats;
   // A_PLAIN over TWO row-aligned sources (channel concatenation without the copy): k-blocks [0, nk1) come from tmA, the
   // rest from tmA2; a2_mod > 0: source 2 has only a2_mod rows and is read at row (m mod a2_mod) (CFG halves sharing a tensor)
   int nk1, a2_mod;

@@ -185,6 +185,7 @@ static Tens run_res(Ctx& c, const ResW& r, const Tens& x, const float* emb_all, 
   Tens h = groupnorm2(c, x, x2, r.g1, r.b1, 1e-5f, true);
   Epi e1;
   e1.rowvec = emb_all + r.emb_off, e1.ldv = emb_rows == 1 ? 0 : emb_ld;
+  e1.want_stats = true;  // h1 feeds GroupNorm: its statistics come out of this conv's epilogue
   Tens h1 = conv3x3_t(c, h, r.c1, e1);
   Tens h2 = groupnorm(c, h1, r.g2, r.b2, 1e-5f, true);
   Tens skip = x;
@@ -200,6 +201,7 @@ static Tens run_res(Ctx& c, const ResW& r, const Tens& x, const float* emb_all, 
   }
   Epi e2;
   e2.res = skip.p, e2.ldr = skip.c;
+  e2.want_stats = true;  // the block output feeds the next block's GroupNorm
   return conv3x3_t(c, h2, r.c2, e2);
 }
 
@@ -262,6 +264,7 @@ static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T,
   Tens h2 = linear_t(c, ff, s.ff2, e2);
   Epi e3;
   e3.res = x.p, e3.ldr = C, e3.res_mod = xres_mod;
+  e3.want_stats = true;
   return conv3x3_t(c, h2, s.proj_out, e3, 1, 0, 0, 0, 0);
 }
 
@@ -292,6 +295,11 @@ struct RunState {
   int st_idx;
 };
 
+static Epi stats_epi() {  // plain epilogue that also leaves GroupNorm partial statistics with the output
+  Epi e;
+  e.want_stats = true;
+  return e;
+}
 // cat.p != nullptr: the first op (a ResBlock) consumes torch.cat([h, cat], 1)
 static Tens run_ops(Ctx& c, const std::vector<UOp>& ops, Tens h, RunState& rs, Tens cat = Tens()) {
   for (const UOp& op : ops) {
@@ -305,9 +313,9 @@ static Tens run_ops(Ctx& c, const std::vector<UOp>& ops, Tens h, RunState& rs, T
         h = run_st(c, op.st, h, rs.ctx, rs.T, rs.N, pre);
         ++rs.st_idx;
       } break;
-      case OP_DOWN: h = conv3x3_t(c, h, op.conv, Epi(), 2, 1, 1, 1, 1); break;
-      case OP_UP: h = upconv3x3_t(c, h, op.conv, Epi()); break;
-      case OP_CONV_IN: h = conv3x3_t(c, h, op.conv, Epi()); break;
+      case OP_DOWN: h = conv3x3_t(c, h, op.conv, stats_epi(), 2, 1, 1, 1, 1); break;
+      case OP_UP: h = upconv3x3_t(c, h, op.conv, stats_epi()); break;
+      case OP_CONV_IN: h = conv3x3_t(c, h, op.conv, stats_epi()); break;
     }
   }
   return h;
@@ -351,7 +359,7 @@ void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const fl
   if (share) {
     // CFG batch: the two halves only differ in the context, which first enters in attn2 of input_blocks.1
     Tens x8 = from_nchw_f32(c, x9, N / 2, u.cfg.in_channels, L, L, u.cfg.in_channels);
-    Tens h0 = conv3x3_t(c, x8, u.inp[0][0].conv, Epi());
+    Tens h0 = conv3x3_t(c, x8, u.inp[0][0].conv, stats_epi());
     hs.push_back(h0);  // N/2 samples: the consumers (last output block) read it modulo its sample count
     Tens r = run_res(c, u.inp[1][0].res, h0, rs.emb, rs.emb_rows, rs.emb_ld);
     const float* pre = !aux->crossvec.empty() ? aux->crossvec[0] : nullptr;

@@ -56,7 +56,7 @@ SIGNATURES = {
     "rfb_target_clip_input": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "rfb_op_linear": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _i, _ll, _vp, _vp]),
     "rfb_op_upconv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
-    "rfb_op_conv2d": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rfb_op_conv2d": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "rfb_op_groupnorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _i, _i, _vp, _vp]),
     "rfb_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _f, _vp, _vp]),
     "rfb_op_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
@@ -403,15 +403,17 @@ class Engine:
         self._ck(self.lib.rfb_op_upconv(self.h, _ptr(x), _ptr(w), _ptr(bias), N, Cc, H, W, O, _ptr(out), self._stream()))
         return out
 
-    def op_conv2d(self, x, w, bias=None, stride=1, pad=(1, 1, 1, 1)):
+    def op_conv2d(self, x, w, bias=None, stride=1, pad=(1, 1, 1, 1), gn=None):
+        """gn=(gamma, beta): the convolution is followed by GroupNorm(32, eps 1e-5) + SiLU fed by epilogue statistics."""
         x, w, bias = self._in(x), self._in(w), self._in(bias)
+        gg, gb = (self._in(gn[0]), self._in(gn[1])) if gn is not None else (None, None)
         N, Cc, H, W = x.shape
         O, _, k, _ = w.shape
         pt, pl, pb, pr = pad
         Ho, Wo = (H + pt + pb - k) // stride + 1, (W + pl + pr - k) // stride + 1
         out = self._new(N, O, Ho, Wo)
         self._ck(self.lib.rfb_op_conv2d(self.h, _ptr(x), _ptr(w), _ptr(bias), N, Cc, H, W, O, k, stride, pt, pl, pb, pr,
-                                        _ptr(out), self._stream()))
+                                        _ptr(gg), _ptr(gb), _ptr(out), self._stream()))
         return out
 
     def op_groupnorm(self, x, gamma, beta, eps, silu=False, x2=None):

@@ -109,6 +109,26 @@ def test_groupnorm(engine, N, C, H, eps, silu, fused):
     assert float((y - ref).abs().max()) < 6e-3
 
 
+@pytest.mark.parametrize("N,C,O,H,k,stride", [(2, 320, 320, 64, 3, 1), (2, 640, 1280, 16, 3, 1), (3, 320, 640, 32, 1, 1),
+                                              (2, 320, 320, 32, 3, 2), (1, 128, 320, 16, 3, 1), (2, 1280, 1280, 8, 3, 1)])
+def test_groupnorm_from_epilogue_statistics(engine, N, C, O, H, k, stride):
+    """conv -> GroupNorm(32) + SiLU (every ResBlock): the convolution's epilogue leaves per-(32 rows, channel) partial
+    sums with its output, GroupNorm folds them and makes ONE streaming pass.  Same result as the stand-alone kernels
+    (fp32 statistics of the same fp16 values); the 8x8 case takes the split-K conv, which falls back to them."""
+    x, w, b = h(rn(N, C, H, H, seed=1)), h(rn(O, C, k, k, seed=2) / math.sqrt(k * k * C)), rn(O, seed=3)
+    gam, bet = 1 + 0.1 * rn(O, seed=4), 0.1 * rn(O, seed=5)
+    p = (k // 2,) * 4
+    y = engine.op_conv2d(x, w, b, stride=stride, pad=p, gn=(gam, bet))
+    engine.set_option("gn_epi_stats", 0)
+    try:
+        y0 = engine.op_conv2d(x, w, b, stride=stride, pad=p, gn=(gam, bet))
+    finally:
+        engine.set_option("gn_epi_stats", 1)
+    ref = F.silu(F.group_norm(F.conv2d(x, w, b, stride=stride, padding=k // 2), 32, gam, bet, 1e-5))
+    assert float((y - ref).abs().max()) < 8e-3 and float((y0 - ref).abs().max()) < 8e-3
+    assert float((y - y0).abs().max()) < 2e-3          # only the summation order of the statistics differs
+
+
 @pytest.mark.parametrize("N,N2,C1,C2,H", [(2, 2, 1280, 640, 8), (4, 2, 320, 320, 16), (2, 2, 640, 320, 32), (2, 1, 1280, 1280, 8),
                                           (2, 2, 640, 320, 64)])
 @pytest.mark.parametrize("fused", [1, 0])
