@@ -616,7 +616,8 @@ int rfb_op_attention(rfb_ctx* h, const float* qkv, int N, int L, int heads, int 
 }
 
 /* Kernel-only timing of the HBM-bound normalisation ops on device-resident fp16 tensors (CUDA events on the
- * launching stream, `iters` back-to-back launches after one warm-up); kind 0 = GroupNorm(32)+SiLU, 1 = LayerNorm. */
+ * launching stream, `iters` back-to-back launches after one warm-up); kind 0 = GroupNorm(32)+SiLU, 1 = LayerNorm,
+ * 2 = GroupNorm(32)+SiLU fed by producer-epilogue statistics (finalize + one streaming pass). */
 int rfb_bench_norm(rfb_ctx* h, int kind, int N, int C, int H, int W, int iters, double* ms_per_launch, void* stream) {
   API_BEGIN(h)
   c.stream = (cudaStream_t)stream;
@@ -625,13 +626,17 @@ int rfb_bench_norm(rfb_ctx* h, int kind, int N, int C, int H, int W, int iters, 
   CUDA_OK(cudaMemsetAsync(x.p, 0x3c, (size_t)x.rows() * C * sizeof(__half), c.stream));  // 0x3c3c = 1.0586
   float* gb = c.alloc_t<float>((size_t)2 * C);
   CUDA_OK(cudaMemsetAsync(gb, 0, (size_t)2 * C * sizeof(float), c.stream));
+  if (kind == 2) {  // GroupNorm fed by producer statistics (finalize + streaming apply): any partial sums will do for timing
+    x.stats = c.alloc_t<float>((size_t)(x.rows() / 32) * C * 2);
+    CUDA_OK(cudaMemsetAsync(x.stats, 0, (size_t)(x.rows() / 32) * C * 2 * sizeof(float), c.stream));
+  }
   cudaEvent_t a, b;
   CUDA_OK(cudaEventCreate(&a));
   CUDA_OK(cudaEventCreate(&b));
   for (int it = -1; it < iters; ++it) {
     if (it == 0) CUDA_OK(cudaEventRecord(a, c.stream));
     const size_t m2 = c.mark();
-    if (kind == 0) groupnorm(c, x, gb, gb + C, 1e-5f, true);
+    if (kind == 0 || kind == 2) groupnorm(c, x, gb, gb + C, 1e-5f, true);
     else layernorm(c, x, gb, gb + C, 1e-5f);
     c.release(m2);
   }

@@ -292,36 +292,44 @@ struct GnStatSrc {
   const float* s2;  // partials of the second concatenated tensor (nullptr: single source)
   int C1, n2mod;
 };
-__global__ void gn_finalize3_kernel(const GnStatSrc st, float* __restrict__ out, int P, int HW, int C, int G, float eps) {
-  // grid (G, N); P = partial rows per sample (HW / 32); blockDim = 128
-  __shared__ float red[2][128];
-  const int gi = blockIdx.x, n = blockIdx.y;
-  const int cpg = C / G;
-  const int total = P * cpg;
+__global__ void __launch_bounds__(256)
+gn_finalize3_kernel(const GnStatSrc st, float* __restrict__ out, int P, int HW, int C, int G, float eps) {
+  // grid (G / 4, N): one block folds FOUR consecutive groups (4 * cpg contiguous channels) of one sample.  Thread t owns
+  // channel (t mod W) of that range (W = 4 * cpg <= 256) and partial rows t / W, t / W + R, ...: consecutive threads read
+  // consecutive float2 (coalesced 8-byte loads), every thread's own sum runs in row order, the R row-phases and then the
+  // cpg channels of a group are folded in a fixed order -> bitwise reproducible, independent of the batch size.
+  __shared__ float2 red[256];
+  const int n = blockIdx.y, g0 = blockIdx.x * 4;
+  const int cpg = C / G, W = 4 * cpg;
+  const int R = 256 / W;
+  const int ci = threadIdx.x % W, rp = threadIdx.x / W;
   float s = 0.f, ss = 0.f;
-  for (int i = threadIdx.x; i < total; i += 128) {
-    const int pr = i / cpg, ch = gi * cpg + (i - pr * cpg);
-    const float2 v = (st.s2 == nullptr || ch < st.C1)
-                         ? __ldg(reinterpret_cast<const float2*>(st.s1) + ((long long)n * P + pr) * st.C1 + ch)
-                         : __ldg(reinterpret_cast<const float2*>(st.s2) +
-                                 ((long long)(st.n2mod > 0 ? n % st.n2mod : n) * P + pr) * (C - st.C1) + (ch - st.C1));
-    s += v.x, ss += v.y;
-  }
-  red[0][threadIdx.x] = s, red[1][threadIdx.x] = ss;
-  __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      red[0][threadIdx.x] += red[0][threadIdx.x + o];
-      red[1][threadIdx.x] += red[1][threadIdx.x + o];
+  if (rp < R) {
+    const int ch = g0 * cpg + ci;
+    const bool first = st.s2 == nullptr || ch < st.C1;
+    const int Cs = first ? st.C1 : C - st.C1;
+    const float2* base = first ? reinterpret_cast<const float2*>(st.s1) + (long long)n * P * Cs + ch
+                               : reinterpret_cast<const float2*>(st.s2) +
+                                     (long long)(st.n2mod > 0 ? n % st.n2mod : n) * P * Cs + (ch - st.C1);
+    for (int pr = rp; pr < P; pr += R) {
+      const float2 v = __ldg(base + (long long)pr * Cs);
+      s += v.x, ss += v.y;
     }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  red[threadIdx.x] = make_float2(s, ss);
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float a = 0.f, b = 0.f;
+    for (int c = 0; c < cpg; ++c)
+      for (int r = 0; r < R; ++r) {
+        const float2 v = red[r * W + threadIdx.x * cpg + c];
+        a += v.x, b += v.y;
+      }
     const float cnt = (float)cpg * (float)HW;
-    const float mean = red[0][0] / cnt;
-    const float var = fmaxf(red[1][0] / cnt - mean * mean, 0.f);
-    out[((long long)n * G + gi) * 2] = mean;
-    out[((long long)n * G + gi) * 2 + 1] = rsqrtf(var + eps);
+    const float mean = a / cnt;
+    const float var = fmaxf(b / cnt - mean * mean, 0.f);
+    out[((long long)n * G + g0 + threadIdx.x) * 2] = mean;
+    out[((long long)n * G + g0 + threadIdx.x) * 2 + 1] = rsqrtf(var + eps);
   }
 }
 __global__ void __launch_bounds__(512)

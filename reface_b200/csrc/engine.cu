@@ -672,7 +672,8 @@ Tens groupnorm2(Ctx& c, const Tens& x1, const Tens& x2, const float* gamma, cons
     // pass (the tensor is read once instead of twice)
     float* st = c.alloc_t<float>((size_t)N * 32 * 2);
     GnStatSrc ss{x1.stats, x2.p ? x2.stats : nullptr, x1.c, src.n2mod};
-    gn_finalize3_kernel<<<dim3(32, (unsigned)N), 128, 0, c.stream>>>(ss, st, HW / 32, HW, C, 32, eps);
+    RFB_CHECK(C / 32 * 4 <= 256, "GroupNorm finalize: more than 64 channels per group");
+    gn_finalize3_kernel<<<dim3(8, (unsigned)N), 256, 0, c.stream>>>(ss, st, HW / 32, HW, C, 32, eps);
     LAUNCH_CHECK(c);
     const int want = std::max(1, (8 * c.num_sms) / std::max(1, N));
     const int slab = std::max(R, (HW + want - 1) / want);

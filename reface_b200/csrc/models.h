@@ -59,8 +59,13 @@ struct UNetAux {                        // optional step-invariant inputs of a f
   // SpatialTransformer) is then computed once for both halves.
   int cfg_dup = 0;
   std::vector<const float*> crossvec;   // per SpatialTransformer (execution order): to_out(to_v(ctx)) [N, C]
+  // uniform_t only: this step's row of every ResBlock's emb_layers output (UNet::emb_cat), precomputed for all the
+  // steps of a sampling run (unet_time_embeddings); nullptr: computed inside the forward pass
+  const float* emb_all = nullptr;
 };
 std::vector<const float*> unet_cross_vectors(Ctx& c, UNet& u, const float* ctx, int N, int T);
+// emb_layers(SiLU(time_embed(timestep_embedding(t)))) of all ResBlocks for R timesteps: [R, u.emb_cat.out] (arena)
+float* unet_time_embeddings(Ctx& c, UNet& u, const long long* t, int R);
 void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const float* ctx, int N, int L, int T,
                   float* eps, const UNetAux* aux = nullptr);
 Tens cross_attention_general(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T, int N);

@@ -335,20 +335,29 @@ std::vector<const float*> unet_cross_vectors(Ctx& c, UNet& u, const float* ctx, 
   return out;
 }
 
+// timestep_embedding -> time_embed MLP (openaimodel.py:874-875) -> every ResBlock's emb_layers (openaimodel.py:264) for R
+// timesteps at once.  The rows do not depend on each other or on R (fixed K order per row): bitwise the per-call values.
+float* unet_time_embeddings(Ctx& c, UNet& u, const long long* t, int R) {
+  const int mc = u.cfg.model_channels;
+  float* emb_all = c.alloc_t<float>((size_t)R * u.emb_cat.out);
+  const size_t mk = c.mark();
+  float* temb = c.alloc_t<float>((size_t)R * mc);
+  float* e1 = c.alloc_t<float>((size_t)R * 4 * mc);
+  float* emb = c.alloc_t<float>((size_t)R * 4 * mc);
+  timestep_embedding(c, t, temb, R, mc);
+  linear_small(c, temb, mc, R, u.te0, e1, 4 * mc, 0, /*silu*/ 1);
+  linear_small(c, e1, 4 * mc, R, u.te2, emb, 4 * mc, 0, 0);
+  linear_small(c, emb, 4 * mc, R, u.emb_cat, emb_all, u.emb_cat.out, /*act_in=silu*/ 1, 0);
+  c.release(mk);
+  return emb_all;
+}
+
 void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const float* ctx, int N, int L, int T,
                   float* eps, const UNetAux* aux) {
   const size_t mk = c.mark();
-  const int mc = u.cfg.model_channels;
-  // time embedding MLP (openaimodel.py:874-875); one row is enough when all samples share the timestep
+  // one time-embedding row is enough when all samples share the timestep
   const int er = (aux && aux->uniform_t) ? 1 : N;
-  float* temb = c.alloc_t<float>((size_t)er * mc);
-  float* e1 = c.alloc_t<float>((size_t)er * 4 * mc);
-  float* emb = c.alloc_t<float>((size_t)er * 4 * mc);
-  timestep_embedding(c, t, temb, er, mc);
-  linear_small(c, temb, mc, er, u.te0, e1, 4 * mc, 0, /*silu*/ 1);
-  linear_small(c, e1, 4 * mc, er, u.te2, emb, 4 * mc, 0, 0);
-  float* emb_all = c.alloc_t<float>((size_t)er * u.emb_cat.out);
-  linear_small(c, emb, 4 * mc, er, u.emb_cat, emb_all, u.emb_cat.out, /*act_in=silu*/ 1, 0);
+  const float* emb_all = (aux && aux->uniform_t && aux->emb_all) ? aux->emb_all : unet_time_embeddings(c, u, t, er);
   RunState rs{emb_all, er, u.emb_cat.out, ctx, T, N, aux, 0};
   std::vector<Tens> hs;
   Tens h;
@@ -397,7 +406,7 @@ void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const fl
 // cache key.  First call with a key: eager; second call: capture + instantiate + launch; afterwards: one cudaGraphLaunch.
 struct DdimBufs {
   float *xa, *xb, *p0, *x9, *eps, *ctx, *z, *mask, *o_x0, *o_ix, *o_ip;
-  long long* ts;
+  long long *ts, *ts1;  // timesteps per (step, sample) / per step
 };
 
 static int ddim_body(Ctx& c, UNet& u, DdimBufs b, int B, int L, int T, const DdimSchedule& s, float scale, bool cfg,
@@ -410,10 +419,14 @@ static int ddim_body(Ctx& c, UNet& u, DdimBufs b, int B, int L, int T, const Ddi
   aux.uniform_t = 1;
   aux.cfg_dup = cfg ? 1 : 0;
   aux.crossvec = unet_cross_vectors(c, u, b.ctx, N, T);
+  // ... and so does the whole time-embedding path: emb_layers(time_embed(t)) for ALL steps in four launches
+  // (per step it streamed the 115 MB of fp32 emb_layers weights for a single row)
+  const float* emb_table = unet_time_embeddings(c, u, b.ts1, s.n);
   int n_inter = 0;
   float *xa = b.xa, *xb = b.xb;
   for (int i = 0; i < s.n; ++i) {
     const int index = s.n - 1 - i;
+    aux.emb_all = emb_table + (size_t)index * u.emb_cat.out;
     concat9(c, xa, b.z, b.mask, b.x9, B, (int)HW, dup);
     unet_forward(c, u, b.x9, b.ts + (size_t)index * N, b.ctx, N, L, T, b.eps, &aux);
     cfg_ddim_update(c, xa, b.eps, noise ? noise + (size_t)i * cnt : nullptr, xb, b.p0, cnt, scale, s.a_t[index],
@@ -446,12 +459,15 @@ void ddim_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, cons
   b.z = c.alloc_t<float>(cnt), b.mask = c.alloc_t<float>((size_t)B * HW);
   b.o_x0 = c.alloc_t<float>(cnt);
   b.o_ix = c.alloc_t<float>((size_t)std::max(K, 1) * cnt), b.o_ip = c.alloc_t<float>((size_t)std::max(K, 1) * cnt);
-  b.ts = c.alloc_t<long long>((size_t)s.n * N);
+  b.ts = c.alloc_t<long long>((size_t)s.n * N + s.n);
+  b.ts1 = b.ts + (size_t)s.n * N;
   // ---- prologue on the caller's stream: stage the inputs into the arena
   {
-    std::vector<long long> h((size_t)s.n * N);
-    for (int i = 0; i < s.n; ++i)
+    std::vector<long long> h((size_t)s.n * N + s.n);
+    for (int i = 0; i < s.n; ++i) {
       for (int j = 0; j < N; ++j) h[(size_t)i * N + j] = s.timesteps[i];
+      h[(size_t)s.n * N + i] = s.timesteps[i];
+    }
     CUDA_OK(cudaMemcpyAsync(b.ts, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
     CUDA_OK(cudaStreamSynchronize(c.stream));  // h goes out of scope
   }

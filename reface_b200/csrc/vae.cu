@@ -124,14 +124,20 @@ VAE* build_vae(Ctx& c, const std::string& pfx) {
   return v;
 }
 
+static Epi stats_epi() {  // plain epilogue that also leaves GroupNorm partial statistics with the output (engine.cu)
+  Epi e;
+  e.want_stats = true;
+  return e;
+}
 static Tens run_vres(Ctx& c, const VResW& r, const Tens& x) {  // model.py:121-141
   Tens h = groupnorm(c, x, r.g1, r.b1, 1e-6f, true);
-  Tens h1 = conv3x3_t(c, h, r.c1, Epi());
+  Tens h1 = conv3x3_t(c, h, r.c1, stats_epi());
   Tens h2 = groupnorm(c, h1, r.g2, r.b2, 1e-6f, true);
   Tens skip = x;
   if (r.skip) skip = conv3x3_t(c, x, r.nin, Epi(), 1, 0, 0, 0, 0);
   Epi e;
   e.res = skip.p, e.ldr = skip.c;
+  e.want_stats = true;  // every block output is normalised next (the following block, the attention block or norm_out)
   return conv3x3_t(c, h2, r.c2, e);
 }
 static Tens run_vattn(Ctx& c, const VAttnW& a, const Tens& x) {  // model.py:178-202
@@ -142,6 +148,7 @@ static Tens run_vattn(Ctx& c, const VAttnW& a, const Tens& x) {  // model.py:178
   attention(c, qkv.p, 3 * C, x.n, x.h * x.w, 1, C, o.p, C, 1.0f / sqrtf((float)C), 0, C, 2 * C);
   Epi e;
   e.res = x.p, e.ldr = C;
+  e.want_stats = true;
   return linear_t(c, o, a.proj, e);
 }
 
@@ -149,11 +156,11 @@ void vae_encode(Ctx& c, VAE& v, const float* img, const float* noise, int B, int
                 float* mean, float* logvar) {
   const size_t mk = c.mark();
   Tens h = from_nchw_f32(c, img, B, 3, H, W, 3);
-  h = conv3x3_t(c, h, v.e_in, Epi());
+  h = conv3x3_t(c, h, v.e_in, stats_epi());
   const int nlev = (int)v.mult.size();
   for (int l = 0; l < nlev; ++l) {
     for (auto& r : v.e_down[l]) h = run_vres(c, r, h);
-    if (l != nlev - 1) h = conv3x3_t(c, h, v.e_ds[l], Epi(), 2, 0, 0, 1, 1);  // model.py:72-79: pad (0,1,0,1), stride 2
+    if (l != nlev - 1) h = conv3x3_t(c, h, v.e_ds[l], stats_epi(), 2, 0, 0, 1, 1);  // model.py:72-79: pad (0,1,0,1), stride 2
   }
   h = run_vres(c, v.e_mid1, h);
   h = run_vattn(c, v.e_attn, h);
@@ -178,14 +185,14 @@ void vae_decode(Ctx& c, VAE& v, const float* z, int B, int hh, int ww, float inv
                                                                                hh * ww, 4, inv_scale);
   CUDA_OK(cudaGetLastError());
   c.launches++;
-  h = conv3x3_t(c, h, v.d_in, Epi());
+  h = conv3x3_t(c, h, v.d_in, stats_epi());
   h = run_vres(c, v.d_mid1, h);
   h = run_vattn(c, v.d_attn, h);
   h = run_vres(c, v.d_mid2, h);
   const int nlev = (int)v.mult.size();
   for (int l = nlev - 1; l >= 0; --l) {
     for (auto& r : v.d_up[l]) h = run_vres(c, r, h);
-    if (l != 0) h = upconv3x3_t(c, h, v.d_us[l], Epi());
+    if (l != 0) h = upconv3x3_t(c, h, v.d_us[l], stats_epi());
   }
   h = groupnorm(c, h, v.d_ng, v.d_nb, 1e-6f, true);
   const long long HW = (long long)h.h * h.w;

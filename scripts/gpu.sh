@@ -25,6 +25,8 @@ for task in "$@"; do
     stages) timeout 600 python scripts/stage_times.py > gpurun_out/${TAG}_stages.log 2>&1; tail -1 gpurun_out/${TAG}_stages.log ;;
     shapes) timeout 600 python scripts/gemm_shapes.py > gpurun_out/${TAG}_shapes${arg:+_$arg}.log 2>&1; head -45 gpurun_out/${TAG}_shapes${arg:+_$arg}.log; tail -1 gpurun_out/${TAG}_shapes${arg:+_$arg}.log ;;
     ab) IFS=';' read -ra SPECS <<< "$arg"; timeout 900 python scripts/unet_ab.py "${SPECS[@]}" > gpurun_out/${TAG}_ab.log 2>&1; tail -20 gpurun_out/${TAG}_ab.log ;;
+    unetlaunches) REPS=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${TAG}_unet_launches.csv python scripts/unet_once.py > gpurun_out/${TAG}_ncu_unet.log 2>&1
+              n=$(grep -o "launches per forward [0-9]*" gpurun_out/${TAG}_ncu_unet.log | grep -o "[0-9]*$"); python scripts/agg_launches.py gpurun_out/${TAG}_unet_launches.csv ${n:-0} > gpurun_out/${TAG}_unet_launches${arg:+_$arg}.txt; head -40 gpurun_out/${TAG}_unet_launches${arg:+_$arg}.txt; rm -f gpurun_out/${TAG}_unet_launches.csv ;;
     micro) timeout 900 python scripts/micro_bench.py > gpurun_out/${TAG}_micro.log 2>&1; tail -40 gpurun_out/${TAG}_micro.log ;;
     launches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip ${SKIP:-30000} -c ${COUNT:-9000} --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
               python scripts/agg_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches.txt; head -34 gpurun_out/${TAG}_launches.txt; rm -f gpurun_out/${TAG}_launches.csv ;;

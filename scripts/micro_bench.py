@@ -63,6 +63,9 @@ for (N, Cc, H) in [(16, 320, 64), (16, 640, 64), (16, 960, 64), (16, 640, 32), (
         ms = eng.bench_norm(0, N, Cc, H, H)
         row[name] = ms * 1e3
         txt.append(f"{name} {ms*1e3:6.1f} us ({gb / (ms * 1e-3) / HBM:.2f})")
+    ms = eng.bench_norm(2, N, Cc, H, H)
+    row["epi_stats"] = ms * 1e3
+    txt.append(f"epi_stats {ms*1e3:6.1f} us ({gb / (ms * 1e-3) / HBM:.2f})")
     print(f"groupnorm N={N} C={Cc} H={H}: " + "  ".join(txt), flush=True)
     out["groupnorm"].append(row)
 eng.set_option("gn_cluster", 16); eng.set_option("gn_threads", 512); eng.set_option("gn_fused_max_elems", 2621440); eng.set_option("gn_fused", 1)

@@ -17,7 +17,7 @@ inp = synth.synthetic_inputs(B, H, dev)
 
 
 def timed(fn, reps=2):
-    fn(); torch.cuda.synchronize()
+    fn(); fn(); torch.cuda.synchronize()      # two warm calls: the second one captures the sampling loop's CUDA graph
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
