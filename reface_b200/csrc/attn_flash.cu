@@ -409,10 +409,10 @@ struct Flash4Cfg {
   static constexpr int CHUNK = 128 * 128;
   static constexpr int Q_BYTES = 2 * CHUNK;
   static constexpr int XCHG_BYTES = 2 * 2 * 2 * 128 * 4;  // [group][tile parity][half][row]
-  static constexpr int SMEM = Q_BYTES + 2 * NS * CHUNK + XCHG_BYTES + 256;
+  static constexpr int SMEM = Q_BYTES + 2 * NS * CHUNK + XCHG_BYTES + 384;
 };
 
-template <int DP, int POLY, int NS>
+template <int DP, int POLY, int NS, int PINGPONG>
 __global__ void __launch_bounds__(576, 1)
 attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out, long long ldo, int L, int heads,
@@ -432,7 +432,9 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t b_q = bars, b_kf = bars + 8, b_ke = b_kf + 8 * NS, b_vf = b_ke + 8 * NS, b_ve = b_vf + 8 * NS;
   const uint32_t b_sfull = b_ve + 8 * NS, b_sfree = b_sfull + 16, b_pfull = b_sfree + 16, b_pfree = b_pfull + 16;
   const uint32_t tptr = b_pfree + 16;
-  static_assert(8 + 4 * 8 * NS + 64 + 8 <= 256, "barrier area");
+  // MUFU turn-taking (see the softmax warps): b_turn[q][g] = "group g of lane quadrant q may start its exponentials"
+  const uint32_t b_turn = tptr + 16;
+  static_assert(8 + 4 * 8 * NS + 64 + 16 + 64 <= 384, "barrier area");
 
   const int qt = blockIdx.x;  // pair of query tiles
   const int z = blockIdx.y;
@@ -458,6 +460,7 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(b_pfull + 8 * g, 8);
       mbar_init(b_pfree + 8 * g, 1);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(b_turn + 8 * i, 2);  // the two column-half warps of the other group arrive
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tptr, 512);
@@ -605,6 +608,18 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const bool any = __any_sync(0xffffffffu, need);
       float rs0 = 0.f, rs1 = 0.f;
       uint32_t pk[32];
+      // MUFU turn-taking.  The four softmax warps of a lane quadrant (two per query tile) share one SM sub-partition and
+      // its 4-lane MUFU unit.  Left alone they run in lock-step -- all four in the exponential phase (MUFU saturated),
+      // then all four in the TMEM load / row-max / P store phases (MUFU idle for ~600 of every ~2700 cycles, the 76 %
+      // of profiles/r01s2_attn_flash4_ncu_full.txt): a start-up stagger does not survive, the group that gets ahead
+      // runs alone at twice the rate until the MMA warp's in-order waits pin its lead at exactly one tile = in phase
+      // again.  So the two groups take explicit turns: group 1 starts its exponentials when group 0 has finished those of
+      // the same tile, group 0 when group 1 has finished the previous tile's; each group's load / max / store phases
+      // then overlap the other group's exponentials.
+      if (PINGPONG) {
+        if (g == 1) mbar_wait(b_turn + 8 * (q * 2 + 1), (uint32_t)j & 1u);
+        else if (j > 0) mbar_wait(b_turn + 8 * (q * 2), (uint32_t)(j - 1) & 1u);
+      }
       // POLY of every 8 exponentials (whole fp16 pairs) go to the FMA pipe.  A warp issues in order, so a warp that is
       // blocked on a full MUFU queue cannot reach polynomial work further down its stream: the two column halves of a
       // quadrant (which share an SM sub-partition) therefore run the two kinds in OPPOSITE order.
@@ -636,6 +651,10 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (((2 * i) & 7) < POLY) exp_pair(i, true);
       }
       l = fmaf(l, alpha, rs0 + rs1);
+      if (PINGPONG) {  // hand the MUFU unit to the other group's warps of this quadrant
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_turn + 8 * (q * 2 + (g ^ 1)));
+      }
       if (tw) RFB_STAMP(j, 7);
       if (j > 0) mbar_wait(bpfree, (uint32_t)(j - 1) & 1u);  // P.V(j-1) done: P free, O stable
       if (tw) RFB_STAMP(j, 8);
@@ -697,9 +716,10 @@ static void launch_flash4(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, 
   constexpr int NS = 4;
   using Cfg = Flash4Cfg<DP, NS>;
   if (c.first_use("flash4")) {
-    CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 0, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 2, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 4, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 0, NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 0, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 2, NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 2, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   }
   dim3 grid((unsigned)(L / 256), (unsigned)(N * heads));
   Ctx::ProfRec rec;
@@ -718,14 +738,17 @@ static void launch_flash4(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, 
     CUDA_OK(cudaMemsetAsync(c.dbg_buf, 0, (size_t)c.num_sms * 8 * sizeof(unsigned long long), c.stream));
     dbg = c.dbg_buf;
   }
-  switch (c.attn_poly) {
-    case 0: attn_flash4_kernel<DP, 0, NS><<<grid, 576, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg,
-                                                                                       c.attn_stagger); break;
-    case 4: attn_flash4_kernel<DP, 4, NS><<<grid, 576, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg,
-                                                                                       c.attn_stagger); break;
-    default: attn_flash4_kernel<DP, 2, NS><<<grid, 576, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg,
-                                                                                       c.attn_stagger); break;
+#define RFB_FLASH4(POLY_, PP_)                                                                                    \
+  attn_flash4_kernel<DP, POLY_, NS, PP_><<<grid, 576, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg, \
+                                                                             c.attn_stagger)
+  if (c.attn_poly) {
+    if (c.attn_pingpong) RFB_FLASH4(2, 1);
+    else RFB_FLASH4(2, 0);
+  } else {
+    if (c.attn_pingpong) RFB_FLASH4(0, 1);
+    else RFB_FLASH4(0, 0);
   }
+#undef RFB_FLASH4
   CUDA_OK(cudaGetLastError());
   c.launches++;
   if (c.profile) {

@@ -176,11 +176,13 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "profile") c.profile = (int)value;
   else if (k == "gn_fused") c.gn_fused = (int)value;
   else if (k == "gn_epi_stats") c.gn_epi_stats = (int)value;
+  else if (k == "gn_apply_bps") c.gn_apply_bps = (int)value;
   else if (k == "cfg_share") c.cfg_share = (int)value;
   else if (k == "gn_cluster") c.gn_cluster = (int)value;
   else if (k == "gn_fused_max_elems") c.gn_fused_max_elems = value;
   else if (k == "gn_threads") c.gn_threads = (int)value;
   else if (k == "attn_poly") c.attn_poly = (int)value;
+  else if (k == "attn_pingpong") c.attn_pingpong = (int)value;
   else if (k == "attn_pad") c.attn_pad = (int)value;
   else if (k == "attn_stagger") c.attn_stagger = (int)value;
   else if (k == "gemm_wave_bn") c.gemm_wave_bn = (int)value;

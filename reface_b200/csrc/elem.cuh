@@ -293,14 +293,17 @@ struct GnStatSrc {
   int C1, n2mod;
 };
 __global__ void __launch_bounds__(256)
-gn_finalize3_kernel(const GnStatSrc st, float* __restrict__ out, int P, int HW, int C, int G, float eps) {
-  // grid (G / 4, N): one block folds FOUR consecutive groups (4 * cpg contiguous channels) of one sample.  Thread t owns
-  // channel (t mod W) of that range (W = 4 * cpg <= 256) and partial rows t / W, t / W + R, ...: consecutive threads read
+gn_finalize3_kernel(const GnStatSrc st, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float2* __restrict__ ab, int P, int HW, int C, int G, int GPB, float eps) {
+  // grid (G / GPB, N): one block folds GPB consecutive groups (W = GPB * cpg <= 256 contiguous channels) of one sample.
+  // Thread t owns channel (t mod W) of that range and partial rows t / W, t / W + R, ...: consecutive threads read
   // consecutive float2 (coalesced 8-byte loads), every thread's own sum runs in row order, the R row-phases and then the
   // cpg channels of a group are folded in a fixed order -> bitwise reproducible, independent of the batch size.
+  // Output: per (sample, channel) the affine map of the normalisation, ab = (rstd * gamma, beta - mean * rstd * gamma).
   __shared__ float2 red[256];
-  const int n = blockIdx.y, g0 = blockIdx.x * 4;
-  const int cpg = C / G, W = 4 * cpg;
+  __shared__ float2 mr[8];
+  const int n = blockIdx.y, g0 = blockIdx.x * GPB;
+  const int cpg = C / G, W = GPB * cpg;
   const int R = 256 / W;
   const int ci = threadIdx.x % W, rp = threadIdx.x / W;
   float s = 0.f, ss = 0.f;
@@ -318,7 +321,7 @@ gn_finalize3_kernel(const GnStatSrc st, float* __restrict__ out, int P, int HW, 
   }
   red[threadIdx.x] = make_float2(s, ss);
   __syncthreads();
-  if (threadIdx.x < 4) {
+  if (threadIdx.x < GPB) {
     float a = 0.f, b = 0.f;
     for (int c = 0; c < cpg; ++c)
       for (int r = 0; r < R; ++r) {
@@ -328,44 +331,48 @@ gn_finalize3_kernel(const GnStatSrc st, float* __restrict__ out, int P, int HW, 
     const float cnt = (float)cpg * (float)HW;
     const float mean = a / cnt;
     const float var = fmaxf(b / cnt - mean * mean, 0.f);
-    out[((long long)n * G + g0 + threadIdx.x) * 2] = mean;
-    out[((long long)n * G + g0 + threadIdx.x) * 2 + 1] = rsqrtf(var + eps);
+    mr[threadIdx.x] = make_float2(mean, rsqrtf(var + eps));
+  }
+  __syncthreads();
+  if (threadIdx.x < W) {
+    const int ch = g0 * cpg + threadIdx.x;
+    const float2 m = mr[threadIdx.x / cpg];
+    const float a = m.y * __ldg(gamma + ch);
+    ab[(long long)n * C + ch] = make_float2(a, __ldg(beta + ch) - m.x * a);
   }
 }
+// y = x * a[n, c] + b[n, c] (* sigmoid): one read, one write.  A block streams `slab` pixels of one sample; a thread keeps
+// the affine map of its 8 channels in registers and has UB 16-byte loads in flight.
 __global__ void __launch_bounds__(512)
-gn_apply3_kernel(const GnSrc src, const float* __restrict__ stats, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, __half* __restrict__ y, int HW, int C, int G, int silu, int slab) {
-  __shared__ float st[64];  // mean / rstd per group (G <= 32)
+gn_apply3_kernel(const GnSrc src, const float2* __restrict__ ab, __half* __restrict__ y, int HW, int C, int silu, int slab) {
   const int n = blockIdx.y;
-  const int cpg = C / G;
-  if (threadIdx.x < 2 * G) st[threadIdx.x] = __ldg(stats + (long long)n * 2 * G + threadIdx.x);
-  __syncthreads();
   const int cv = C >> 3;
   const int R = blockDim.x / cv;
   const int cq = threadIdx.x % cv, pr = threadIdx.x / cv;
-  if (pr >= R) return;
   float a[8], b[8];
+  {
+    const float4* p = reinterpret_cast<const float4*>(ab + (long long)n * C + cq * 8);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cq * 8 + j;
-    const int gi = c / cpg;
-    a[j] = st[2 * gi + 1] * __ldg(gamma + c);
-    b[j] = __ldg(beta + c) - st[2 * gi] * a[j];
+    for (int j = 0; j < 4; ++j) {
+      const float4 v = __ldg(p + j);
+      a[2 * j] = v.x, b[2 * j] = v.y, a[2 * j + 1] = v.z, b[2 * j + 1] = v.w;
+    }
   }
   const int p0 = blockIdx.x * slab;
   const int p1 = min(HW, p0 + slab);
   int xs;
   const __half* xn = gn_src_ptr(src, n, HW, C, cq, xs);
   __half* yn = y + (long long)n * HW * C + cq * 8;
-  for (int pb = p0 + pr; pb < p1; pb += 4 * R) {
-    uint4 u[4];
+  constexpr int UB = 8;
+  for (int pb = p0 + pr; pb < p1; pb += UB * R) {
+    uint4 u[UB];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < UB; ++k) {
       const int p = pb + k * R;
       if (p < p1) u[k] = __ldg(reinterpret_cast<const uint4*>(xn + (long long)p * xs));
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < UB; ++k) {
       const int p = pb + k * R;
       if (p < p1) {
         const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};

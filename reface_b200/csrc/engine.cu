@@ -670,15 +670,19 @@ Tens groupnorm2(Ctx& c, const Tens& x1, const Tens& x2, const float* gamma, cons
   if (c.gn_epi_stats && x1.stats && (!x2.p || x2.stats) && HW % 32 == 0) {
     // statistics came with the tensor(s) from the producing epilogue: fold them per (sample, group), then ONE streaming
     // pass (the tensor is read once instead of twice)
-    float* st = c.alloc_t<float>((size_t)N * 32 * 2);
+    float2* ab = c.alloc_t<float2>((size_t)N * C);
     GnStatSrc ss{x1.stats, x2.p ? x2.stats : nullptr, x1.c, src.n2mod};
-    RFB_CHECK(C / 32 * 4 <= 256, "GroupNorm finalize: more than 64 channels per group");
-    gn_finalize3_kernel<<<dim3(8, (unsigned)N), 256, 0, c.stream>>>(ss, st, HW / 32, HW, C, 32, eps);
+    const int cpg = C / 32;
+    const int gpb = 4 * cpg <= 256 ? 4 : (2 * cpg <= 256 ? 2 : 1);
+    RFB_CHECK(cpg <= 256, "GroupNorm finalize: more than 256 channels per group");
+    gn_finalize3_kernel<<<dim3((unsigned)(32 / gpb), (unsigned)N), 256, 0, c.stream>>>(ss, gamma, beta, ab, HW / 32, HW, C, 32, gpb,
+                                                                                     eps);
     LAUNCH_CHECK(c);
-    const int want = std::max(1, (8 * c.num_sms) / std::max(1, N));
+    // gn_apply_bps blocks per SM over the whole batch; a function of the batch only through the work split, never the values
+    const int want = std::max(1, (c.gn_apply_bps * c.num_sms) / std::max(1, N));
     const int slab = std::max(R, (HW + want - 1) / want);
     dim3 g3((unsigned)((HW + slab - 1) / slab), (unsigned)N);
-    gn_apply3_kernel<<<g3, cv * R, 0, c.stream>>>(src, st, gamma, beta, y.p, HW, C, 32, silu ? 1 : 0, slab);
+    gn_apply3_kernel<<<g3, cv * R, 0, c.stream>>>(src, ab, y.p, HW, C, silu ? 1 : 0, slab);
     LAUNCH_CHECK(c);
     c.release(mk);
     return y;

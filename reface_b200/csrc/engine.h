@@ -89,12 +89,14 @@ struct Ctx {
   int gemm_pair = 0;
   int attn_stagger = 0;  // attention v4: cycles by which the second query tile's softmax starts late
   int attn_pad = 0;      // test hook: rfb_op_attention repacks q/k/v with 64-element head slices
+  int attn_pingpong = 1; // attention v4: the two query tiles' softmax warps take turns on the MUFU unit (see attn_flash.cu)
   int attn_poly = 0;     // attention v3/v4: exponentials per 8 evaluated on the FMA pipe (measured slower: off)
   int cfg_share = 1;     // samplers: compute the context-independent head of the UNet once per CFG pair
   int conv_tma_stride2 = 1;  // stride-2 3x3 convs as implicit GEMM through strided TMA boxes (0: explicit im2col)
   int gemm_splitk = 1;   // 3-way split-K for the long-K 3x3 convs of <= 8x8 maps (slice count from the per-sample shape only)
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)
   int gn_epi_stats = 1;  // GroupNorm from the producer epilogue's partial statistics where available (finalize + streaming apply)
+  int gn_apply_bps = 4;  // streaming GroupNorm apply: blocks per SM
   int gn_fused = 1;  // single-launch cluster GroupNorm (0: stats / finalize / apply kernels)
   long long gn_fused_max_elems = 2621440;  // = 64*64*640: per-sample H*W*C from which GroupNorm takes the whole-grid path
   int gn_cluster = 16, gn_threads = 512;  // fused GroupNorm: CTAs per sample (cluster size), threads per CTA

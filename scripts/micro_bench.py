@@ -25,10 +25,10 @@ for (N, L, heads, d) in ([] if os.environ.get("ONLY") == "gn" else [(16, 4096, 8
     q, k, v = qkv.chunk(3, dim=-1)
     sp = lambda t: t.reshape(N, L, heads, d).transpose(1, 2)
     ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(N, L, C)
-    for mode, poly, pad in ((4, 0, 0), (4, 2, 0), (4, 4, 0), (4, 0, 0), (4, 2, 0)):
+    for mode, poly, pad in ((4, 0, 0), (4, 0, 1), (4, 2, 1), (4, 0, 0), (4, 0, 1), (3, 0, 0)):   # pad = MUFU turn-taking on/off
         eng.set_option("attn_flash", mode)
         eng.set_option("attn_poly", poly)
-        eng.set_option("attn_stagger", pad)
+        eng.set_option("attn_pingpong", pad)
         y = eng.op_attention(qkv, heads)
         err = float((y - ref).abs().max())
         best = 1e9
@@ -40,13 +40,13 @@ for (N, L, heads, d) in ([] if os.environ.get("ONLY") == "gn" else [(16, 4096, 8
             best = min(best, ms)
         tf = 4.0 * L * L * d * N * heads / best / 1e9
         exps = N * heads * L * L / (best * 1e-3) / 1e12
-        print(f"attention v{mode} poly={poly} stagger={pad} N={N} L={L} d={d}: {best*1e3:8.1f} us  {tf:7.1f} TFLOP/s  {exps:5.2f} Texp/s  "
+        print(f"attention v{mode} poly={poly} pingpong={pad} N={N} L={L} d={d}: {best*1e3:8.1f} us  {tf:7.1f} TFLOP/s  {exps:5.2f} Texp/s  "
               f"max_err={err:.2e}", flush=True)
         out["attention"].append({"mode": mode, "poly": poly, "N": N, "L": L, "d": d, "us": best * 1e3, "tflops": tf, "err": err})
     del qkv, ref, y
 eng.set_option("attn_flash", 4)
 eng.set_option("attn_poly", 0)
-eng.set_option("attn_stagger", 0)
+eng.set_option("attn_pingpong", 1)
 if os.environ.get("ONLY") == "attn":
     sys.exit(0)
 if os.environ.get("ONLY") == "gn":
@@ -63,9 +63,12 @@ for (N, Cc, H) in [(16, 320, 64), (16, 640, 64), (16, 960, 64), (16, 640, 32), (
         ms = eng.bench_norm(0, N, Cc, H, H)
         row[name] = ms * 1e3
         txt.append(f"{name} {ms*1e3:6.1f} us ({gb / (ms * 1e-3) / HBM:.2f})")
-    ms = eng.bench_norm(2, N, Cc, H, H)
-    row["epi_stats"] = ms * 1e3
-    txt.append(f"epi_stats {ms*1e3:6.1f} us ({gb / (ms * 1e-3) / HBM:.2f})")
+    for bps in (2, 4, 8):
+        eng.set_option("gn_apply_bps", bps)
+        ms = eng.bench_norm(2, N, Cc, H, H)
+        row[f"epi_stats_bps{bps}"] = ms * 1e3
+        txt.append(f"epi_stats/bps{bps} {ms*1e3:6.1f} us ({gb / (ms * 1e-3) / HBM:.2f})")
+    eng.set_option("gn_apply_bps", 4)
     print(f"groupnorm N={N} C={Cc} H={H}: " + "  ".join(txt), flush=True)
     out["groupnorm"].append(row)
 eng.set_option("gn_cluster", 16); eng.set_option("gn_threads", 512); eng.set_option("gn_fused_max_elems", 2621440); eng.set_option("gn_fused", 1)
