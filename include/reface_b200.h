@@ -32,6 +32,11 @@ const char* rfb_last_error(rfb_ctx* ctx);
  * `data` may be a host or a device pointer (fp32). */
 int rfb_set_param(rfb_ctx* ctx, const char* name, const float* data, int ndim, const int64_t* shape);
 int rfb_has_param(rfb_ctx* ctx, const char* name);
+/* After the rfb_build_* calls: frees the fp32 device copies of every parameter that only served as the source of a
+ * packed fp16 GEMM operand (conv / linear weights: ~5 GB of the ~8 GB a full REFace checkpoint occupies); biases, norm
+ * vectors and the small fp32 GEMV weights the networks keep reading stay.  Returns the bytes freed.  Rebuilding a
+ * network afterwards requires registering its weights again (rfb_set_param). */
+long long rfb_release_packed_originals(rfb_ctx* ctx);
 /* Build the packed (fp16, implicit-GEMM layout) networks from the registered parameters.  `prefix` is the
  * state-dict prefix ("model.diffusion_model.", "first_stage_model.", "cond_stage_model.",
  * "face_ID_model.facenet.").  Replace the constructors reached through instantiate_from_config:

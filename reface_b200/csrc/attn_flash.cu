@@ -445,6 +445,10 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   do {                                                                       \
     if (trace && (j) < 32 && lane == 0) dbg[(j) * 16 + (slot)] = clock64();  \
   } while (0)
+#define RFB_STAMP1(j, slot) /* the second query tile's warp of the same sub-partition: second half of the buffer */ \
+  do {                                                                                                            \
+    if (trace && (j) < 32 && lane == 0) dbg[512 + (j) * 16 + (slot)] = clock64();                                 \
+  } while (0)
 
   if (threadIdx.x == 0) {
     mbar_init(b_q, 1);
@@ -562,7 +566,7 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t bsfull = b_sfull + 8 * g, bsfree = b_sfree + 8 * g, bpfull = b_pfull + 8 * g, bpfree = b_pfree + 8 * g;
     float* xch = reinterpret_cast<float*>(smem_raw + (sX - base)) + g * 512;  // [parity][half][row]
     const int bar_id = 1 + g * 4 + q;
-    const bool tw = (warp == 2);
+    const bool tw = (warp == 2), tw1 = (warp == 10);
     float m = 0.f, l = 0.f;
     if (g == 1 && stagger > 0) {
       // start the second query tile's softmax half a tile late: its TMEM load / max / P-store phases then overlap
@@ -574,6 +578,7 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(bsfull, (uint32_t)j & 1u);
       if (tw) RFB_STAMP(j, 4);
+      if (tw1) RFB_STAMP1(j, 4);
       tc_fence_after();
       uint32_t sv[64];
       tmem_ld32(tS + lane_off + 64 * hh, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
@@ -594,6 +599,7 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       xch[((j & 1) * 2 + hh) * 128 + r] = mh;
       named_bar_sync(bar_id, 64);
       if (tw) RFB_STAMP(j, 6);
+      if (tw1) RFB_STAMP1(j, 6);
       const float mo = xch[((j & 1) * 2 + (hh ^ 1)) * 128 + r];
       const float mnew = fmaxf(mh, mo) * scale_log2e;
       float alpha = 1.0f;
@@ -620,6 +626,8 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (g == 1) mbar_wait(b_turn + 8 * (q * 2 + 1), (uint32_t)j & 1u);
         else if (j > 0) mbar_wait(b_turn + 8 * (q * 2), (uint32_t)(j - 1) & 1u);
       }
+      if (tw) RFB_STAMP(j, 13);
+      if (tw1) RFB_STAMP1(j, 13);
       // POLY of every 8 exponentials (whole fp16 pairs) go to the FMA pipe.  A warp issues in order, so a warp that is
       // blocked on a full MUFU queue cannot reach polynomial work further down its stream: the two column halves of a
       // quadrant (which share an SM sub-partition) therefore run the two kinds in OPPOSITE order.
@@ -656,6 +664,7 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (lane == 0) mbar_arrive(b_turn + 8 * (q * 2 + (g ^ 1)));
       }
       if (tw) RFB_STAMP(j, 7);
+      if (tw1) RFB_STAMP1(j, 7);
       if (j > 0) mbar_wait(bpfree, (uint32_t)(j - 1) & 1u);  // P.V(j-1) done: P free, O stable
       if (tw) RFB_STAMP(j, 8);
       tc_fence_after();
@@ -676,6 +685,7 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(bpfull);
       if (tw) RFB_STAMP(j, 9);
+      if (tw1) RFB_STAMP1(j, 9);
     }
     mbar_wait(bpfree, (uint32_t)(ntiles - 1) & 1u);
     tc_fence_after();
@@ -708,6 +718,7 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tmem_dealloc(tmem_base, 512);
   }
 #undef RFB_STAMP
+#undef RFB_STAMP1
 }
 
 template <int DP>

@@ -135,6 +135,22 @@ int rfb_set_param(rfb_ctx* h, const char* name, const float* data, int ndim, con
   API_END
 }
 int rfb_has_param(rfb_ctx* h, const char* name) { return (h && h->c.has(name)) ? 1 : 0; }
+long long rfb_release_packed_originals(rfb_ctx* h) {
+  if (!h) return -1;
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  cudaDeviceSynchronize();  // pack kernels read the fp32 originals asynchronously
+  long long freed = 0;
+  for (auto& kv : c.params) {
+    Param& p = kv.second;
+    if (p.f32 && p.packed && !p.pinned && kv.first.rfind("__op.", 0) != 0) {
+      cudaFree(p.f32);
+      p.f32 = nullptr;
+      freed += (long long)(p.numel * sizeof(float));
+    }
+  }
+  return freed;
+}
 
 int rfb_build_unet(rfb_ctx* h, const char* prefix) {
   API_BEGIN(h)

@@ -343,7 +343,8 @@ gn_finalize3_kernel(const GnStatSrc st, const float* __restrict__ gamma, const f
 }
 // y = x * a[n, c] + b[n, c] (* sigmoid): one read, one write.  A block streams `slab` pixels of one sample; a thread keeps
 // the affine map of its 8 channels in registers and has UB 16-byte loads in flight.
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)  // <= 64 registers: the 90-register first version ran one block per SM and was
+                                           // latency-bound at 21 % warp occupancy (profiles/r02_gn3_ncu_full.txt)
 gn_apply3_kernel(const GnSrc src, const float2* __restrict__ ab, __half* __restrict__ y, int HW, int C, int silu, int slab) {
   const int n = blockIdx.y;
   const int cv = C >> 3;
@@ -363,7 +364,7 @@ gn_apply3_kernel(const GnSrc src, const float2* __restrict__ ab, __half* __restr
   int xs;
   const __half* xn = gn_src_ptr(src, n, HW, C, cq, xs);
   __half* yn = y + (long long)n * HW * C + cq * 8;
-  constexpr int UB = 8;
+  constexpr int UB = 4;
   for (int pb = p0 + pr; pb < p1; pb += UB * R) {
     uint4 u[UB];
 #pragma unroll

@@ -30,7 +30,15 @@ void* Ctx::dmalloc(size_t bytes) {
 const Param& Ctx::param(const std::string& name) const {
   auto it = params.find(name);
   if (it == params.end()) throw std::runtime_error("missing parameter: " + name);
+  if (!it->second.f32)
+    throw std::runtime_error("parameter " + name + " was released after packing (rfb_release_packed_originals): register it again");
+  it->second.packed = true;
   return it->second;
+}
+const float* Ctx::pf(const std::string& name) const {
+  const Param& p = param(name);
+  p.packed = false, p.pinned = true;
+  return p.f32;
 }
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -124,6 +132,7 @@ LinW pack_geglu(Ctx& c, const std::string& wname, const std::string& bname, int 
 }
 Lin32 lin32(Ctx& c, const std::string& wname, const std::string& bname) {
   const Param& p = c.param(wname);
+  p.pinned = true;
   Lin32 w;
   w.w = p.f32, w.out = (int)p.shape[0], w.in = (int)(p.numel / p.shape[0]);
   w.b = bname.empty() ? nullptr : c.pf(bname);

@@ -13,9 +13,12 @@
 namespace rfb {
 
 struct Param {
-  float* f32 = nullptr;  // device copy, fp32, original layout
+  float* f32 = nullptr;  // device copy, fp32, original layout (nullptr after rfb_release_packed_originals)
   std::vector<int64_t> shape;
   size_t numel = 0;
+  // how the builders used it: `packed` = converted into an fp16 GEMM operand (the fp32 original is then dead weight),
+  // `pinned` = a built model reads the fp32 buffer itself (biases, norm affine vectors, small-M GEMV weights)
+  mutable bool packed = false, pinned = false;
 };
 
 struct Tens {  // NHWC fp16 activation
@@ -145,8 +148,8 @@ struct Ctx {
     return t;
   }
   void* dmalloc(size_t bytes);  // persistent device allocation (weights)
-  const Param& param(const std::string& name) const;
-  const float* pf(const std::string& name) const { return param(name).f32; }
+  const Param& param(const std::string& name) const;  // for packing (marks it `packed`)
+  const float* pf(const std::string& name) const;      // fp32 buffer a model keeps reading (marks it `pinned`)
   bool has(const std::string& name) const { return params.count(name) != 0; }
 };
 

@@ -221,13 +221,15 @@ class LatentDiffusion:
             self.load_state_dict(state_dict)
 
     # -- weights
-    def load_state_dict(self, sd, strict=False):
+    def load_state_dict(self, sd, strict=False, release_originals=True):
         e = self.engine
         e.load_state_dict(sd)
         e.build_unet()
         e.build_vae()
         e.build_clip()
         e.build_arcface()
+        if release_originals:
+            e.release_packed_originals()      # keep the packed fp16 operands only (~2.7 GB instead of ~8 GB)
         self.learnable_vector = sd["learnable_vector"].to(self.device, torch.float32)
         return [], []
 

@@ -25,6 +25,7 @@ SIGNATURES = {
     "rfb_last_error": (C.c_char_p, [_vp]),
     "rfb_set_param": (_i, [_vp, C.c_char_p, _vp, _i, C.POINTER(C.c_int64)]),
     "rfb_has_param": (_i, [_vp, C.c_char_p]),
+    "rfb_release_packed_originals": (_ll, [_vp]),
     "rfb_build_unet": (_i, [_vp, C.c_char_p]),
     "rfb_build_vae": (_i, [_vp, C.c_char_p]),
     "rfb_build_clip": (_i, [_vp, C.c_char_p]),
@@ -158,6 +159,10 @@ class Engine:
             self._ck(self.lib.rfb_set_param(self.h, k.encode(), C.c_void_p(v.data_ptr()), max(1, v.dim()), shape))
             n += 1
         return n
+
+    def release_packed_originals(self):
+        """Frees the fp32 originals of weights that now live as packed fp16 operands; returns the bytes freed."""
+        return int(self.lib.rfb_release_packed_originals(self.h))
 
     def has_param(self, name):
         return bool(self.lib.rfb_has_param(self.h, name.encode()))

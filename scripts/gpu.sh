@@ -27,6 +27,11 @@ for task in "$@"; do
     ab) IFS=';' read -ra SPECS <<< "$arg"; timeout 900 python scripts/unet_ab.py "${SPECS[@]}" > gpurun_out/${TAG}_ab.log 2>&1; tail -20 gpurun_out/${TAG}_ab.log ;;
     unetlaunches) REPS=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${TAG}_unet_launches.csv python scripts/unet_once.py > gpurun_out/${TAG}_ncu_unet.log 2>&1
               n=$(grep -o "launches per forward [0-9]*" gpurun_out/${TAG}_ncu_unet.log | grep -o "[0-9]*$"); python scripts/agg_launches.py gpurun_out/${TAG}_unet_launches.csv ${n:-0} > gpurun_out/${TAG}_unet_launches${arg:+_$arg}.txt; head -40 gpurun_out/${TAG}_unet_launches${arg:+_$arg}.txt; rm -f gpurun_out/${TAG}_unet_launches.csv ;;
+    ncu) # ncu:<WHAT>:<kernel regex>  one --set full capture of the matching kernels of scripts/ncu_ops.py
+         what=${arg%%:*}; kre=${arg#*:}
+         WHAT=$what timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kre -c ${COUNT:-2} -o gpurun_out/${TAG}_$what -f python scripts/ncu_ops.py > gpurun_out/${TAG}_ncu_$what.log 2>&1
+         python scripts/ncu_summary.py gpurun_out/${TAG}_$what.ncu-rep > gpurun_out/${TAG}_${what}_ncu_full.txt 2>&1; cat gpurun_out/${TAG}_${what}_ncu_full.txt | head -60 ;;
+    trace) PINGPONG=${arg:-1} timeout 300 python scripts/attn_trace.py > gpurun_out/${TAG}_attn_trace_pp${arg:-1}.txt 2>&1; cat gpurun_out/${TAG}_attn_trace_pp${arg:-1}.txt | cut -c1-260 | head -26 ;;
     micro) timeout 900 python scripts/micro_bench.py > gpurun_out/${TAG}_micro.log 2>&1; tail -40 gpurun_out/${TAG}_micro.log ;;
     launches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip ${SKIP:-30000} -c ${COUNT:-9000} --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
               python scripts/agg_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches.txt; head -34 gpurun_out/${TAG}_launches.txt; rm -f gpurun_out/${TAG}_launches.csv ;;

@@ -15,6 +15,8 @@ if "attn" in what:
 if "gn" in what:
     eng.bench_norm(0, 16, 320, 64, 64, iters=1)
     eng.bench_norm(0, 8, 128, 512, 512, iters=1)
+if "gn3" in what:   # GroupNorm + SiLU fed by producer statistics: gn_finalize3 + gn_apply3 (streaming pass)
+    eng.bench_norm(2, 16, 320, 64, 64, iters=1)
 if "ln" in what:
     eng.bench_norm(1, 16, 320, 64, 64, iters=1)
 if "lin" in what:   # the HBM-bound K=320 projection of the 64x64 level with bias + residual (attn1.to_out / proj_out)
