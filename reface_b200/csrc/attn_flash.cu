@@ -100,16 +100,20 @@ struct Flash3Cfg {
   static constexpr int CHUNK = 128 * 128;
   static constexpr int Q_BYTES = NC * CHUNK;
   static constexpr int KV_BYTES = NC * CHUNK;
-  static constexpr int STAGES = 2;
   static constexpr int XCHG_BYTES = 2 * 2 * 128 * 4;  // row-max exchange [tile parity][half][row]
+  // K / V ring depth: two stages where they fit next to Q (head dim <= 128), one for the 160-wide heads of the 16x16 /
+  // 8x8 levels (L <= 256: at most two KV tiles anyway)
+  static constexpr int STAGES = (Q_BYTES + 4 * KV_BYTES + XCHG_BYTES + 128 <= 227 * 1024) ? 2 : 1;
   static constexpr int SMEM = Q_BYTES + 2 * STAGES * KV_BYTES + XCHG_BYTES + 128;
   static constexpr int TMEM_COLS = (DP <= 64) ? 256 : 512;
-  static constexpr int P_COL = (DP <= 64) ? 192 : 256;  // S [0,128) | O [128,128+DP) | P 64 columns
-  static constexpr int SPLIT = (DP <= 48) ? 24 : 40;    // output columns written by the first warp of a quadrant
+  static constexpr int P_COL = (DP <= 64) ? 192 : (DP <= 128 ? 256 : 320);  // S [0,128) | O [128,128+DP) | P 64 columns
+  static constexpr int SPLIT = (DP <= 48) ? 24 : (DP <= 64 ? 32 : (DP <= 80 ? 40 : 80));  // output columns of a quadrant's first warp
+  static constexpr int MIN_CTAS = (DP <= 64) ? 2 : 1;
+  static_assert(P_COL >= 128 + DP && P_COL + 64 <= TMEM_COLS, "TMEM layout");
 };
 
 template <int DP, int POLY>
-__global__ void __launch_bounds__(320, (DP <= 48) ? 2 : 1)
+__global__ void __launch_bounds__(320, Flash3Cfg<DP>::MIN_CTAS)
 attn_flash3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, __half* __restrict__ out, long long ldo, int L, int heads,
                    int d, float scale_log2e, unsigned long long* __restrict__ dbg) {
@@ -138,7 +142,7 @@ attn_flash3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int qt = blockIdx.x;
   const int z = blockIdx.y;
   const int n = z / heads, head = z % heads;
-  const int ntiles = L / 128;
+  const int ntiles = (L + 127) / 128;  // keys beyond L (zero-filled by TMA) are masked in the last tile
 
   if (threadIdx.x == 0) {
     mbar_init(b_q, 1);
@@ -172,8 +176,8 @@ attn_flash3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     __syncwarp();
     for (int j = 0; j < ntiles; ++j) {
-      const int s = j & 1;
-      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+      const int s = j % Cfg::STAGES;
+      const uint32_t ph = (uint32_t)(j / Cfg::STAGES) & 1u;
       mbar_wait(b_ke + 8 * s, ph ^ 1u);
       RFB_STAMP(j, 0);
       if (elect_one()) {
@@ -197,8 +201,8 @@ attn_flash3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(b_q, 0);
     for (int j = 0; j <= ntiles; ++j) {
       if (j < ntiles) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        const int s = j % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(j / Cfg::STAGES) & 1u;
         mbar_wait(b_kf + 8 * s, ph);
         RFB_STAMP(j, 10);
         if (j > 0) mbar_wait(b_sfree, (uint32_t)(j - 1) & 1u);
@@ -223,8 +227,8 @@ attn_flash3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
       }
       if (j > 0) {
-        const int jj = j - 1, s = jj & 1;
-        const uint32_t ph = (uint32_t)(jj >> 1) & 1u;
+        const int jj = j - 1, s = jj % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(jj / Cfg::STAGES) & 1u;
         mbar_wait(b_vf + 8 * s, ph);
         RFB_STAMP(jj, 12);
         mbar_wait(b_pfull, (uint32_t)jj & 1u);
@@ -262,6 +266,12 @@ attn_flash3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_sfree);
+      if ((L & 127) && j == ntiles - 1) {  // ragged sequence (CLIP: 257 tokens; 8x8 maps: 64): keys >= L score -inf
+        const int valid = L - j * 128 - 64 * hh;
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= valid) sv[i] = 0xff800000u;
+      }
       float mr0 = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
       float mr1 = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
 #pragma unroll
@@ -328,6 +338,7 @@ attn_flash3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float inv = 1.0f / (l + xch[(hh ^ 1) * 128 + r]);
     __half* op = out + ((long long)n * L + (long long)qt * 128 + r) * ldo + (long long)head * d;
     const int c_begin = hh ? Cfg::SPLIT : 0, c_end = hh ? d : Cfg::SPLIT;
+    const bool row_ok = qt * 128 + r < L;  // query rows beyond L exist only as zero-filled padding
 #pragma unroll
     for (int cc = 0; cc < Cfg::SPLIT; cc += 8) {
       const int c0 = c_begin + cc;
@@ -340,7 +351,7 @@ attn_flash3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         u.y = pack_h2(__uint_as_float(ov[2]) * inv, __uint_as_float(ov[3]) * inv);
         u.z = pack_h2(__uint_as_float(ov[4]) * inv, __uint_as_float(ov[5]) * inv);
         u.w = pack_h2(__uint_as_float(ov[6]) * inv, __uint_as_float(ov[7]) * inv);
-        *reinterpret_cast<uint4*>(op + c0) = u;
+        if (row_ok) *reinterpret_cast<uint4*>(op + c0) = u;
       }
     }
     tc_fence_before();
@@ -357,13 +368,12 @@ template <int DP>
 static void launch_flash3(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, __half* out,
                           long long ldo, int N, int L, int heads, int d, float scale) {
   using Cfg = Flash3Cfg<DP>;
-  if (c.first_use(DP == 48 ? "flash3_48" : "flash3_80")) {
+  static const char* keys[] = {"flash3_48", "flash3_64", "flash3_80", "flash3_160"};
+  if (c.first_use(keys[DP == 48 ? 0 : DP == 64 ? 1 : DP == 80 ? 2 : 3])) {
     CUDA_OK(cudaFuncSetAttribute(attn_flash3_kernel<DP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    CUDA_OK(cudaFuncSetAttribute(attn_flash3_kernel<DP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     CUDA_OK(cudaFuncSetAttribute(attn_flash3_kernel<DP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    CUDA_OK(cudaFuncSetAttribute(attn_flash3_kernel<DP, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   }
-  dim3 grid((unsigned)(L / 128), (unsigned)(N * heads));
+  dim3 grid((unsigned)((L + 127) / 128), (unsigned)(N * heads));
   Ctx::ProfRec rec;
   if (c.profile) {
     CUDA_OK(cudaEventCreate(&rec.a));
@@ -380,12 +390,8 @@ static void launch_flash3(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, 
     CUDA_OK(cudaMemsetAsync(c.dbg_buf, 0, (size_t)c.num_sms * 8 * sizeof(unsigned long long), c.stream));
     dbg = c.dbg_buf;
   }
-  switch (c.attn_poly) {
-    case 0: attn_flash3_kernel<DP, 0><<<grid, 320, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg); break;
-    case 1: attn_flash3_kernel<DP, 1><<<grid, 320, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg); break;
-    case 3: attn_flash3_kernel<DP, 3><<<grid, 320, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg); break;
-    default: attn_flash3_kernel<DP, 2><<<grid, 320, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg); break;
-  }
+  if (c.attn_poly) attn_flash3_kernel<DP, 2><<<grid, 320, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg);
+  else attn_flash3_kernel<DP, 0><<<grid, 320, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg);
   CUDA_OK(cudaGetLastError());
   c.launches++;
   if (c.profile) {
@@ -770,10 +776,13 @@ static void launch_flash4(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, 
 
 bool attention_flash(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads, int d, __half* out,
                      long long ldo, float scale, int q_off, int k_off, int v_off, int hs) {
-  if (L % 128 != 0 || (d != 40 && d != 80) || (d % 8) != 0) return false;
+  // fused kernels: head dims 40 / 64 / 80 / 160 (UNet 64^2 / CLIP / 32^2 / 16^2 + 8^2 levels), any sequence length (keys
+  // beyond L are masked); d = 512 (the VAE's single-head AttnBlock) stays on the materialised path
+  if ((d != 40 && d != 64 && d != 80 && d != 160) || L < 1) return false;
   if (hs <= 0) hs = d;
   // padded head slices (hs > d, zero filled): the whole 64-column box is in bounds and every row is one aligned line
-  const uint64_t dims[4] = {(uint64_t)std::min(hs, d <= 64 ? 64 : 128), (uint64_t)heads, (uint64_t)L, (uint64_t)N};
+  const int ncols = d <= 64 ? 64 : (d <= 128 ? 128 : 192);
+  const uint64_t dims[4] = {(uint64_t)std::min(hs, ncols), (uint64_t)heads, (uint64_t)L, (uint64_t)N};
   const uint64_t str[3] = {(uint64_t)hs * 2, (uint64_t)ldq * 2, (uint64_t)L * ldq * 2};
   const uint32_t box[4] = {64, 1, 128, 1};
   CUtensorMap tq = make_tmap(c, qkv + q_off, 4, dims, str, box);
@@ -783,8 +792,12 @@ bool attention_flash(Ctx& c, const __half* qkv, long long ldq, int N, int L, int
     launch_flash4<48>(c, tq, tk, tv, out, ldo, N, L, heads, d, scale);
     return true;
   }
-  if (d == 40) launch_flash3<48>(c, tq, tk, tv, out, ldo, N, L, heads, d, scale);
-  else launch_flash3<80>(c, tq, tk, tv, out, ldo, N, L, heads, d, scale);
+  switch (d) {
+    case 40: launch_flash3<48>(c, tq, tk, tv, out, ldo, N, L, heads, d, scale); break;
+    case 64: launch_flash3<64>(c, tq, tk, tv, out, ldo, N, L, heads, d, scale); break;
+    case 80: launch_flash3<80>(c, tq, tk, tv, out, ldo, N, L, heads, d, scale); break;
+    default: launch_flash3<160>(c, tq, tk, tv, out, ldo, N, L, heads, d, scale); break;
+  }
   return true;
 }
 
