@@ -888,6 +888,74 @@ __global__ void cfg_ddim_update_kernel(const float* __restrict__ x, const float*
   }
 }
 
+// The UNet's output convolution (320 -> 4 channels, 3x3, openaimodel.py:829-836) runs as ONE thin GEMM over the 9 taps:
+// taps[p, tap * 4 + co] = sum_c h[p, c] * W[co, c, tap] (fp32, [N*L*L, 36]); a pixel's eps is then the sum of the 9 tap
+// partials of its 3x3 neighbourhood (zero outside the map = the conv's padding) plus the bias.  As a 3x3 implicit GEMM the
+// layer moved 9x the activation bytes through 128x32 tiles of which 4 columns were real (55-73 us); the tap GEMM reads
+// the activation once.
+__device__ __forceinline__ float4 eps_gather(const float* __restrict__ taps, const float* __restrict__ bias, int n, int y,
+                                             int x, int L) {
+  float4 acc = make_float4(bias[0], bias[1], bias[2], bias[3]);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    if (yy >= 0 && yy < L && xx >= 0 && xx < L) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(taps + (((long long)n * L + yy) * L + xx) * 36 + tap * 4));
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+  }
+  return acc;
+}
+// eps [N,4,L,L] fp32 from the tap partials (UNetModel.forward's return value)
+__global__ void eps_from_taps_kernel(const float* __restrict__ taps, const float* __restrict__ bias, float* __restrict__ eps,
+                                     int N, int L) {
+  const long long total = (long long)N * L * L;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % L), y = (int)((i / L) % L), n = (int)(i / ((long long)L * L));
+    const float4 e = eps_gather(taps, bias, n, y, x, L);
+    float* o = eps + (long long)n * 4 * L * L + (long long)y * L + x;
+    o[0] = e.x, o[(long long)L * L] = e.y, o[2ll * L * L] = e.z, o[3ll * L * L] = e.w;
+  }
+}
+// p_sample_ddim's tail as the END of the output convolution: tap gather (+bias) for the uncond / cond halves ->
+// e_t = e_u + s (e_c - e_u) (ddim.py:346) -> pred_x0, dir_xt, x_{t-1} (ddim.py:363-374), same fp32 op order as
+// cfg_ddim_update_kernel; eps never goes to HBM.  One thread per latent pixel (4 channels).
+__global__ void taps_cfg_ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ taps,
+                                            const float* __restrict__ bias, const float* __restrict__ noise,
+                                            float* __restrict__ x_prev, float* __restrict__ pred_x0, int B, int L, float scale,
+                                            float a_t, float a_prev, float sigma, float sqrt_one_minus_at, int has_uncond) {
+  const float sqrt_at = __fsqrt_rn(a_t);
+  const float sqrt_aprev = __fsqrt_rn(a_prev);
+  const float dir_coef = __fsqrt_rn(__fsub_rn(__fsub_rn(1.0f, a_prev), __fmul_rn(sigma, sigma)));
+  const long long HW = (long long)L * L, total = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % L), yy = (int)((i / L) % L), b = (int)(i / HW);
+    const float4 eu4 = eps_gather(taps, bias, b, yy, xx, L);
+    float4 ec4 = eu4;
+    if (has_uncond) ec4 = eps_gather(taps, bias, B + b, yy, xx, L);
+    const float eu[4] = {eu4.x, eu4.y, eu4.z, eu4.w}, ec[4] = {ec4.x, ec4.y, ec4.z, ec4.w};
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const long long idx = ((long long)b * 4 + ch) * HW + (long long)yy * L + xx;
+      const float e = has_uncond ? __fadd_rn(eu[ch], __fmul_rn(scale, __fsub_rn(ec[ch], eu[ch]))) : eu[ch];
+      const float p0 = __fdiv_rn(__fsub_rn(x[idx], __fmul_rn(sqrt_one_minus_at, e)), sqrt_at);
+      const float dir = __fmul_rn(dir_coef, e);
+      const float nz = noise ? __fmul_rn(sigma, noise[idx]) : 0.0f;
+      x_prev[idx] = __fadd_rn(__fadd_rn(__fmul_rn(sqrt_aprev, p0), dir), nz);
+      if (pred_x0) pred_x0[idx] = p0;
+    }
+  }
+}
+// [4, C, 3, 3] fp32 -> [64 (36 used), C] fp16, row = tap * 4 + co
+__global__ void pack_out_taps_kernel(const float* __restrict__ w, __half* __restrict__ dst, int C, int kp) {
+  const int total = 64 * kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % kp, r = i / kp;
+    const int tap = r >> 2, co = r & 3;
+    dst[i] = (r < 36 && k < C) ? __float2half_rn(w[((long long)co * C + k) * 9 + tap]) : __float2half_rn(0.f);
+  }
+}
+
 // classifier-free guidance combine alone (get_model_output, plms.py:184-188): e = e_u + scale * (e_c - e_u)
 __global__ void cfg_combine_kernel(const float* __restrict__ eps2, float* __restrict__ out, long long count, float scale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {

@@ -862,6 +862,27 @@ void cfg_ddim_update(Ctx& c, const float* x, const float* eps2, const float* noi
   LAUNCH_CHECK(c);
 }
 
+void eps_from_taps(Ctx& c, const float* taps, const float* bias, float* eps, int N, int L) {
+  eps_from_taps_kernel<<<grid_for((long long)N * L * L), 256, 0, c.stream>>>(taps, bias, eps, N, L);
+  LAUNCH_CHECK(c);
+}
+void taps_cfg_ddim_update(Ctx& c, const float* x, const float* taps, const float* bias, const float* noise, float* x_prev,
+                          float* pred_x0, int B, int L, float scale, float a_t, float a_prev, float sigma,
+                          float sqrt_one_minus_at, int has_uncond) {
+  taps_cfg_ddim_update_kernel<<<grid_for((long long)B * L * L, 128), 128, 0, c.stream>>>(
+      x, taps, bias, noise, x_prev, pred_x0, B, L, scale, a_t, a_prev, sigma, sqrt_one_minus_at, has_uncond);
+  LAUNCH_CHECK(c);
+}
+LinW pack_out_taps(Ctx& c, const std::string& wname) {
+  const Param& p = c.param(wname);
+  RFB_CHECK(p.shape.size() == 4 && p.shape[0] == 4 && p.shape[2] == 3 && p.shape[3] == 3, "output conv must be [4,C,3,3]");
+  LinW w;
+  w.in = (int)p.shape[1], w.out = 36, w.kp = round_up(w.in, 64);
+  w.w = (__half*)c.dmalloc((size_t)64 * w.kp * sizeof(__half));
+  pack_out_taps_kernel<<<grid_for(64ll * w.kp), 256, 0, c.stream>>>(p.f32, w.w, w.in, w.kp);
+  LAUNCH_CHECK(c);
+  return w;
+}
 void cfg_combine(Ctx& c, const float* eps2, float* out, long long count, float scale) {
   cfg_combine_kernel<<<grid_for(count), 256, 0, c.stream>>>(eps2, out, count, scale);
   LAUNCH_CHECK(c);

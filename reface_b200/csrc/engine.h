@@ -216,6 +216,11 @@ void cfg_ddim_update(Ctx& c, const float* x, const float* eps2, const float* noi
                      long long count, float scale, float a_t, float a_prev, float sigma, float sqrt_one_minus_at,
                      int has_uncond);
 
+void eps_from_taps(Ctx& c, const float* taps, const float* bias, float* eps, int N, int L);
+void taps_cfg_ddim_update(Ctx& c, const float* x, const float* taps, const float* bias, const float* noise, float* x_prev,
+                          float* pred_x0, int B, int L, float scale, float a_t, float a_prev, float sigma,
+                          float sqrt_one_minus_at, int has_uncond);
+LinW pack_out_taps(Ctx& c, const std::string& wname);
 void cfg_combine(Ctx& c, const float* eps2, float* out, long long count, float scale);
 void plms_combine(Ctx& c, const float* e_t, const float* o1, const float* o2, const float* o3, const float* e_next,
                   float* out, long long count, int order);

@@ -42,7 +42,8 @@ struct UNet {
   std::vector<UOp> mid;
   Lin32 te0, te2, emb_cat;
   const float *out_g = nullptr, *out_b = nullptr;
-  ConvW out_conv;
+  LinW out_taps;  // out.2 (3x3, 320 -> 4) as a [36, 320] tap GEMM: row = tap * 4 + co (elem.cuh: eps_gather)
+  const float* out_bias = nullptr;
 };
 
 struct DdimSchedule {
@@ -62,6 +63,9 @@ struct UNetAux {                        // optional step-invariant inputs of a f
   // uniform_t only: this step's row of every ResBlock's emb_layers output (UNet::emb_cat), precomputed for all the
   // steps of a sampling run (unet_time_embeddings); nullptr: computed inside the forward pass
   const float* emb_all = nullptr;
+  // != nullptr: leave the output convolution's tap partials [N*L*L, 36] fp32 here instead of writing eps (the sampler's
+  // update kernel finishes the convolution itself)
+  float* taps_out = nullptr;
 };
 std::vector<const float*> unet_cross_vectors(Ctx& c, UNet& u, const float* ctx, int N, int T);
 // emb_layers(SiLU(time_embed(timestep_embedding(t)))) of all ResBlocks for R timesteps: [R, u.emb_cat.out] (arena)

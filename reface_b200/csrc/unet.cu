@@ -169,7 +169,8 @@ UNet* build_unet(Ctx& c, const std::string& pfx, const UNetCfg& cfg) {
     u->emb_cat.w = w, u->emb_cat.b = b, u->emb_cat.in = in, u->emb_cat.out = total;
   }
   u->out_g = c.pf(pfx + "out.0.weight"), u->out_b = c.pf(pfx + "out.0.bias");
-  u->out_conv = pack_conv(c, pfx + "out.2.weight", pfx + "out.2.bias");
+  u->out_taps = pack_out_taps(c, pfx + "out.2.weight");
+  u->out_bias = c.pf(pfx + "out.2.bias");
   CUDA_OK(cudaStreamSynchronize(c.stream));
   return u;
 }
@@ -391,10 +392,14 @@ void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const fl
     h = run_ops(c, ops, h, rs, skip);
   }
   Tens hn = groupnorm(c, h, u.out_g, u.out_b, 1e-5f, true);
+  // out.2 (3x3, 320 -> 4): one [N*L*L, 320] x [320, 36] tap GEMM, finished by a 9-tap gather (elem.cuh: eps_gather)
+  RFB_CHECK(u.cfg.out_channels == 4, "the tap formulation of the output conv is written for 4 output channels");
+  const long long M = hn.rows();
+  float* taps = (aux && aux->taps_out) ? aux->taps_out : c.alloc_t<float>((size_t)M * 36);
   Epi e;
-  const long long HW = (long long)L * L;
-  e.out32 = eps, e.o32_sn = u.cfg.out_channels * HW, e.o32_sp = 1, e.o32_sc = HW, e.o32_rpn = (int)HW;
-  conv3x3_t(c, hn, u.out_conv, e);
+  e.out32 = taps, e.o32_sn = 36, e.o32_sp = 0, e.o32_sc = 1, e.o32_rpn = 1;
+  gemm(c, hn.p, hn.c, M, hn.c, u.out_taps.w, u.out_taps.kp, 36, nullptr, 0, e);
+  if (!(aux && aux->taps_out)) eps_from_taps(c, taps, u.out_bias, eps, N, L);
   c.release(mk);
 }
 
@@ -405,7 +410,7 @@ void unet_forward(Ctx& c, UNet& u, const float* x9, const long long* t, const fl
 // schedule: arena addresses are a deterministic function of the arena mark at entry, which is part of the
 // cache key.  First call with a key: eager; second call: capture + instantiate + launch; afterwards: one cudaGraphLaunch.
 struct DdimBufs {
-  float *xa, *xb, *p0, *x9, *eps, *ctx, *z, *mask, *o_x0, *o_ix, *o_ip;
+  float *xa, *xb, *p0, *x9, *taps, *ctx, *z, *mask, *o_x0, *o_ix, *o_ip;
   long long *ts, *ts1;  // timesteps per (step, sample) / per step
 };
 
@@ -419,6 +424,7 @@ static int ddim_body(Ctx& c, UNet& u, DdimBufs b, int B, int L, int T, const Ddi
   aux.uniform_t = 1;
   aux.cfg_dup = cfg ? 1 : 0;
   aux.crossvec = unet_cross_vectors(c, u, b.ctx, N, T);
+  aux.taps_out = b.taps;
   // ... and so does the whole time-embedding path: emb_layers(time_embed(t)) for ALL steps in four launches
   // (per step it streamed the 115 MB of fp32 emb_layers weights for a single row)
   const float* emb_table = unet_time_embeddings(c, u, b.ts1, s.n);
@@ -428,9 +434,10 @@ static int ddim_body(Ctx& c, UNet& u, DdimBufs b, int B, int L, int T, const Ddi
     const int index = s.n - 1 - i;
     aux.emb_all = emb_table + (size_t)index * u.emb_cat.out;
     concat9(c, xa, b.z, b.mask, b.x9, B, (int)HW, dup);
-    unet_forward(c, u, b.x9, b.ts + (size_t)index * N, b.ctx, N, L, T, b.eps, &aux);
-    cfg_ddim_update(c, xa, b.eps, noise ? noise + (size_t)i * cnt : nullptr, xb, b.p0, cnt, scale, s.a_t[index],
-                    s.a_prev[index], s.sigma[index], s.sqrt_one_minus_a[index], cfg ? 1 : 0);
+    unet_forward(c, u, b.x9, b.ts + (size_t)index * N, b.ctx, N, L, T, nullptr, &aux);
+    // CFG combine + DDIM update fused with the end of the UNet's output convolution: eps never reaches HBM
+    taps_cfg_ddim_update(c, xa, b.taps, u.out_bias, noise ? noise + (size_t)i * cnt : nullptr, xb, b.p0, B, L, scale,
+                         s.a_t[index], s.a_prev[index], s.sigma[index], s.sqrt_one_minus_a[index], cfg ? 1 : 0);
     std::swap(xa, xb);
     if (log_every_t > 0 && (index % log_every_t == 0 || index == s.n - 1)) {  // ddim.py:247-249
       CUDA_OK(cudaMemcpyAsync(b.o_ix + (size_t)n_inter * cnt, xa, cnt * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
@@ -454,7 +461,7 @@ void ddim_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, cons
     if (log_every_t > 0 && (index % log_every_t == 0 || index == s.n - 1)) ++K;
   DdimBufs b;
   b.xa = c.alloc_t<float>(cnt), b.xb = c.alloc_t<float>(cnt), b.p0 = c.alloc_t<float>(cnt);
-  b.x9 = c.alloc_t<float>((size_t)N * 9 * HW), b.eps = c.alloc_t<float>((size_t)N * 4 * HW);
+  b.x9 = c.alloc_t<float>((size_t)N * 9 * HW), b.taps = c.alloc_t<float>((size_t)N * HW * 36);
   b.ctx = c.alloc_t<float>((size_t)N * T * 768);
   b.z = c.alloc_t<float>(cnt), b.mask = c.alloc_t<float>((size_t)B * HW);
   b.o_x0 = c.alloc_t<float>(cnt);

@@ -127,6 +127,21 @@ def test_sampling_loop_cuda_graph_replays_are_bit_exact(unet_engine):
         eng.set_option("cfg_share", 1)
 
 
+def test_fused_output_conv_cfg_ddim_update_equals_separate_kernels(unet_engine, oracle):
+    """Inside the sampler the UNet's output convolution (a [N*L*L,320]x[320,36] tap GEMM) is finished by the update
+    kernel itself: 9-tap gather + bias -> CFG combine -> x_{t-1} / pred_x0 (ddim.py:346,363-374), eps never stored.
+    One step must give the bits of UNetModel.forward -> rfb_cfg_ddim_update (itself bit-exact vs the oracle)."""
+    g = _g("ddim_S5_L16")
+    eng = unet_engine
+    sch = oracle.ddim_schedule(5)
+    _, ix, ip = eng.ddim_sample(g["x_T"], g["z"], g["mask"], g["c"], g["uc"], S=5, scale=3.5, log_every_t=1, n_steps_limit=1)
+    x9 = eng.concat9(g["x_T"], g["z"], g["mask"], dup=2)
+    t = torch.full((2,), int(sch["timesteps"][4]), dtype=torch.long)
+    eps2 = eng.unet_forward(x9, t, torch.cat([g["uc"], g["c"]]))
+    xp, p0 = eng.cfg_ddim_update(g["x_T"], eps2, 3.5, *[sch[k][4] for k in ("a_t", "a_prev", "sigma", "sqrt_one_minus_a")])
+    assert torch.equal(ix[0], xp) and torch.equal(ip[0], p0)
+
+
 def test_cfg_head_sharing_is_bit_exact(unet_engine):
     """Inside the samplers the two CFG halves share their input and timestep (ddim.py:338-344): conv_in, the first
     ResBlock and attn1 of the first SpatialTransformer are computed once per pair (option cfg_share).  The results
