@@ -193,6 +193,7 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "gn_fused") c.gn_fused = (int)value;
   else if (k == "gn_epi_stats") c.gn_epi_stats = (int)value;
   else if (k == "gn_apply_bps") c.gn_apply_bps = (int)value;
+  else if (k == "gn_fold") c.gn_fold = (int)value;
   else if (k == "cfg_share") c.cfg_share = (int)value;
   else if (k == "gn_cluster") c.gn_cluster = (int)value;
   else if (k == "gn_fused_max_elems") c.gn_fused_max_elems = value;

@@ -294,51 +294,64 @@ struct GnStatSrc {
 };
 __global__ void __launch_bounds__(256)
 gn_finalize3_kernel(const GnStatSrc st, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    float2* __restrict__ ab, int P, int HW, int C, int G, int GPB, float eps) {
-  // grid (G / GPB, N): one block folds GPB consecutive groups (W = GPB * cpg <= 256 contiguous channels) of one sample.
-  // Thread t owns channel (t mod W) of that range and partial rows t / W, t / W + R, ...: consecutive threads read
-  // consecutive float2 (coalesced 8-byte loads), every thread's own sum runs in row order, the R row-phases and then the
-  // cpg channels of a group are folded in a fixed order -> bitwise reproducible, independent of the batch size.
+                    float2* __restrict__ ab, int P, int HW, int C, int G, float eps) {
+  // grid (G, N): one block folds ONE group (cpg <= 256 contiguous channels) of one sample.  Thread t owns channel
+  // (t mod cpg) and partial rows t / cpg, t / cpg + R, ... (four independent loads in flight): consecutive threads read
+  // consecutive float2, every thread's own sum runs in row order, the R row-phases and then the cpg channels are folded
+  // in a fixed order -> bitwise reproducible, independent of the batch size.
   // Output: per (sample, channel) the affine map of the normalisation, ab = (rstd * gamma, beta - mean * rstd * gamma).
   __shared__ float2 red[256];
-  __shared__ float2 mr[8];
-  const int n = blockIdx.y, g0 = blockIdx.x * GPB;
-  const int cpg = C / G, W = GPB * cpg;
-  const int R = 256 / W;
-  const int ci = threadIdx.x % W, rp = threadIdx.x / W;
+  __shared__ float2 mr;
+  const int n = blockIdx.y, gi = blockIdx.x;
+  const int cpg = C / G;
+  const int R = 256 / cpg;
+  const int ci = threadIdx.x % cpg, rp = threadIdx.x / cpg;
   float s = 0.f, ss = 0.f;
   if (rp < R) {
-    const int ch = g0 * cpg + ci;
+    const int ch = gi * cpg + ci;
     const bool first = st.s2 == nullptr || ch < st.C1;
     const int Cs = first ? st.C1 : C - st.C1;
     const float2* base = first ? reinterpret_cast<const float2*>(st.s1) + (long long)n * P * Cs + ch
                                : reinterpret_cast<const float2*>(st.s2) +
                                      (long long)(st.n2mod > 0 ? n % st.n2mod : n) * P * Cs + (ch - st.C1);
-    for (int pr = rp; pr < P; pr += R) {
+    int pr = rp;
+    for (; pr + 3 * R < P; pr += 4 * R) {
+      const float2 v0 = __ldg(base + (long long)pr * Cs), v1 = __ldg(base + (long long)(pr + R) * Cs);
+      const float2 v2 = __ldg(base + (long long)(pr + 2 * R) * Cs), v3 = __ldg(base + (long long)(pr + 3 * R) * Cs);
+      s += v0.x, ss += v0.y;
+      s += v1.x, ss += v1.y;
+      s += v2.x, ss += v2.y;
+      s += v3.x, ss += v3.y;
+    }
+    for (; pr < P; pr += R) {
       const float2 v = __ldg(base + (long long)pr * Cs);
       s += v.x, ss += v.y;
     }
   }
   red[threadIdx.x] = make_float2(s, ss);
   __syncthreads();
-  if (threadIdx.x < GPB) {
+  if (threadIdx.x < cpg) {  // row phases of one channel, in phase order
     float a = 0.f, b = 0.f;
-    for (int c = 0; c < cpg; ++c)
-      for (int r = 0; r < R; ++r) {
-        const float2 v = red[r * W + threadIdx.x * cpg + c];
-        a += v.x, b += v.y;
-      }
+    for (int r = 0; r < R; ++r) {
+      const float2 v = red[r * cpg + threadIdx.x];
+      a += v.x, b += v.y;
+    }
+    red[threadIdx.x] = make_float2(a, b);  // phase 0's slot of this channel: read only by this thread above
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // channels of the group, in channel order
+    float a = 0.f, b = 0.f;
+    for (int c = 0; c < cpg; ++c) a += red[c].x, b += red[c].y;
     const float cnt = (float)cpg * (float)HW;
     const float mean = a / cnt;
     const float var = fmaxf(b / cnt - mean * mean, 0.f);
-    mr[threadIdx.x] = make_float2(mean, rsqrtf(var + eps));
+    mr = make_float2(mean, rsqrtf(var + eps));
   }
   __syncthreads();
-  if (threadIdx.x < W) {
-    const int ch = g0 * cpg + threadIdx.x;
-    const float2 m = mr[threadIdx.x / cpg];
-    const float a = m.y * __ldg(gamma + ch);
-    ab[(long long)n * C + ch] = make_float2(a, __ldg(beta + ch) - m.x * a);
+  if (threadIdx.x < cpg) {
+    const int ch = gi * cpg + threadIdx.x;
+    const float a = mr.y * __ldg(gamma + ch);
+    ab[(long long)n * C + ch] = make_float2(a, __ldg(beta + ch) - mr.x * a);
   }
 }
 // y = x * a[n, c] + b[n, c] (* sigmoid): one read, one write.  A block streams `slab` pixels of one sample; a thread keeps
@@ -389,6 +402,34 @@ gn_apply3_kernel(const GnSrc src, const float2* __restrict__ ab, __half* __restr
       }
     }
   }
+}
+
+// An activation-free GroupNorm in front of a 1x1 convolution / linear layer (SpatialTransformer.norm -> proj_in,
+// attention.py:256-262,281-283) is a per-(sample, channel) affine map, so it folds into the layer:
+//   W (x * a_n + b_n) + bias = (W diag(a_n)) x + (W b_n + bias)
+// -> per-sample fp16 weights Wn[n] = W * a_n (columns scaled) and a per-sample bias row; the GEMM then reads the RAW
+// tensor and the normalisation pass over it disappears.  One warp per (sample, output row); fp32 originals of W.
+__global__ void gn_fold_weights_kernel(const float* __restrict__ w32, const float* __restrict__ bias,
+                                       const float2* __restrict__ ab, __half* __restrict__ Wn, float* __restrict__ biasn,
+                                       int Cin, int Cout, int kp, int cout_p) {
+  const int n = blockIdx.y;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= cout_p) return;
+  __half* dst = Wn + ((long long)n * cout_p + o) * kp;
+  float acc = 0.f;
+  for (int k = lane; k < kp; k += 32) {
+    float v = 0.f;
+    if (o < Cout && k < Cin) {
+      const float w = __ldg(w32 + (long long)o * Cin + k);
+      const float2 t = __ldg(ab + (long long)n * Cin + k);
+      v = w * t.x;
+      acc = fmaf(w, t.y, acc);
+    }
+    dst[k] = __float2half_rn(v);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0 && o < Cout) biasn[(long long)n * Cout + o] = acc + (bias ? bias[o] : 0.f);
 }
 
 // Single-launch GroupNorm: the CTAs of one sample (gridDim.x = cluster size, 8 or 16) form a thread-block cluster.  Each CTA reduces its pixel

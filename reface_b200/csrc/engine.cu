@@ -661,6 +661,17 @@ void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads
 }
 
 // ------------------------------------------------------------------------------------------ normalisation etc.
+// GroupNorm(32) of [x1 | x2] as a per-(sample, channel) affine map y = x * a + b, folded from the partial statistics the
+// producing epilogues left with the tensors: ab[n][c] = (rstd * gamma, beta - mean * rstd * gamma) (arena, [N][C])
+float2* gn_affine_from_stats(Ctx& c, const Tens& x1, const Tens& x2, const float* gamma, const float* beta, float eps) {
+  const int C = x1.c + (x2.p ? x2.c : 0), N = x1.n, HW = x1.h * x1.w;
+  RFB_CHECK(x1.stats && (!x2.p || x2.stats) && HW % 32 == 0 && C % 32 == 0 && C / 32 <= 256, "GroupNorm: no producer statistics");
+  float2* ab = c.alloc_t<float2>((size_t)N * C);
+  GnStatSrc ss{x1.stats, x2.p ? x2.stats : nullptr, x1.c, (x2.p && x2.n != x1.n) ? x2.n : 0};
+  gn_finalize3_kernel<<<dim3(32, (unsigned)N), 256, 0, c.stream>>>(ss, gamma, beta, ab, HW / 32, HW, C, 32, eps);
+  LAUNCH_CHECK(c);
+  return ab;
+}
 Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps, bool silu) {
   return groupnorm2(c, x, Tens(), gamma, beta, eps, silu);
 }
@@ -679,14 +690,7 @@ Tens groupnorm2(Ctx& c, const Tens& x1, const Tens& x2, const float* gamma, cons
   if (c.gn_epi_stats && x1.stats && (!x2.p || x2.stats) && HW % 32 == 0) {
     // statistics came with the tensor(s) from the producing epilogue: fold them per (sample, group), then ONE streaming
     // pass (the tensor is read once instead of twice)
-    float2* ab = c.alloc_t<float2>((size_t)N * C);
-    GnStatSrc ss{x1.stats, x2.p ? x2.stats : nullptr, x1.c, src.n2mod};
-    const int cpg = C / 32;
-    const int gpb = 4 * cpg <= 256 ? 4 : (2 * cpg <= 256 ? 2 : 1);
-    RFB_CHECK(cpg <= 256, "GroupNorm finalize: more than 256 channels per group");
-    gn_finalize3_kernel<<<dim3((unsigned)(32 / gpb), (unsigned)N), 256, 0, c.stream>>>(ss, gamma, beta, ab, HW / 32, HW, C, 32, gpb,
-                                                                                     eps);
-    LAUNCH_CHECK(c);
+    float2* ab = gn_affine_from_stats(c, x1, x2, gamma, beta, eps);
     // gn_apply_bps blocks per SM over the whole batch; a function of the batch only through the work split, never the values
     const int want = std::max(1, (c.gn_apply_bps * c.num_sms) / std::max(1, N));
     const int slab = std::max(R, (HW + want - 1) / want);
@@ -753,6 +757,45 @@ Tens groupnorm2(Ctx& c, const Tens& x1, const Tens& x2, const float* gamma, cons
   RFB_CHECK(cv * R >= 256, "GroupNorm: block too small for the in-kernel finalize");
   gn_apply2_kernel<<<g2, cv * R, 0, c.stream>>>(src, partial, nslab, gamma, beta, y.p, HW, C, 32, eps, silu ? 1 : 0, slab2);
   LAUNCH_CHECK(c);
+  c.release(mk);
+  return y;
+}
+
+// conv1x1(GroupNorm(x)) with the activation-free GroupNorm folded into per-sample weights (elem.cuh:
+// gn_fold_weights_kernel); x must carry producer statistics.  w32: fp32 [Cout, Cin] (the 1x1 conv weight), bias [Cout].
+Tens conv1x1_gn_folded(Ctx& c, const Tens& x, const float* gn_gamma, const float* gn_beta, float eps, const float* w32,
+                       const float* bias, int Cout) {
+  const int Cin = x.c, N = x.n, HW = x.h * x.w;
+  RFB_CHECK(Cin % 64 == 0 && Cout % 8 == 0 && HW % 128 == 0, "folded GroupNorm + 1x1 conv: shape not supported");
+  Tens y = c.new_tens(N, x.h, x.w, Cout);
+  const size_t mk = c.mark();
+  float2* ab = gn_affine_from_stats(c, x, Tens(), gn_gamma, gn_beta, eps);
+  const int kp = Cin, cout_p = round_up(Cout, 32);
+  __half* Wn = c.alloc_t<__half>((size_t)N * cout_p * kp);
+  float* biasn = c.alloc_t<float>((size_t)N * Cout);
+  gn_fold_weights_kernel<<<dim3((unsigned)((cout_p + 7) / 8), (unsigned)N), 256, 0, c.stream>>>(w32, bias, ab, Wn, biasn, Cin,
+                                                                                             Cout, kp, cout_p);
+  LAUNCH_CHECK(c);
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = HW, g.N = Cout, g.nk = Cin / 64;
+  g.BN = pick_bn(c, (long long)HW * N, Cout, false, Cin, true);
+  g.a_mode = A_BATCH3, g.b_mode = B_BATCH3;
+  Epi e;
+  e.rowvec = biasn, e.ldv = 0, e.rows_per_vec = HW;
+  fill_epi(g, e, y.p, Cout);
+  g.rowvec_zs = Cout;
+  g.zdiv = 1, g.zs_outer = (long long)HW * Cout, g.zs_inner = 0;
+  const uint64_t da[3] = {(uint64_t)Cin, (uint64_t)HW, (uint64_t)N};
+  const uint64_t sa[2] = {(uint64_t)Cin * 2, (uint64_t)HW * Cin * 2};
+  const uint32_t ba[3] = {64, 128, 1};
+  const uint64_t db[3] = {(uint64_t)kp, (uint64_t)cout_p, (uint64_t)N};
+  const uint64_t sb[2] = {(uint64_t)kp * 2, (uint64_t)cout_p * kp * 2};
+  const uint32_t bb[3] = {64, (uint32_t)g.BN, 1};
+  CUtensorMap tmA = make_tmap(c, x.p, 3, da, sa, ba);
+  CUtensorMap tmB = make_tmap(c, Wn, 3, db, sb, bb);
+  dim3 grid((unsigned)(HW / 128), (unsigned)((Cout + g.BN - 1) / g.BN), (unsigned)N);
+  launch_gemm(c, tmA, tmB, g, grid, (double)Cin);
   c.release(mk);
   return y;
 }

@@ -99,6 +99,7 @@ struct Ctx {
   int gemm_splitk = 1;   // 3-way split-K for the long-K 3x3 convs of <= 8x8 maps (slice count from the per-sample shape only)
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)
   int gn_epi_stats = 1;  // GroupNorm from the producer epilogue's partial statistics where available (finalize + streaming apply)
+  int gn_fold = 1;  // SpatialTransformer: fold the activation-free GroupNorm into per-sample proj_in weights (maps >= 32x32)
   int gn_apply_bps = 4;  // streaming GroupNorm apply: blocks per SM
   int gn_fused = 1;  // single-launch cluster GroupNorm (0: stats / finalize / apply kernels)
   long long gn_fused_max_elems = 2621440;  // = 64*64*640: per-sample H*W*C from which GroupNorm takes the whole-grid path
@@ -201,6 +202,9 @@ void attention(Ctx& c, const __half* qkv, long long ldq, int N, int L, int heads
 void cross_attn_small(Ctx& c, const __half* q, const float* kc, const float* vc, __half* out, int N, int L, int T, int C,
                       int heads);
 Tens groupnorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps, bool silu);
+float2* gn_affine_from_stats(Ctx& c, const Tens& x1, const Tens& x2, const float* gamma, const float* beta, float eps);
+Tens conv1x1_gn_folded(Ctx& c, const Tens& x, const float* gn_gamma, const float* gn_beta, float eps, const float* w32,
+                       const float* bias, int Cout);
 Tens groupnorm2(Ctx& c, const Tens& x1, const Tens& x2, const float* gamma, const float* beta, float eps, bool silu);
 Tens layernorm(Ctx& c, const Tens& x, const float* gamma, const float* beta, float eps);
 Tens upsample2x(Ctx& c, const Tens& x);

@@ -171,7 +171,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile&
   const int BN = g.BN;
   const long long m = t.m_base + lane;  // the row this thread owns next to TMEM
   const bool row_ok = m < g.M;
-  const float* rv = (g.rowvec && row_ok) ? g.rowvec + (m / g.rows_per_vec) * g.ldv : nullptr;
+  const float* rv = (g.rowvec && row_ok) ? g.rowvec + (long long)t.z * g.rowvec_zs + (m / g.rows_per_vec) * g.ldv : nullptr;
   const uint32_t bias_s = wbuf + EPI_STAGE_BYTES;
   const int sw = lane & 7;
 

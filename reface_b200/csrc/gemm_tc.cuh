@@ -38,6 +38,7 @@ struct GemmArgs {
   const float* bias;    // [N] (packed order for GEGLU) or nullptr
   const float* rowvec;  // per-sample vector added per column: rowvec[(m / rows_per_vec) * ldv + col]
   int rows_per_vec, ldv;
+  long long rowvec_zs;  // batched launches: rowvec advances by rowvec_zs floats per batch index z
   const float* act_param;  // PReLU slopes [N]
   int act, geglu;
   int relu_after_res;  // ReLU applied AFTER the residual add (ResNet BasicBlock: relu(shortcut + bn(conv)))

@@ -23,6 +23,7 @@ struct STW {
   const float *gn_g = nullptr, *gn_b = nullptr, *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr,
               *ln3g = nullptr, *ln3b = nullptr;
   ConvW proj_in, proj_out;
+  const float *proj_in_w32 = nullptr, *proj_in_b = nullptr;  // fp32 originals for the folded GroupNorm (engine.cu)
   LinW qkv, o1, ff1, ff2, q2, kv2, o2h;
   Lin32 v2, o2, k2;
   int c = 0, heads = 0, d = 0, ctx_dim = 0, ff_bn = 256;

@@ -30,6 +30,7 @@ static STW build_st(Ctx& c, const std::string& p, int ch, int heads, int ctx_dim
   const std::string b = p + "transformer_blocks.0.";
   s.gn_g = c.pf(p + "norm.weight"), s.gn_b = c.pf(p + "norm.bias");
   s.proj_in = pack_conv(c, p + "proj_in.weight", p + "proj_in.bias");
+  s.proj_in_w32 = c.pf(p + "proj_in.weight"), s.proj_in_b = c.pf(p + "proj_in.bias");
   s.proj_out = pack_conv(c, p + "proj_out.weight", p + "proj_out.bias");
   s.ln1g = c.pf(b + "norm1.weight"), s.ln1b = c.pf(b + "norm1.bias");
   s.ln2g = c.pf(b + "norm2.weight"), s.ln2b = c.pf(b + "norm2.bias");
@@ -222,9 +223,15 @@ static float* cross_vec(Ctx& c, const STW& s, const float* ctx, int N) {
 static Tens run_st(Ctx& c, const STW& s, const Tens& x, const float* ctx, int T, int N, const float* vec_pre,
                    bool share_halves = false) {
   const int C = s.c;
-  Tens xn = groupnorm(c, x, s.gn_g, s.gn_b, 1e-6f, false);
-  Tens h = conv3x3_t(c, xn, s.proj_in, Epi(), 1, 0, 0, 0, 0);
   const int L = x.h * x.w;
+  Tens h;
+  if (c.gn_fold && c.gn_epi_stats && x.stats && L >= 1024 && L % 128 == 0) {
+    // norm (no activation) + proj_in as ONE GEMM over the raw tensor with per-sample folded weights
+    h = conv1x1_gn_folded(c, x, s.gn_g, s.gn_b, 1e-6f, s.proj_in_w32, s.proj_in_b, C);
+  } else {
+    Tens xn = groupnorm(c, x, s.gn_g, s.gn_b, 1e-6f, false);
+    h = conv3x3_t(c, xn, s.proj_in, Epi(), 1, 0, 0, 0, 0);
+  }
   // --- attn1 (self attention) [attention.py:240]
   Tens n1 = layernorm(c, h, s.ln1g, s.ln1b, 1e-5f);
   Tens qkv = linear_t(c, n1, s.qkv, Epi());
