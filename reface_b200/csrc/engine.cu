@@ -8,6 +8,7 @@
 
 #include "elem.cuh"
 #include "gemm_pair.cuh"
+#include "gemm_mcast.cuh"
 
 namespace rfb {
 
@@ -200,7 +201,8 @@ int pick_bn(Ctx& c, long long M, int N, bool geglu, int K, bool allow16) {
 
 // Bplain/kp/nrows_w: the plain 2-D weight operand (lets the 2-CTA kernel rebuild the B map with a half-height box)
 static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, dim3 grid, double kalg,
-                        const __half* Bplain = nullptr, int kp = 0, int nrows_w = 0, const CUtensorMap* tmA2p = nullptr) {
+                        const __half* Bplain = nullptr, int kp = 0, int nrows_w = 0, const CUtensorMap* tmA2p = nullptr,
+                        int mcast_cs = 0) {
   const CUtensorMap& tmA2 = tmA2p ? *tmA2p : tmA;
   if (g.ctw <= 0) g.ctw = 3;
   RFB_CHECK(!g.up || (!g.res && !g.rowvec && !g.out32 && !g.ksplit), "folded upsample conv: plain fp16 epilogue only");
@@ -228,7 +230,54 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   const bool pair_ok = c.gemm_pair && g.cstride <= 1 && !g.up && !g.nk1 && Bplain != nullptr && grid.z == 1 && grid.x >= 2 &&
                        (g.a_mode == A_PLAIN || g.a_mode == A_CONV3) && g.b_mode == B_PLAIN && g.nk >= c.gemm_pair_min_nk &&
                        (long long)grid.x * grid.y >= c.num_sms / 2;
-  if (pair_ok) {
+  if (mcast_cs > 1) {
+    // cluster of mcast_cs CTAs on consecutive M tiles sharing every weight tile by TMA multicast (gemm_mcast.cuh);
+    // tmB must have been built with a box of BN / mcast_cs rows
+    RFB_CHECK(grid.x % mcast_cs == 0 && (g.BN / mcast_cs) % 8 == 0 && g.BN % mcast_cs == 0 && g.b_mode == B_PLAIN &&
+                  (g.a_mode == A_PLAIN || (g.a_mode == A_CONV3 && g.cstride == 1 && !g.up)) && !g.nk1 && !g.geglu,
+              "multicast GEMM: shape not supported");
+    const bool fast = g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f;
+    const int budget = (227 - 3) * 1024 - 4 * 2 * EPI_WARP_BYTES;
+    g.stages = c.force_stages ? c.force_stages : std::max(2, std::min(8, budget / stage_bytes));
+    const size_t psmem = gemmp_smem_bytes(g.stages, g.BN, 2);
+    RFB_CHECK(psmem <= 227 * 1024, "GEMM smem over budget");
+    const int m_groups = (int)grid.x / mcast_cs, n_tiles = (int)grid.y;
+    const int units = m_groups * n_tiles * (int)grid.z;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(GEMMP_THREADS);
+    cfg.dynamicSmemBytes = psmem;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)mcast_cs, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+#define RFB_MCAST(MODE_, CS_)                                                                                          \
+  do {                                                                                                                 \
+    auto kfn = gemm_mcast_kernel<MODE_, CS_>;                                                                          \
+    const std::string key = std::string("gemm_mcast_") + #MODE_ + "_" + #CS_;                                          \
+    if (c.first_use(key.c_str())) {                                                                                    \
+      CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));                     \
+      cfg.gridDim = dim3((unsigned)(c.num_sms / CS_ * CS_));                                                           \
+      int nc = 0;                                                                                                      \
+      if (cudaOccupancyMaxActiveClusters(&nc, kfn, &cfg) != cudaSuccess || nc < 1) nc = 1, cudaGetLastError();        \
+      c.once_flags[key + "_max"] = nc;                                                                                 \
+    }                                                                                                                  \
+    const int clusters = std::min(units, c.once_flags[key + "_max"]);                                                  \
+    cfg.gridDim = dim3((unsigned)(clusters * CS_));                                                                    \
+    CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, g, m_groups, n_tiles, units));                                     \
+  } while (0)
+    if (fast) {
+      if (mcast_cs == 8) RFB_MCAST(EPI_FAST, 8);
+      else if (mcast_cs == 4) RFB_MCAST(EPI_FAST, 4);
+      else RFB_MCAST(EPI_FAST, 2);
+    } else {
+      if (mcast_cs == 8) RFB_MCAST(EPI_GENERIC, 8);
+      else if (mcast_cs == 4) RFB_MCAST(EPI_GENERIC, 4);
+      else RFB_MCAST(EPI_GENERIC, 2);
+    }
+#undef RFB_MCAST
+  } else if (pair_ok) {
     // 2-CTA pairs (cta_group::2): each CTA loads its 128 A rows and half of the B tile
     if (c.first_use("gemm_pair")) {
       CUDA_OK(cudaFuncSetAttribute(gemm_pair_kernel<EPI_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -479,13 +528,21 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
     // with element strides the box spans stride * (elements loaded) positions of the traversed dimension
     const uint32_t ba[4] = {64, (uint32_t)(g.bw * stride), (uint32_t)(g.bh * stride), (uint32_t)g.bimg};
     const uint32_t ea[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    // Weight-tile multicast across a cluster of CTAs on consecutive M tiles (gemm_mcast.cuh) where the weight operand
+    // dominates the operand traffic: the split-K convolutions of the <= 8x8 maps.  The cluster size follows from the M
+    // tile count (a pure work-distribution choice: the arithmetic is the 1-CTA kernel's).
+    int cs = 0;
+    if (c.gemm_mcast && ks > 1 && stride == 1 && M % 128 == 0) {
+      const long long mt = M / 128;
+      cs = mt % 8 == 0 ? 8 : (mt % 4 == 0 ? 4 : (mt % 2 == 0 ? 2 : 0));
+    }
     const uint64_t db[2] = {(uint64_t)w.kp, (uint64_t)round_up(w.cout, 32)};
     const uint64_t sb[1] = {(uint64_t)w.kp * 2};
-    const uint32_t bb[2] = {64, (uint32_t)g.BN};
+    const uint32_t bb[2] = {64, (uint32_t)(cs > 1 ? g.BN / cs : g.BN)};
     CUtensorMap tmA = make_tmap(c, x.p, 4, da, sa, ba, stride > 1 ? ea : nullptr);
     CUtensorMap tmB = make_tmap(c, w.w, 2, db, sb, bb);
     dim3 grid((unsigned)((M + 127) / 128), (unsigned)((w.cout + g.BN - 1) / g.BN), (unsigned)ks);
-    launch_gemm(c, tmA, tmB, g, grid, 9.0 * w.cin / ks, w.w, w.kp, round_up(w.cout, 32));
+    launch_gemm(c, tmA, tmB, g, grid, 9.0 * w.cin / ks, w.w, w.kp, round_up(w.cout, 32), nullptr, cs);
     if (ks > 1) {
       splitk_finish(c, part, ks, M, w.cout, e_full, y.p, y.c);
       c.release(mk_split);

@@ -37,6 +37,32 @@ def test_linear_tcgen05(engine, M, K, N):
     assert rel(y, ref) < 4e-3, rel(y, ref)
 
 
+@pytest.mark.parametrize("kind", ["linear", "linear_res", "geglu", "conv"])
+def test_cta_pair_kernel(engine, kind):
+    """gemm_pair.cuh (tcgen05 cta_group::2: 256-row tiles over a CTA pair, each CTA loading half of the B tile) is opt-in
+    (option gemm_pair; slower than the 1-CTA kernel on the UNet's shapes) but must stay correct: same K order per output
+    element as the default kernel, so the results are the same bits."""
+    def run():
+        if kind == "conv":
+            x, w, b = h(rn(4, 640, 32, 32, seed=1)), h(rn(640, 640, 3, 3, seed=2) / math.sqrt(9 * 640)), rn(640, seed=3)
+            return engine.op_conv2d(x, w, b), F.conv2d(x, w, b, padding=1)
+        M, K, N = 4096, 1280, 1280
+        x, w, b = h(rn(M, K, seed=1)), h(rn(N * (2 if kind == "geglu" else 1), K, seed=2) / math.sqrt(K)), rn(N * (2 if kind == "geglu" else 1), seed=3)
+        if kind == "geglu":
+            a, gate = F.linear(x, w, b).chunk(2, dim=-1)
+            return engine.op_linear(x, w, b, geglu=True), a * F.gelu(gate)
+        r = h(rn(M, N, seed=4)) if kind == "linear_res" else None
+        return engine.op_linear(x, w, b, residual=r), F.linear(x, w, b) + (r if r is not None else 0)
+    y1, ref = run()
+    engine.set_option("gemm_pair", 1)
+    try:
+        y2, _ = run()
+    finally:
+        engine.set_option("gemm_pair", 0)
+    assert rel(y2, ref) < 4e-3, rel(y2, ref)
+    assert torch.equal(y1, y2)
+
+
 @pytest.mark.parametrize("act,fn", [(1, F.silu), (2, F.gelu), (3, lambda v: v * torch.sigmoid(1.702 * v))])
 def test_linear_epilogues(engine, act, fn):
     M, K, N = 512, 640, 640
@@ -254,6 +280,14 @@ def test_split_k_is_batch_independent(engine, batch):
     finally:
         engine.set_option("gemm_splitk", 1)
     assert rel(y0, ref) < 4e-3 and not torch.equal(y0, y)
+    # the K slices run as clusters of CTAs sharing each weight tile by TMA multicast (gemm_mcast.cuh): a pure
+    # work-distribution change, the bits are those of the 1-CTA kernel
+    engine.set_option("gemm_mcast", 0)
+    try:
+        y_nomc = engine.op_conv2d(x, w, b)
+    finally:
+        engine.set_option("gemm_mcast", 1)
+    assert torch.equal(y_nomc, y)
 
 
 def test_paste_back_bit_exact(engine, oracle):
