@@ -25,7 +25,7 @@ for (N, L, heads, d) in ([] if os.environ.get("ONLY") == "gn" else [(16, 4096, 8
     q, k, v = qkv.chunk(3, dim=-1)
     sp = lambda t: t.reshape(N, L, heads, d).transpose(1, 2)
     ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(N, L, C)
-    for mode, poly, pad in ((4, 0, 0), (4, 0, 1), (4, 2, 1), (4, 0, 0), (4, 0, 1), (3, 0, 0)):   # pad = MUFU turn-taking on/off
+    for mode, poly, pad in ((4, 0, 1), (4, 1, 1), (4, 1, 0), (4, 0, 1), (4, 1, 1), (4, 1, 0), (4, 0, 0)):   # pad = MUFU turn-taking on/off
         eng.set_option("attn_flash", mode)
         eng.set_option("attn_poly", poly)
         eng.set_option("attn_pingpong", pad)
