@@ -314,9 +314,11 @@ def main():
                 gpu_launches=int(launches),
                 roofline=dict(bound="tensor", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s",
                               frac=achieved / pk["tflops"], traffic=traffic, traffic_source=traffic_src,
-                              kernel="gemm_persist_kernel (tcgen05 GEMM / implicit-GEMM conv) + attn_flash4/3_kernel (fused attention)",
+                              kernel="gemm_persist_kernel / gemm_mcast_kernel (tcgen05 GEMM / implicit-GEMM conv) + attn_flash4/3_kernel (fused attention)",
                               alg_flop_per_unit=fpf,
-                              launches_per_step=int(g_n), kernel_ms_per_step=g_ms, alg_tflop_per_step=g_flops / 1e12,
+                              launches_per_step=int(g_n), kernel_ms_per_step=g_ms, executed_tflop_per_step=g_flops / 1e12,
+                              flops_note="achieved = EXECUTED tensor-core FLOPs / their CUDA-event time (folded upsample convs "
+                                         "execute 4/9 of the reference's MACs); whole_path_frac uses the reference-equivalent FLOPs",
                               share_of_step=g_ms / (ms / args.steps), peak_source=pk["source"] + ", sustained bf16",
                               whole_path_frac=(value / world) * fpf / (pk["tflops"] * 1e12) if fpf else None),
                 clocks=sampler.summary() if rank == 0 else None, arena_peak_gb=eng.arena_peak / 2 ** 30)

@@ -634,7 +634,10 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       if (tw) RFB_STAMP(j, 13);
       if (tw1) RFB_STAMP1(j, 13);
-      // POLY of every 8 exponentials (whole fp16 pairs) go to the FMA pipe.  A warp issues in order, so a warp that is
+      // POLY of every 8 exponentials (whole fp16 pairs) go to the FMA pipe (option attn_poly; measured slower in every
+      // arrangement -- interleaved per element, opposite order in the two column halves, and (round 2) ONE of the four
+      // warps of a sub-partition doing all its exponentials by polynomial: 814-880 us against 700-730 us, that warp
+      // becomes the straggler every tile waits for; profiles/r02_s3_attn_micro.txt).  A warp issues in order, so a warp that is
       // blocked on a full MUFU queue cannot reach polynomial work further down its stream: the two column halves of a
       // quadrant (which share an SM sub-partition) therefore run the two kinds in OPPOSITE order.
       auto exp_pair = [&](int i, bool poly) {
@@ -649,18 +652,6 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (POLY == 0) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) exp_pair(i, false);
-      } else if (POLY == 1) {
-        // warp-specialised split: of the four softmax warps that share a sub-partition, ONE (second query tile, upper
-        // column half) evaluates all its exponentials on the FMA pipe, the other three use MUFU.  A warp issues in order,
-        // so mixing the two kinds inside one warp let a full MUFU queue block the polynomial work behind it (the
-        // interleaved POLY = 2 form: slower); a warp that never touches MUFU just fills the issue slots the others leave.
-        if (g == 1 && hh == 1) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) exp_pair(i, true);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) exp_pair(i, false);
-        }
       } else if (hh == 0) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -749,8 +740,6 @@ static void launch_flash4(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, 
     CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 0, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 2, NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 2, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 1, NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    CUDA_OK(cudaFuncSetAttribute(attn_flash4_kernel<DP, 1, NS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
   }
   dim3 grid((unsigned)(L / 256), (unsigned)(N * heads));
   Ctx::ProfRec rec;
@@ -772,10 +761,7 @@ static void launch_flash4(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, 
 #define RFB_FLASH4(POLY_, PP_)                                                                                    \
   attn_flash4_kernel<DP, POLY_, NS, PP_><<<grid, 576, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg, \
                                                                              c.attn_stagger)
-  if (c.attn_poly == 1) {
-    if (c.attn_pingpong) RFB_FLASH4(1, 1);
-    else RFB_FLASH4(1, 0);
-  } else if (c.attn_poly) {
+  if (c.attn_poly) {
     if (c.attn_pingpong) RFB_FLASH4(2, 1);
     else RFB_FLASH4(2, 0);
   } else {

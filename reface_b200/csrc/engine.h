@@ -92,7 +92,7 @@ struct Ctx {
   int gemm_pair = 0;
   int attn_stagger = 0;  // attention v4: cycles by which the second query tile's softmax starts late
   int attn_pad = 0;      // test hook: rfb_op_attention repacks q/k/v with 64-element head slices
-  int attn_pingpong = 1; // attention v4: the two query tiles' softmax warps take turns on the MUFU unit (see attn_flash.cu)
+  int attn_pingpong = 0; // (opt-in: +2 % on one box, -3 % on another) attention v4: the two query tiles' softmax warps take turns on the MUFU unit (see attn_flash.cu)
   int attn_poly = 0;     // attention v3/v4: exponentials per 8 evaluated on the FMA pipe (measured slower: off)
   int cfg_share = 1;     // samplers: compute the context-independent head of the UNet once per CFG pair
   int conv_tma_stride2 = 1;  // stride-2 3x3 convs as implicit GEMM through strided TMA boxes (0: explicit im2col)

@@ -7,6 +7,9 @@
 #   ref              bench.py --impl reference                    stages         per-stage times of one step
 #   shapes           per-launch tensor-core table of one UNet forward (scripts/gemm_shapes.py)
 #   ab:"o=v,o=v;..." scripts/unet_ab.py A/B of engine options     micro          scripts/micro_bench.py
+#   scale:N[:wl]     bench.py on N GPUs (torchrun), workload 512 / 1024 / video
+#   ncu:W:K          ncu --set full of the kernels matching K in scripts/ncu_ops.py WHAT=W    trace[:pp]  attention clock64 trace
+#   unetlaunches     ncu launch list of one UNet forward
 #   launches         ncu launch list (gpu__time_duration) of a bench window -> gpurun_out/launches.txt
 #   env: TAG names the output files (default r02), RFB_* are forwarded to the engine as options
 mkdir -p gpurun_out
@@ -32,6 +35,10 @@ for task in "$@"; do
          WHAT=$what timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kre -c ${COUNT:-2} -o gpurun_out/${TAG}_$what -f python scripts/ncu_ops.py > gpurun_out/${TAG}_ncu_$what.log 2>&1
          python scripts/ncu_summary.py gpurun_out/${TAG}_$what.ncu-rep > gpurun_out/${TAG}_${what}_ncu_full.txt 2>&1; cat gpurun_out/${TAG}_${what}_ncu_full.txt | head -60 ;;
     trace) PINGPONG=${arg:-1} timeout 300 python scripts/attn_trace.py > gpurun_out/${TAG}_attn_trace_pp${arg:-1}.txt 2>&1; cat gpurun_out/${TAG}_attn_trace_pp${arg:-1}.txt | cut -c1-260 | head -26 ;;
+    scale) # scale:<N>[:<workload>]  bench.py on N GPUs of this box (one rank per GPU, torchrun)
+         n=${arg%%:*}; wl=512; [[ "$arg" == *:* ]] && wl=${arg#*:}
+         timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --workload $wl --steps ${STEPS:-5} --warmup 3 > gpurun_out/${TAG}_bench_${wl}_${n}gpu.json 2> gpurun_out/${TAG}_bench_${wl}_${n}gpu.err
+         tail -c 1800 gpurun_out/${TAG}_bench_${wl}_${n}gpu.json; tail -2 gpurun_out/${TAG}_bench_${wl}_${n}gpu.err ;;
     micro) timeout 900 python scripts/micro_bench.py > gpurun_out/${TAG}_micro.log 2>&1; tail -40 gpurun_out/${TAG}_micro.log ;;
     launches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip ${SKIP:-30000} -c ${COUNT:-9000} --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
               python scripts/agg_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches.txt; head -34 gpurun_out/${TAG}_launches.txt; rm -f gpurun_out/${TAG}_launches.csv ;;

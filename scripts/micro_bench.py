@@ -46,7 +46,7 @@ for (N, L, heads, d) in ([] if os.environ.get("ONLY") == "gn" else [(16, 4096, 8
     del qkv, ref, y
 eng.set_option("attn_flash", 4)
 eng.set_option("attn_poly", 0)
-eng.set_option("attn_pingpong", 1)
+eng.set_option("attn_pingpong", 0)
 if os.environ.get("ONLY") == "attn":
     sys.exit(0)
 if os.environ.get("ONLY") == "gn":

@@ -195,3 +195,39 @@ def test_full_size_batch_and_shard_independence(engine, unet_sd, vae_sd, clip_sd
     parts = [swap_faces(model, S=2, scale=3.5, **shard_batch(inp, r, 2))["image"] for r in range(2)]
     assert bool(torch.isfinite(full).all())
     assert torch.equal(full, torch.cat(parts, 0))
+
+
+def test_activation_outliers_stay_finite_and_accurate(engine, oracle, clip_sd, unet_sd):
+    """Real checkpoints produce activations far from the unit scale of random-init weights (CLIP's residual stream carries
+    a few channels in the hundreds; latents at late DDIM steps reach |x| ~ 80 here).  The fp16 NHWC activations must stay
+    finite and within tolerance when the synthetic weights are re-scaled to create such outliers."""
+    # CLIP: two residual-stream channels pushed to ~ +-300 through the position embedding (pre-LN ViT: they persist
+    # through all 24 layers), patch embedding 8x larger
+    sd = {k: v.clone() for k, v in clip_sd.items()}
+    pos = sd[oracle.PFX_CLIP + "model.vision_model.embeddings.position_embedding.weight"]
+    pos[:, 7] += 300.0
+    pos[:, 500] -= 250.0
+    sd[oracle.PFX_CLIP + "model.vision_model.embeddings.patch_embedding.weight"] *= 8.0
+    engine.load_state_dict(sd)
+    engine.build_clip()
+    img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(31)) * 2.0
+    with torch.no_grad():
+        ref = oracle.clip_embed(oracle.Params(sd, oracle.PFX_CLIP), img)
+    out = engine.clip_encode(img).cpu()
+    assert torch.isfinite(out).all()
+    print("clip with outliers", rel(out, ref))
+    assert rel(out, ref) < 3e-2
+    engine.load_state_dict(clip_sd)          # restore for the tests that follow
+    engine.build_clip()
+    # UNet: latents / inpaint channels 40x the unit scale (|x| up to ~150), as at the end of a random-init sampling run
+    engine.load_state_dict(unet_sd)
+    engine.build_unet()
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(2, 9, 16, 16, generator=g) * 40.0
+    t, ctx = torch.tensor([21, 21]), torch.randn(2, 1, 768, generator=g) * 5.0
+    with torch.no_grad():
+        ref = oracle.unet_forward(oracle.Params(unet_sd, oracle.PFX_UNET), x, t, ctx)
+    eps = engine.unet_forward(x, t, ctx).cpu()
+    assert torch.isfinite(eps).all()
+    print("unet with 40x inputs", rel(eps, ref))
+    assert rel(eps, ref) < 2e-2
