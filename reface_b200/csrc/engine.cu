@@ -129,7 +129,6 @@ LinW pack_geglu(Ctx& c, const std::string& wname, const std::string& bname, int 
                                                                              w.kp, BN);
   LAUNCH_CHECK(c);
   w.b = bo;
-  w.bn = BN;
   return w;
 }
 Lin32 lin32(Ctx& c, const std::string& wname, const std::string& bname) {
@@ -334,28 +333,12 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     const int np = (g.nk <= c.gemm_epi3_max_nk && g.BN > 64 && g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f) ? 3 : 2;
     const int budget = (227 - 3) * 1024 - 4 * np * EPI_WARP_BYTES;
     int ps = c.force_stages ? c.force_stages : std::max(2, std::min(8, budget / stage_bytes));
+    g.stages = ps;
+    const size_t psmem = gemmp_smem_bytes(ps, g.BN, np);
+    RFB_CHECK(psmem <= 227 * 1024, "GEMM smem over budget");
     const int m_tiles = (int)grid.x, n_tiles = (int)grid.y;
     const int total = m_tiles * n_tiles * (int)grid.z;
-    int ctas = std::min(total, c.num_sms);
-    size_t psmem = gemmp_smem_bytes(ps, g.BN, np);
-    // Weight-stationary schedule for the K <= 320 GEMMs of the 64x64 level (QKV, proj_in/out, attention out-projection,
-    // GEGLU in-projection): a 128 x BN x 320 tile needs (128 + BN) * 640 B of operands for 20 MMAs, ~2x what an SM can pull
-    // from L2 in that time (measured ~57 B/clk/SM on every GEMM of this kernel family).  Keeping the CTA's B tile (all
-    // nk k-blocks) resident and streaming only A tiles halves the operand traffic.  The K order per output element is
-    // unchanged -> same bits.
-    g.b_stat = 0;
-    if (c.gemm_bstat && g.b_mode == B_PLAIN && g.a_mode == A_PLAIN && grid.z == 1 && !g.ksplit && g.nk <= 5 &&
-        n_tiles <= c.num_sms && m_tiles >= 2 * (c.num_sms / n_tiles)) {
-      const int a_stages = (budget - g.nk * g.BN * 128) / GEMM_A_STAGE_BYTES;
-      if (a_stages >= 3) {
-        g.b_stat = 1;
-        ps = std::min(8, a_stages);
-        psmem = gemmp_smem_bytes_bstat(ps, g.BN, g.nk, np);
-        ctas = n_tiles * (c.num_sms / n_tiles);
-      }
-    }
-    g.stages = ps;
-    RFB_CHECK(psmem <= 227 * 1024, "GEMM smem over budget");
+    const int ctas = std::min(total, c.num_sms);
     const int thr = 64 + np * 128;
     if (g.geglu) {
       if (np == 3) gemm_persist_kernel<EPI_GEGLU, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
@@ -471,7 +454,7 @@ Tens linear_t(Ctx& c, const Tens& x, const LinW& w, Epi e) {
   e.stats_out = nullptr;
   if (epi_stats_ok(c, e, w.out, out_c, (long long)x.h * x.w))
     e.stats_out = y.stats = c.alloc_t<float>((size_t)(y.rows() / 32) * out_c * 2);
-  gemm(c, x.p, x.c, x.rows(), x.c, w.w, w.kp, w.out, y.p, out_c, e, e.geglu ? w.bn : 0);
+  gemm(c, x.p, x.c, x.rows(), x.c, w.w, w.kp, w.out, y.p, out_c, e);
   return y;
 }
 

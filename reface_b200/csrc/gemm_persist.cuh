@@ -24,22 +24,12 @@ __host__ __device__ inline size_t gemmp_smem_bytes(int stages, int BN, int np = 
   return 2048 + (size_t)stages * (GEMM_A_STAGE_BYTES + (size_t)BN * 128) + 16 * stages + 128 +
          (size_t)(4 * np) * EPI_WARP_BYTES;
 }
-// weight-stationary layout: `stages` A tiles + all nk k-blocks of one B tile
-__host__ __device__ inline size_t gemmp_smem_bytes_bstat(int stages, int BN, int nk, int np) {
-  return 2048 + (size_t)stages * GEMM_A_STAGE_BYTES + (size_t)nk * BN * 128 + 16 * stages + 128 +
-         (size_t)(4 * np) * EPI_WARP_BYTES;
-}
 
 // (z, m_tile, n_tile) of the tiles a CTA visits (tile = blockIdx.x + i * gridDim.x), advanced with adds and compares:
 // decomposing the linear tile index with runtime integer divisions cost ~280 instructions per epilogue warp and
 // tile (28 % of everything the K=320 GEMMs executed, profiles/r01s2_gemm_k320_ncu_full.txt).
 struct TileIter {
   int z, m_tile, n_tile, step_z, step_m, step_n;
-  // weight-stationary schedule: fixed N tile, M tiles blockIdx.x / n_tiles, + gridDim.x / n_tiles, ...
-  __device__ __forceinline__ void init_bstat(int cta, int ctas, int n_tiles) {
-    z = 0, n_tile = cta % n_tiles, m_tile = cta / n_tiles;
-    step_z = 0, step_n = 0, step_m = ctas / n_tiles;
-  }
   __device__ __forceinline__ void init(int tile, int stride, int m_tiles, int n_tiles) {
     const int per_z = m_tiles * n_tiles;
     z = tile / per_z;
@@ -70,21 +60,11 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t sA = base;
   const uint32_t sB = base + (uint32_t)S * GEMM_A_STAGE_BYTES;
   const uint32_t b_stage_bytes = (uint32_t)BN * 128u;
-  // B region: a ring of S stages, or (weight-stationary schedule) all nk k-blocks of this CTA's one N tile
-  const uint32_t bars = sB + (uint32_t)(g.b_stat ? g.nk : S) * b_stage_bytes;  // full[S], empty[S]
+  const uint32_t bars = sB + (uint32_t)S * b_stage_bytes;  // full[S], empty[S]
   const uint32_t bar_accf = bars + 16u * S;                // acc_full[2]
   const uint32_t bar_acce = bar_accf + 16u;                // acc_empty[2]
-  const uint32_t bar_bfull = bar_acce + 16u;               // weight-stationary: the B tile has landed
-  const uint32_t tptr = bar_bfull + 16u;
+  const uint32_t tptr = bar_acce + 16u;
   const uint32_t epi_stage = (tptr + 16u + 1023u) & ~1023u;  // 8 x 4 KB staging tiles
-  // tiles of this CTA: round-robin over (z, m, n) with n fastest, or a fixed N tile and every (gridDim / n_tiles)-th M tile
-  int my_tiles;
-  if (g.b_stat) {
-    const int per_n = (int)gridDim.x / n_tiles, m0 = (int)blockIdx.x / n_tiles;
-    my_tiles = m0 < m_tiles ? (m_tiles - m0 + per_n - 1) / per_n : 0;
-  } else {
-    my_tiles = (int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
@@ -95,7 +75,6 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(bar_accf + 8u * i, 1);
       mbar_init(bar_acce + 8u * i, 4 * NP);
     }
-    mbar_init(bar_bfull, 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -112,21 +91,11 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (converged warp, elected issue)
-    const uint32_t tx = g.b_stat ? GEMM_A_STAGE_BYTES : GEMM_A_STAGE_BYTES + b_stage_bytes;
+    const uint32_t tx = GEMM_A_STAGE_BYTES + b_stage_bytes;
     uint32_t st = 0, sp = 0;
     TileIter it;
-    if (g.b_stat) {
-      it.init_bstat(blockIdx.x, gridDim.x, n_tiles);
-      if (my_tiles > 0 && elect_one()) {  // the whole B operand of this CTA's N tile, once
-        mbar_expect_tx(bar_bfull, (uint32_t)g.nk * b_stage_bytes);
-        for (int kb = 0; kb < g.nk; ++kb)
-          tma_load_2d(sB + (uint32_t)kb * b_stage_bytes, &tmB, bar_bfull, kb * GEMM_BK, it.n_tile * BN);
-      }
-      __syncwarp();
-    } else {
-      it.init(blockIdx.x, gridDim.x, m_tiles, n_tiles);
-    }
-    for (int ti = 0; ti < my_tiles; ++ti, it.next(m_tiles, n_tiles)) {
+    it.init(blockIdx.x, gridDim.x, m_tiles, n_tiles);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it.next(m_tiles, n_tiles)) {
       const int z = it.z, m_tile = it.m_tile, n_tile = it.n_tile;
       int cw = 0, ch = 0, cn = 0;
       if (g.a_mode == A_CONV3) {
@@ -169,7 +138,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             case A_BATCH3: tma_load_3d(dA, &tmA, full, kb * GEMM_BK, m0, z); break;
             default: tma_load_4d(dA, &tmA, full, kb * GEMM_BK, z % g.heads, m0, z / g.heads); break;
           }
-          if (!g.b_stat) switch (g.b_mode) {
+          switch (g.b_mode) {
             case B_PLAIN: tma_load_2d(dB, &tmB, full, kg * GEMM_BK, n0); break;
             case B_BATCH3: tma_load_3d(dB, &tmB, full, kb * GEMM_BK, n0, z); break;
             default: tma_load_4d(dB, &tmB, full, kb * GEMM_BK, z % g.heads, n0, z / g.heads); break;
@@ -181,9 +150,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (converged warp, elected issue)
     const uint32_t idesc = idesc_f16(GEMM_BM, (uint32_t)BN);
-    uint32_t st = 0, sp = 0;
-    if (g.b_stat && my_tiles > 0) mbar_wait(bar_bfull, 0);
-    for (uint32_t ti = 0; ti < (uint32_t)my_tiles; ++ti) {
+    uint32_t ti = 0, st = 0, sp = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
       mbar_wait(bar_acce + 8u * as, aph ^ 1u);  // epilogue has drained this accumulator stage
       tc_fence_after();
@@ -195,7 +163,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         if (elect_one()) {
           const uint64_t da = smem_desc_k_sw128(sA + s * GEMM_A_STAGE_BYTES);
-          const uint64_t db = smem_desc_k_sw128(sB + (g.b_stat ? (uint32_t)kb : s) * b_stage_bytes);
+          const uint64_t db = smem_desc_k_sw128(sB + s * b_stage_bytes);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
             mma_f16_ss(tacc, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
@@ -211,21 +179,21 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;   // TMEM lane quadrant
     const int half = e >> 2;  // which 64-column chunks this warp drains
     const uint32_t stage = epi_stage + (uint32_t)e * EPI_WARP_BYTES;  // this warp's staging tile + bias strip
+    uint32_t ti = 0;
     float nb[4] = {0.f, 0.f, 0.f, 0.f};
     TileIter it;
-    if (g.b_stat) it.init_bstat(blockIdx.x, gridDim.x, n_tiles);
-    else it.init(blockIdx.x, gridDim.x, m_tiles, n_tiles);
-    if (my_tiles > 0) {
+    it.init(blockIdx.x, gridDim.x, m_tiles, n_tiles);
+    if ((int)blockIdx.x < total_tiles) {
       const EpiTile e0 = epi_tile_info<MODE>(g, q, it.m_tile, it.n_tile, it.z);
       epilogue_lookahead<MODE, NP>(g, e0, lane, half, nb);
     }
-    for (uint32_t ti = 0; ti < (uint32_t)my_tiles; ++ti) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
       const int n_tile = it.n_tile;
       const EpiTile et = epi_tile_info<MODE>(g, q, it.m_tile, it.n_tile, it.z);
       epilogue_prefetch<MODE, NP>(g, et, stage, lane, half, n_tile, nb);  // bias / residual while the MMAs still run
       it.next(m_tiles, n_tiles);
-      if (ti + 1 < (uint32_t)my_tiles) {  // next tile's bias -> registers, residual lines -> L2
+      if (tile + (int)gridDim.x < total_tiles) {  // next tile's bias -> registers, residual lines -> L2
         const EpiTile en = epi_tile_info<MODE>(g, q, it.m_tile, it.n_tile, it.z);
         epilogue_lookahead<MODE, NP>(g, en, lane, half, nb);
       }

@@ -29,9 +29,6 @@ struct GemmArgs {
   // and the sum of squares of the fp16 results, stats[(prow * N + col) * 2 + {0,1}], prow = m / 32 (folded upsample conv:
   // (m / 32) * 4 + phase, which keeps every sample's partial rows contiguous).  nullptr: off.
   float* stats;
-  // Weight-stationary schedule for short-K GEMMs (K <= 640): a CTA keeps ONE N tile's whole B operand (nk k-blocks) in
-  // shared memory and walks M tiles (m = blockIdx.x / n_tiles, step gridDim.x / n_tiles); only A streams through the ring.
-  int b_stat;
   // A_PLAIN over TWO row-aligned sources (channel concatenation without the copy): k-blocks [0, nk1) come from tmA, the
   // rest from tmA2; a2_mod > 0: source 2 has only a2_mod rows and is read at row (m mod a2_mod) (CFG halves sharing a tensor)
   int nk1, a2_mod;

@@ -44,9 +44,7 @@ static STW build_st(Ctx& c, const std::string& p, int ch, int heads, int ctx_dim
   s.q2 = pack_linear(c, b + "attn2.to_q.weight", "");
   s.kv2 = pack_linear_rows(c, {b + "attn2.to_k.weight", b + "attn2.to_v.weight"});
   s.o2h = pack_linear(c, b + "attn2.to_out.0.weight", b + "attn2.to_out.0.bias");
-  // GEGLU tile width (value rows | gate rows interleaved per tile): 256, but 128 for the 320-channel blocks whose K = 320
-  // in-projection runs weight-stationary (a 256 x 320 B tile + the A ring would not fit shared memory)
-  s.ff_bn = ch <= 320 ? 128 : 256;
+  s.ff_bn = 256;
   while ((8 * ch) % s.ff_bn) s.ff_bn /= 2;
   s.ff1 = pack_geglu(c, b + "ff.net.0.proj.weight", b + "ff.net.0.proj.bias", s.ff_bn);
   s.ff2 = pack_linear(c, b + "ff.net.2.weight", b + "ff.net.2.bias");

@@ -37,32 +37,6 @@ def test_linear_tcgen05(engine, M, K, N):
     assert rel(y, ref) < 4e-3, rel(y, ref)
 
 
-@pytest.mark.parametrize("M,K,N,kind", [(20480, 320, 320, "res"), (20480, 320, 960, "plain"), (20480, 320, 2560, "geglu"),
-                                          (24000, 256, 320, "plain"), (20480, 128, 256, "res")])
-def test_weight_stationary_schedule(engine, M, K, N, kind):
-    """K <= 320 GEMMs with many M tiles (the 64x64 level of the UNet) keep the CTA's whole B tile in shared memory and
-    stream only A tiles (option gemm_bstat): same K order per output element, so the same bits as the round-robin
-    schedule."""
-    x, w, b = h(rn(M, K, seed=1)), h(rn(N, K, seed=2) / math.sqrt(K)), rn(N, seed=3)
-    r = h(rn(M, N, seed=4)) if kind == "res" else None
-
-    def run():
-        return engine.op_linear(x, w, b, residual=r, geglu=(kind == "geglu"))
-    y = run()
-    engine.set_option("gemm_bstat", 0)
-    try:
-        y0 = run()
-    finally:
-        engine.set_option("gemm_bstat", 1)
-    if kind == "geglu":
-        a, gate = F.linear(x, w, b).chunk(2, dim=-1)
-        ref = a * F.gelu(gate)
-    else:
-        ref = F.linear(x, w, b) + (r if r is not None else 0)
-    assert rel(y, ref) < 4e-3, rel(y, ref)
-    assert torch.equal(y, y0)
-
-
 @pytest.mark.parametrize("kind", ["linear", "linear_res", "geglu", "conv"])
 def test_cta_pair_kernel(engine, kind):
     """gemm_pair.cuh (tcgen05 cta_group::2: 256-row tiles over a CTA pair, each CTA loading half of the B tile) is opt-in
