@@ -101,15 +101,21 @@ struct Flash3Cfg {
   static constexpr int Q_BYTES = NC * CHUNK;
   static constexpr int KV_BYTES = NC * CHUNK;
   static constexpr int XCHG_BYTES = 2 * 2 * 128 * 4;  // row-max exchange [tile parity][half][row]
-  // K / V ring depth: two stages where they fit next to Q (head dim <= 128), one for the 160-wide heads of the 16x16 /
-  // 8x8 levels (L <= 256: at most two KV tiles anyway)
-  static constexpr int STAGES = (Q_BYTES + 4 * KV_BYTES + XCHG_BYTES + 128 <= 227 * 1024) ? 2 : 1;
+  // COMPACT (64 < head dim <= 128, i.e. d = 80): P is written over the first 64 columns of the S tile it was computed
+  // from, so S | O fit 256 TMEM columns and TWO CTAs share an SM (16 softmax warps keep the MUFU unit busy; with one CTA
+  // the 8 warps of the 32x32 level left it half idle).  Price: Q.K^T of tile j+1 can only be issued after P.V of tile j
+  // (it would overwrite P) -- the other CTA's work fills that gap.  One K / V stage each.
+  static constexpr bool COMPACT = DP > 64 && DP <= 128;
+  // K / V ring depth: two stages where they fit next to Q (head dim <= 64), one for COMPACT and for the 160-wide heads
+  // of the 16x16 / 8x8 levels (L <= 256: at most two KV tiles anyway)
+  static constexpr int STAGES = (!COMPACT && Q_BYTES + 4 * KV_BYTES + XCHG_BYTES + 128 <= 227 * 1024) ? 2 : 1;
   static constexpr int SMEM = Q_BYTES + 2 * STAGES * KV_BYTES + XCHG_BYTES + 128;
-  static constexpr int TMEM_COLS = (DP <= 64) ? 256 : 512;
-  static constexpr int P_COL = (DP <= 64) ? 192 : (DP <= 128 ? 256 : 320);  // S [0,128) | O [128,128+DP) | P 64 columns
+  static constexpr int TMEM_COLS = (DP <= 128) ? 256 : 512;
+  static constexpr int P_COL = COMPACT ? 0 : ((DP <= 64) ? 192 : 320);  // S [0,128) | O [128,128+DP) | P 64 columns
   static constexpr int SPLIT = (DP <= 48) ? 24 : (DP <= 64 ? 32 : (DP <= 80 ? 40 : 80));  // output columns of a quadrant's first warp
-  static constexpr int MIN_CTAS = (DP <= 64) ? 2 : 1;
-  static_assert(P_COL >= 128 + DP && P_COL + 64 <= TMEM_COLS, "TMEM layout");
+  static constexpr int MIN_CTAS = (DP <= 128) ? 2 : 1;
+  static_assert(COMPACT || (P_COL >= 128 + DP && P_COL + 64 <= TMEM_COLS), "TMEM layout");
+  static_assert(128 + DP <= TMEM_COLS, "TMEM layout");
 };
 
 template <int DP, int POLY>
@@ -200,6 +206,29 @@ attn_flash3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t idesc_o = idesc_f16(128, DP, 0, 1);  // B (= V) is MN-major
     mbar_wait(b_q, 0);
     for (int j = 0; j <= ntiles; ++j) {
+      // COMPACT: P(j-1) occupies the S columns, so P.V(j-1) is issued BEFORE Q.K^T(j) (tcgen05.mma executes in issue order)
+      auto issue_pv = [&]() {
+        if (j > 0) {
+        const int jj = j - 1, s = jj % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(jj / Cfg::STAGES) & 1u;
+        mbar_wait(b_vf + 8 * s, ph);
+        RFB_STAMP(jj, 12);
+        mbar_wait(b_pfull, (uint32_t)jj & 1u);
+        RFB_STAMP(jj, 3);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t db = smem_desc_mn_sw128(sV + s * Cfg::KV_BYTES + k * 2048, Cfg::CHUNK);
+            mma_f16_ts(tO, tP + 8u * k, db, idesc_o, (jj > 0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit(b_ve + 8 * s);
+          mma_commit(b_pfree);
+        }
+        __syncwarp();
+        }
+      };
+      if (Cfg::COMPACT) issue_pv();
       if (j < ntiles) {
         const int s = j % Cfg::STAGES;
         const uint32_t ph = (uint32_t)(j / Cfg::STAGES) & 1u;
@@ -226,25 +255,7 @@ attn_flash3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         __syncwarp();
       }
-      if (j > 0) {
-        const int jj = j - 1, s = jj % Cfg::STAGES;
-        const uint32_t ph = (uint32_t)(jj / Cfg::STAGES) & 1u;
-        mbar_wait(b_vf + 8 * s, ph);
-        RFB_STAMP(jj, 12);
-        mbar_wait(b_pfull, (uint32_t)jj & 1u);
-        RFB_STAMP(jj, 3);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t db = smem_desc_mn_sw128(sV + s * Cfg::KV_BYTES + k * 2048, Cfg::CHUNK);
-            mma_f16_ts(tO, tP + 8u * k, db, idesc_o, (jj > 0 || k > 0) ? 1u : 0u);
-          }
-          mma_commit(b_ve + 8 * s);
-          mma_commit(b_pfree);
-        }
-        __syncwarp();
-      }
+      if (!Cfg::COMPACT) issue_pv();
     }
   } else {
     // ------------------------------------------------------------------ softmax warps 2..9
