@@ -316,9 +316,12 @@ def main():
                               frac=achieved / pk["tflops"], traffic=traffic, traffic_source=traffic_src,
                               kernel="gemm_persist_kernel / gemm_mcast_kernel (tcgen05 GEMM / implicit-GEMM conv) + attn_flash4/3_kernel (fused attention)",
                               alg_flop_per_unit=fpf,
-                              launches_per_step=int(g_n), kernel_ms_per_step=g_ms, executed_tflop_per_step=g_flops / 1e12,
-                              flops_note="achieved = EXECUTED tensor-core FLOPs / their CUDA-event time (folded upsample convs "
-                                         "execute 4/9 of the reference's MACs); whole_path_frac uses the reference-equivalent FLOPs",
+                              launches_per_step=int(g_n), kernel_ms_per_step=g_ms, alg_tflop_per_step=g_flops / 1e12,
+                              executed_tflop_per_step=eng.last_executed_flops / 1e12,
+                              executed_frac=(eng.last_executed_flops / (g_ms / 1e3) / 1e12 / pk["tflops"]) if g_ms > 0 else None,
+                              flops_note="achieved = ALGORITHMIC (reference-equivalent, SURVEY 8d) FLOPs of the tensor-core launches / "
+                                         "their CUDA-event time; the folded upsample convs execute 4/9 of their reference MACs: "
+                                         "executed_* gives the tensor cores' own rate",
                               share_of_step=g_ms / (ms / args.steps), peak_source=pk["source"] + ", sustained bf16",
                               whole_path_frac=(value / world) * fpf / (pk["tflops"] * 1e12) if fpf else None),
                 clocks=sampler.summary() if rank == 0 else None, arena_peak_gb=eng.arena_peak / 2 ** 30)

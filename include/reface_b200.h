@@ -56,8 +56,9 @@ long long rfb_launch_count(rfb_ctx* ctx); /* kernels launched by this library so
 long long rfb_graph_replays(rfb_ctx* ctx);
 /* With option "profile"=1 every tensor-core (tcgen05 GEMM / implicit-GEMM conv / attention) launch is bracketed
  * by CUDA events on the launching stream; this drains them: summed device time [ms], summed ALGORITHMIC FLOPs
- * (2*M*N*K of the reference-equivalent contraction, no padding) and the number of launches. */
-int rfb_profile_read(rfb_ctx* ctx, double* ms, double* flops, long long* n_launches);
+ * (2*M*N*K of the reference-equivalent contraction, no padding: a folded upsample convolution counts the 9-tap
+ * convolution at output resolution that it replaces), summed EXECUTED FLOPs and the number of launches. */
+int rfb_profile_read(rfb_ctx* ctx, double* ms, double* flops, double* flops_executed, long long* n_launches);
 /* With option "gemm_debug"=1 the 2-CTA GEMM records per-CTA clock64 totals (8 x u64 per CTA: MMA-thread total, wait
  * on operands, wait on accumulator drain, producer wait, epilogue wait, epilogue total, k-stages, tiles). [host] out. */
 int rfb_debug_read(rfb_ctx* ctx, unsigned long long* out, int n_u64);

@@ -389,7 +389,7 @@ static void launch_flash3(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, 
   if (c.profile) {
     CUDA_OK(cudaEventCreate(&rec.a));
     CUDA_OK(cudaEventCreate(&rec.b));
-    rec.flops = 4.0 * (double)L * (double)L * (double)d * (double)N * (double)heads;
+    rec.flops = rec.flops_exec = 4.0 * (double)L * (double)L * (double)d * (double)N * (double)heads;
     rec.kind = 1;
     rec.M = L, rec.N = L, rec.K = d, rec.BN = DP, rec.z = N * heads;
     CUDA_OK(cudaEventRecord(rec.a, c.stream));
@@ -757,7 +757,7 @@ static void launch_flash4(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, 
   if (c.profile) {
     CUDA_OK(cudaEventCreate(&rec.a));
     CUDA_OK(cudaEventCreate(&rec.b));
-    rec.flops = 4.0 * (double)L * (double)L * (double)d * (double)N * (double)heads;
+    rec.flops = rec.flops_exec = 4.0 * (double)L * (double)L * (double)d * (double)N * (double)heads;
     rec.kind = 1;
     rec.M = L, rec.N = L, rec.K = d, rec.BN = DP, rec.z = N * heads;
     CUDA_OK(cudaEventRecord(rec.a, c.stream));

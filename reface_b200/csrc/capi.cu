@@ -225,14 +225,14 @@ int rfb_debug_read(rfb_ctx* h, unsigned long long* out, int n) {
                      cudaMemcpyDeviceToHost));
   API_END
 }
-int rfb_profile_read(rfb_ctx* h, double* ms, double* flops, long long* n) {
+int rfb_profile_read(rfb_ctx* h, double* ms, double* flops, double* flops_exec, long long* n) {
   API_BEGIN(h)
   CUDA_OK(cudaDeviceSynchronize());
-  double tms = 0, tf = 0;
+  double tms = 0, tf = 0, te = 0;
   for (auto& r : c.prof) {
     float e = 0;
     CUDA_OK(cudaEventElapsedTime(&e, r.a, r.b));
-    tms += e, tf += r.flops;
+    tms += e, tf += r.flops, te += r.flops_exec;
     if (c.profile >= 2)
       printf("PROF kind=%d M=%d N=%d K=%d BN=%d z=%d mode=%d us=%.2f tflops=%.1f\n", r.kind, r.M, r.N, r.K, r.BN, r.z, r.mode,
              e * 1e3, r.flops / (e * 1e-3) / 1e12);
@@ -241,6 +241,7 @@ int rfb_profile_read(rfb_ctx* h, double* ms, double* flops, long long* n) {
   }
   if (ms) *ms = tms;
   if (flops) *flops = tf;
+  if (flops_exec) *flops_exec = te;
   if (n) *n = (long long)c.prof.size();
   c.prof.clear();
   API_END

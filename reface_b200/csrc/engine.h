@@ -112,7 +112,9 @@ struct Ctx {
   int profile = 0;       // 1: time every tensor-core launch; 2: also print one line per launch in rfb_profile_read
   int gemm_debug = 0;                       // per-CTA clock64 counters of the last 2-CTA GEMM launch
   unsigned long long* dbg_buf = nullptr;    // [num_sms * 8]
-  struct ProfRec { cudaEvent_t a, b; double flops; int kind; int M = 0, N = 0, K = 0, BN = 0, mode = 0, z = 1; };
+  // flops: ALGORITHMIC (reference-equivalent: the folded upsample conv counts the 9-tap conv at output resolution it
+  // replaces); flops_exec: what the tensor cores executed
+  struct ProfRec { cudaEvent_t a, b; double flops; int kind; int M = 0, N = 0, K = 0, BN = 0, mode = 0, z = 1; double flops_exec = 0; };
   std::vector<ProfRec> prof;
   // CUDA graphs of whole sampling loops (unet.cu: ddim_sample), keyed by shape / schedule / arena mark / graph_epoch
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; bool failed = false; long long launches = 0; };

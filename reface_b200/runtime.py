@@ -35,7 +35,7 @@ SIGNATURES = {
     "rfb_launch_count": (_ll, [_vp]),
     "rfb_graph_replays": (_ll, [_vp]),
     "rfb_arena_peak": (_sz, [_vp]),
-    "rfb_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
+    "rfb_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
     "rfb_debug_read": (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
     "rfb_unet_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "rfb_concat9": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
@@ -193,9 +193,11 @@ class Engine:
         return int(self.lib.rfb_graph_replays(self.h))
 
     def profile_read(self):
-        """(ms, algorithmic_flops, n_launches) of the tensor-core launches since option 'profile' was set."""
-        ms, fl, n = C.c_double(), C.c_double(), _ll()
-        self._ck(self.lib.rfb_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(n)))
+        """(ms, algorithmic_flops, n_launches) of the tensor-core launches since option 'profile' was set; the executed
+        FLOPs of the same launches are left in `self.last_executed_flops`."""
+        ms, fl, fe, n = C.c_double(), C.c_double(), C.c_double(), _ll()
+        self._ck(self.lib.rfb_profile_read(self.h, C.byref(ms), C.byref(fl), C.byref(fe), C.byref(n)))
+        self.last_executed_flops = fe.value
         return ms.value, fl.value, n.value
 
     @property
