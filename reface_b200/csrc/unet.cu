@@ -510,6 +510,11 @@ void ddim_sample(Ctx& c, UNet& u, const float* x_T, const float* z_inpaint, cons
     add(s.a_prev.data(), s.a_prev.size() * sizeof(float));
     add(s.sigma.data(), s.sigma.size() * sizeof(float));
     add(s.sqrt_one_minus_a.data(), s.sqrt_one_minus_a.size() * sizeof(float));
+    if (c.graphs.size() >= 16 && !c.graphs.count(key)) {  // bounded cache: a server cycling through many shapes starts over
+      const long long epoch = c.graph_epoch;
+      c.drop_graphs();
+      c.graph_epoch = epoch;  // same options / weights: keys stay valid
+    }
     Ctx::GraphEntry& ge = c.graphs[key];
     ++ge.seen;
     if (!ge.exec && !ge.failed && ge.seen >= 2) {
