@@ -211,6 +211,8 @@ class Engine:
         N, _, L, _ = x9.shape
         T = context.shape[1]
         eps = self._new(N, 4, L, L)
+        if N == 0:          # empty batch: torch modules return empty tensors, so do we
+            return eps
         self._ck(self.lib.rfb_unet_forward(self.h, _ptr(x9), _ptr(t), _ptr(context), N, L, T, _ptr(eps), self._stream()))
         return eps
 
@@ -249,6 +251,8 @@ class Engine:
         x0 = torch.empty_like(x_T)
         inter_x = self._new(max(K, 1), *x_T.shape)
         inter_p = self._new(max(K, 1), *x_T.shape)
+        if B == 0:
+            return x0, inter_x[:K], inter_p[:K]
         hp = lambda a: a.ctypes.data_as(C.c_void_p)
         self._ck(self.lib.rfb_ddim_sample(self.h, _ptr(x_T), _ptr(z_inpaint), _ptr(mask), _ptr(cond), _ptr(uncond), B, L, T,
                                           hp(ts), hp(tabs[0]), hp(tabs[1]), hp(tabs[2]), hp(tabs[3]), n, float(scale),
@@ -272,6 +276,8 @@ class Engine:
         K = len([i for i in range(n) if log_every_t > 0 and (i % log_every_t == 0 or i == n - 1)])
         x0 = torch.empty_like(x_T)
         inter_x, inter_p = self._new(max(K, 1), *x_T.shape), self._new(max(K, 1), *x_T.shape)
+        if B == 0:
+            return x0, inter_x[:K], inter_p[:K]
         hp = lambda a: a.ctypes.data_as(C.c_void_p)
         self._ck(self.lib.rfb_plms_sample(self.h, _ptr(x_T), _ptr(z_inpaint), _ptr(mask), _ptr(cond), _ptr(uncond), B, L, T,
                                           hp(ts), hp(tabs[0]), hp(tabs[1]), hp(tabs[2]), hp(tabs[3]), n, float(scale),
@@ -334,6 +340,8 @@ class Engine:
         img, noise = self._in(img), self._in(noise)
         B, _, H, W = img.shape
         z, mean, logvar = self._new(B, 4, H // 8, W // 8), self._new(B, 4, H // 8, W // 8), self._new(B, 4, H // 8, W // 8)
+        if B == 0:
+            return (z, mean, logvar) if return_moments else z
         self._ck(self.lib.rfb_vae_encode(self.h, _ptr(img), _ptr(noise), B, H, W, float(scale_factor), _ptr(z), _ptr(mean),
                                          _ptr(logvar), self._stream()))
         return (z, mean, logvar) if return_moments else z
@@ -345,6 +353,8 @@ class Engine:
             z = z[:, :4].contiguous()   # ddpm.py:1334-1335
         B, _, h, w = z.shape
         img = self._new(B, 3, 8 * h, 8 * w)
+        if B == 0:
+            return img
         self._ck(self.lib.rfb_vae_decode(self.h, _ptr(z), B, h, w, float(scale_factor), _ptr(img), self._stream()))
         return img
 
@@ -352,6 +362,8 @@ class Engine:
         img224 = self._in(img224)
         B = img224.shape[0]
         out = self._new(B, 1, 768)
+        if B == 0:
+            return out
         self._ck(self.lib.rfb_clip_encode(self.h, _ptr(img224), B, _ptr(out), self._stream()))
         return out
 
@@ -359,6 +371,8 @@ class Engine:
         img224 = self._in(img224)
         B = img224.shape[0]
         out = self._new(B, 512)
+        if B == 0:
+            return out
         self._ck(self.lib.rfb_arcface_embed(self.h, _ptr(img224), B, _ptr(out), self._stream()))
         return out
 
@@ -366,6 +380,8 @@ class Engine:
         tar = self._in(tar)
         B, _, H, W = tar.shape
         out = self._new(B, 3, 224, 224)
+        if B == 0:
+            return out
         self._ck(self.lib.rfb_target_clip_input(self.h, _ptr(tar), B, H, W, _ptr(out), self._stream()))
         return out
 
@@ -377,6 +393,8 @@ class Engine:
         lm_proj = None if lm_proj is None else self._in(lm_proj).reshape(-1, 768)
         B = clip_src.shape[0]
         out = self._new(B, 1, 768)
+        if B == 0:
+            return out
         self._ck(self.lib.rfb_condition_fuse(self.h, _ptr(clip_src), _ptr(clip_tgt), _ptr(id_feat), _ptr(lm136),
                                              _ptr(lm_proj), B, float(w_clip), float(w_id), float(w_lm), _ptr(out),
                                              self._stream()))
@@ -386,6 +404,8 @@ class Engine:
         """landmark_proj_out(lm136): [B,136] raw dlib points (zeros = no face) -> [B,768] (ddpm.py:1081-1096)."""
         lm136 = self._in(lm136).reshape(-1, 136)
         out = self._new(lm136.shape[0], 768)
+        if lm136.shape[0] == 0:
+            return out
         self._ck(self.lib.rfb_landmark_project(self.h, _ptr(lm136), lm136.shape[0], _ptr(out), self._stream()))
         return out
 

@@ -20,7 +20,7 @@ for task in "$@"; do
   case $name in
     tests) timeout 1700 python -m pytest tests -m gpu -q -x --timeout 900 --timeout-method=thread ${arg:+-k "$arg"} -s > gpurun_out/${TAG}_pytest.log 2>&1
            echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log; grep -E "rel err|drift|decoded pixel|full path|vae (512|1024)|cond \(|passed|failed|Error|error|rc=" gpurun_out/${TAG}_pytest.log | tail -40 ;;
-    smoke) timeout 600 python __graft_entry__.py smoke 2>&1 | tail -2 ;;
+    smoke) timeout 600 python -u __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${TAG}_smoke.log ;;
     bench) timeout 900 python bench.py --steps ${STEPS:-5} --warmup 3 $arg > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 3000 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err ;;
     bench1024) timeout 1200 python bench.py --workload 1024 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_1024.json 2> gpurun_out/${TAG}_bench_1024.err; tail -c 2500 gpurun_out/${TAG}_bench_1024.json; tail -3 gpurun_out/${TAG}_bench_1024.err ;;
     benchvideo) timeout 1200 python bench.py --workload video --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_video.json 2> gpurun_out/${TAG}_bench_video.err; tail -c 2500 gpurun_out/${TAG}_bench_video.json; tail -3 gpurun_out/${TAG}_bench_video.err ;;

@@ -108,3 +108,20 @@ def test_ddim_update_with_noise_bit_exact(engine, oracle):
     from reface_b200.runtime import ddim_schedule
     s2 = ddim_schedule(50, 0.7)
     assert np.array_equal(s2["sigma"], sch["sigma"])
+
+
+def test_empty_and_single_batches(engine, oracle, unet_sd, vae_sd, clip_sd, arc_sd, fusion_sd):
+    """Edge cases of the batch dimension: an EMPTY batch flows through the whole drop-in path like it does through the
+    reference's torch modules (empty tensors out, no kernel launched on zero rows); a batch of one equals row 0 of a batch
+    of three bit for bit (ragged last chunks of a video, shards of unequal size)."""
+    from reface_b200.ldm_api import LatentDiffusion, swap_faces
+    sd = {**unet_sd, **vae_sd, **clip_sd, **arc_sd, **fusion_sd}
+    model = LatentDiffusion(sd, engine=engine)
+    inp = {k: v.cuda() for k, v in oracle.synthetic_inputs(3, 128, seed=9).items()}
+    empty = {k: v[:0] for k, v in inp.items()}
+    out = swap_faces(model, S=3, scale=3.5, **empty)
+    assert out["image"].shape == (0, 3, 128, 128) and out["samples"].shape == (0, 4, 16, 16) and out["c"].shape == (0, 1, 768)
+    full = swap_faces(model, S=3, scale=3.5, **inp)
+    one = swap_faces(model, S=3, scale=3.5, **{k: v[:1] for k, v in inp.items()})
+    assert torch.equal(one["image"], full["image"][:1]) and torch.equal(one["samples"], full["samples"][:1])
+    assert torch.isfinite(full["image"]).all()
