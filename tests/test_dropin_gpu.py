@@ -119,9 +119,9 @@ def test_empty_and_single_batches(engine, oracle, unet_sd, vae_sd, clip_sd, arc_
     model = LatentDiffusion(sd, engine=engine)
     inp = {k: v.cuda() for k, v in oracle.synthetic_inputs(3, 128, seed=9).items()}
     empty = {k: v[:0] for k, v in inp.items()}
-    out = swap_faces(model, S=3, scale=3.5, **empty)
+    out = swap_faces(model, S=4, scale=3.5, **empty)
     assert out["image"].shape == (0, 3, 128, 128) and out["samples"].shape == (0, 4, 16, 16) and out["c"].shape == (0, 1, 768)
-    full = swap_faces(model, S=3, scale=3.5, **inp)
-    one = swap_faces(model, S=3, scale=3.5, **{k: v[:1] for k, v in inp.items()})
+    full = swap_faces(model, S=4, scale=3.5, **inp)
+    one = swap_faces(model, S=4, scale=3.5, **{k: v[:1] for k, v in inp.items()})
     assert torch.equal(one["image"], full["image"][:1]) and torch.equal(one["samples"], full["samples"][:1])
     assert torch.isfinite(full["image"]).all()
