@@ -1083,6 +1083,67 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int ks, lon
   }
 }
 
+// The same reduction, organised so that it can also leave the GroupNorm partial statistics the GEMM epilogues write
+// (GemmArgs::stats: per 32 rows and channel the sum / sum of squares of the fp16 results): a block of 128 threads owns 32
+// rows x 128 columns; thread (cg, rq) reduces columns 4 cg .. 4 cg + 3 of rows 8 rq .. 8 rq + 7, the four row quarters
+// are folded through shared memory in quarter order.  M % 32 == 0, N % 128 == 0.
+__global__ void __launch_bounds__(128)
+splitk_reduce_stats_kernel(const float* __restrict__ part, int ks, long long M, int N, const float* __restrict__ bias,
+                           const float* __restrict__ rowvec, int rpv, int ldv, const __half* __restrict__ res, long long ldr,
+                           __half* __restrict__ out, long long ldo, float* __restrict__ stats) {
+  __shared__ float sh[4][32][8];
+  const int cg = threadIdx.x & 31, rq = threadIdx.x >> 5;
+  const int n = blockIdx.y * 128 + cg * 4;
+  const long long m0 = (long long)blockIdx.x * 32 + rq * 8;
+  const long long zs = M * N;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) bv = *reinterpret_cast<const float4*>(bias + n);
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int r = 0; r < 8; ++r) {
+    const long long m = m0 + r;
+    const float* p = part + m * N + n;
+    float4 a = *reinterpret_cast<const float4*>(p);
+    for (int z = 1; z < ks; ++z) {
+      const float4 b = *reinterpret_cast<const float4*>(p + z * zs);
+      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    }
+    if (bias) a.x += bv.x, a.y += bv.y, a.z += bv.z, a.w += bv.w;
+    if (rowvec) {
+      const float* rv = rowvec + (m / rpv) * ldv + n;
+      a.x += rv[0], a.y += rv[1], a.z += rv[2], a.w += rv[3];
+    }
+    if (res) {
+      const uint2 u = *reinterpret_cast<const uint2*>(res + m * ldr + n);
+      const float2 f0 = unpack_h2(u.x), f1 = unpack_h2(u.y);
+      a.x += f0.x, a.y += f0.y, a.z += f1.x, a.w += f1.y;
+    }
+    uint2 o;
+    o.x = pack_h2(a.x, a.y), o.y = pack_h2(a.z, a.w);
+    *reinterpret_cast<uint2*>(out + m * ldo + n) = o;
+    if (stats) {  // statistics of the ROUNDED values, like the GEMM epilogue's
+      const float2 g0 = unpack_h2(o.x), g1 = unpack_h2(o.y);
+      s[0] += g0.x, q[0] = fmaf(g0.x, g0.x, q[0]);
+      s[1] += g0.y, q[1] = fmaf(g0.y, g0.y, q[1]);
+      s[2] += g1.x, q[2] = fmaf(g1.x, g1.x, q[2]);
+      s[3] += g1.y, q[3] = fmaf(g1.y, g1.y, q[3]);
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sh[rq][cg][2 * j] = s[j], sh[rq][cg][2 * j + 1] = q[j];
+    __syncthreads();
+    if (rq == 0) {
+      float o8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o8[j] = ((sh[0][cg][j] + sh[1][cg][j]) + sh[2][cg][j]) + sh[3][cg][j];
+      float4* sp = reinterpret_cast<float4*>(stats + ((long long)blockIdx.x * N + n) * 2);
+      sp[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+      sp[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+    }
+  }
+}
+
 // fp32 -> fp16 copy with optional row padding: dst[r, 0..Kp) = src[r, 0..K) (zeros beyond K)
 __global__ void pack_rows_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long rows, int K,
                                      int Kp) {

@@ -387,10 +387,19 @@ static int pick_ksplit(Ctx& c, int rows_per_sample, int N, int nk, const Epi& e,
     return 1;
   return 3;
 }
-static void splitk_finish(Ctx& c, const float* part, int ks, long long M, int N, const Epi& e, __half* out, long long ldo) {
-  splitk_reduce_kernel<<<grid_for(M * (N / 4)), 256, 0, c.stream>>>(part, ks, M, N, e.bias, e.rowvec,
-                                                                     e.rows_per_vec > 0 ? e.rows_per_vec : 1, e.ldv, e.res,
-                                                                     e.ldr, out, ldo);
+static void splitk_finish(Ctx& c, const float* part, int ks, long long M, int N, const Epi& e, __half* out, long long ldo,
+                          float* stats) {
+  if (M % 32 == 0 && N % 128 == 0 && (!e.res || (e.ldr & 3) == 0)) {
+    dim3 grid((unsigned)(M / 32), (unsigned)(N / 128));
+    splitk_reduce_stats_kernel<<<grid, 128, 0, c.stream>>>(part, ks, M, N, e.bias, e.rowvec,
+                                                          e.rows_per_vec > 0 ? e.rows_per_vec : 1, e.ldv, e.res, e.ldr, out, ldo,
+                                                          stats);
+  } else {
+    RFB_CHECK(stats == nullptr, "split-K statistics need M % 32 == 0 and N % 128 == 0");
+    splitk_reduce_kernel<<<grid_for(M * (N / 4)), 256, 0, c.stream>>>(part, ks, M, N, e.bias, e.rowvec,
+                                                                       e.rows_per_vec > 0 ? e.rows_per_vec : 1, e.ldv, e.res,
+                                                                       e.ldr, out, ldo);
+  }
   LAUNCH_CHECK(c);
 }
 
@@ -493,7 +502,8 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
   const bool tma_path = !(w.ksz == 1 && stride == 1) && conv_tma_ok(c, x, w, stride, pad_t, pad_l, pad_b, pad_r, Ho, Wo);
   const bool split = tma_path && pick_ksplit(c, Ho * Wo, w.cout, 9 * (w.cin / 64), e, y.c) > 1;
   e.stats_out = nullptr;
-  if (f16_out && !split && epi_stats_ok(c, e, w.cout, y.c, (long long)Ho * Wo))
+  // (split-K convs get their statistics from the reduction kernel instead of the GEMM epilogue)
+  if (f16_out && epi_stats_ok(c, e, w.cout, y.c, (long long)Ho * Wo) && (!split || (M % 32 == 0 && w.cout % 128 == 0)))
     e.stats_out = y.stats = c.alloc_t<float>((size_t)(M / 32) * y.c * 2);
   if (w.ksz == 1 && stride == 1) {
     gemm(c, x.p, x.c, M, x.c, w.w, w.kp, w.cout, y.p, y.c, e);
@@ -545,7 +555,7 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
     dim3 grid((unsigned)((M + 127) / 128), (unsigned)((w.cout + g.BN - 1) / g.BN), (unsigned)ks);
     launch_gemm(c, tmA, tmB, g, grid, 9.0 * w.cin / ks, w.w, w.kp, round_up(w.cout, 32), nullptr, cs);
     if (ks > 1) {
-      splitk_finish(c, part, ks, M, w.cout, e_full, y.p, y.c);
+      splitk_finish(c, part, ks, M, w.cout, e_full, y.p, y.c, e_full.stats_out);
       c.release(mk_split);
     }
     return y;

@@ -140,7 +140,7 @@ def test_groupnorm(engine, N, C, H, eps, silu, fused):
 def test_groupnorm_from_epilogue_statistics(engine, N, C, O, H, k, stride):
     """conv -> GroupNorm(32) + SiLU (every ResBlock): the convolution's epilogue leaves per-(32 rows, channel) partial
     sums with its output, GroupNorm folds them and makes ONE streaming pass.  Same result as the stand-alone kernels
-    (fp32 statistics of the same fp16 values); the 8x8 case takes the split-K conv, which falls back to them."""
+    (fp32 statistics of the same fp16 values); the 8x8 case takes the split-K conv, whose reduction kernel writes them."""
     x, w, b = h(rn(N, C, H, H, seed=1)), h(rn(O, C, k, k, seed=2) / math.sqrt(k * k * C)), rn(O, seed=3)
     gam, bet = 1 + 0.1 * rn(O, seed=4), 0.1 * rn(O, seed=5)
     p = (k // 2,) * 4
