@@ -228,6 +228,13 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     rec.mode = g.a_mode * 100 + (g.geglu ? 10 : 0) + (g.res ? 1 : 0) + (g.rowvec ? 2 : 0) + (g.out32 ? 4 : 0);
     CUDA_OK(cudaEventRecord(rec.a, c.stream));
   }
+  g.dbg = nullptr;
+  if (c.gemm_debug) {  // per-CTA clock64 role breakdown of this launch (rfb_debug_read)
+    // raw cudaMalloc on purpose: Ctx::owned is rolled back by the single-op test entry points
+    if (!c.dbg_buf) CUDA_OK(cudaMalloc((void**)&c.dbg_buf, (size_t)c.num_sms * 8 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemsetAsync(c.dbg_buf, 0, (size_t)c.num_sms * 8 * sizeof(unsigned long long), c.stream));
+    g.dbg = c.dbg_buf;
+  }
   const bool pair_ok = c.gemm_pair && g.cstride <= 1 && !g.up && !g.nk1 && Bplain != nullptr && grid.z == 1 && grid.x >= 2 &&
                        (g.a_mode == A_PLAIN || g.a_mode == A_CONV3) && g.b_mode == B_PLAIN && g.nk >= c.gemm_pair_min_nk &&
                        (long long)grid.x * grid.y >= c.num_sms / 2;
@@ -294,13 +301,6 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     const uint64_t sb[1] = {(uint64_t)kp * 2};
     const uint32_t bb[2] = {64, (uint32_t)(g.BN / 2)};
     CUtensorMap tmB2 = make_tmap(c, Bplain, 2, db, sb, bb);
-    g.dbg = nullptr;
-    if (c.gemm_debug) {
-      // raw cudaMalloc on purpose: Ctx::owned is rolled back by the single-op test entry points
-      if (!c.dbg_buf) CUDA_OK(cudaMalloc((void**)&c.dbg_buf, (size_t)c.num_sms * 8 * sizeof(unsigned long long)));
-      CUDA_OK(cudaMemsetAsync(c.dbg_buf, 0, (size_t)c.num_sms * 8 * sizeof(unsigned long long), c.stream));
-      g.dbg = c.dbg_buf;
-    }
     const int m_pairs = ((int)grid.x + 1) / 2, n_tiles = (int)grid.y;
     const int total_pairs = m_pairs * n_tiles;
     const int pairs = std::min(total_pairs, c.num_sms / 2);

@@ -93,6 +93,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------ TMA producer (converged warp, elected issue)
     const uint32_t tx = GEMM_A_STAGE_BYTES + b_stage_bytes;
     uint32_t st = 0, sp = 0;
+    long long t_dbg = 0;  // option gemm_debug: cycles this role spent waiting (see GemmArgs::dbg)
     TileIter it;
     it.init(blockIdx.x, gridDim.x, m_tiles, n_tiles);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it.next(m_tiles, n_tiles)) {
@@ -115,7 +116,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int kb = 0; kb < g.nk; ++kb) {
         const uint32_t s = st, ph = sp;
         if (++st == (uint32_t)S) st = 0, sp ^= 1u;
+        const long long tw0 = g.dbg ? clock64() : 0;
         mbar_wait(bars + 8u * (S + s), ph ^ 1u);
+        if (g.dbg) t_dbg += clock64() - tw0;
         const uint32_t full = bars + 8u * s;
         if (elect_one()) {
           mbar_expect_tx(full, tx);
@@ -147,19 +150,26 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
       }
     }
+    if (g.dbg && lane == 0) g.dbg[(size_t)blockIdx.x * 8 + 3] = (unsigned long long)t_dbg;
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (converged warp, elected issue)
     const uint32_t idesc = idesc_f16(GEMM_BM, (uint32_t)BN);
     uint32_t ti = 0, st = 0, sp = 0;
+    long long t_full = 0, t_acc = 0;
+    const long long t_begin = g.dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+      long long tw0 = g.dbg ? clock64() : 0;
       mbar_wait(bar_acce + 8u * as, aph ^ 1u);  // epilogue has drained this accumulator stage
+      if (g.dbg) t_acc += clock64() - tw0;
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * 256u;
       for (int kb = 0; kb < g.nk; ++kb) {
         const uint32_t s = st, ph = sp;
         if (++st == (uint32_t)S) st = 0, sp ^= 1u;
+        tw0 = g.dbg ? clock64() : 0;
         mbar_wait(bars + 8u * s, ph);
+        if (g.dbg) t_full += clock64() - tw0;
         tc_fence_after();
         if (elect_one()) {
           const uint64_t da = smem_desc_k_sw128(sA + s * GEMM_A_STAGE_BYTES);
@@ -173,6 +183,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
       }
     }
+    if (g.dbg && lane == 0) {
+      unsigned long long* d = g.dbg + (size_t)blockIdx.x * 8;
+      d[0] = (unsigned long long)(clock64() - t_begin), d[1] = (unsigned long long)t_full, d[2] = (unsigned long long)t_acc, d[7] = ti;
+    }
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..9)
     const int e = warp - 2;
@@ -181,6 +195,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t stage = epi_stage + (uint32_t)e * EPI_WARP_BYTES;  // this warp's staging tile + bias strip
     uint32_t ti = 0;
     float nb[4] = {0.f, 0.f, 0.f, 0.f};
+    long long t_wait = 0, t_pre = 0;
+    const long long t_ebegin = g.dbg ? clock64() : 0;
     TileIter it;
     it.init(blockIdx.x, gridDim.x, m_tiles, n_tiles);
     if ((int)blockIdx.x < total_tiles) {
@@ -191,13 +207,16 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
       const int n_tile = it.n_tile;
       const EpiTile et = epi_tile_info<MODE>(g, q, it.m_tile, it.n_tile, it.z);
+      const long long tp0 = g.dbg ? clock64() : 0;
       epilogue_prefetch<MODE, NP>(g, et, stage, lane, half, n_tile, nb);  // bias / residual while the MMAs still run
       it.next(m_tiles, n_tiles);
       if (tile + (int)gridDim.x < total_tiles) {  // next tile's bias -> registers, residual lines -> L2
         const EpiTile en = epi_tile_info<MODE>(g, q, it.m_tile, it.n_tile, it.z);
         epilogue_lookahead<MODE, NP>(g, en, lane, half, nb);
       }
+      const long long tw0 = g.dbg ? clock64() : 0;
       mbar_wait(bar_accf + 8u * as, aph);
+      if (g.dbg) t_wait += clock64() - tw0, t_pre += tw0 - tp0;
       tc_fence_after();
       const uint32_t trow = tmem_base + as * 256u + ((uint32_t)(q * 32) << 16);
       epilogue_drain<MODE, NP>(g, et, trow, stage, lane, half, n_tile);
@@ -205,6 +224,10 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acce + 8u * as);
+    }
+    if (g.dbg && warp == 2 && lane == 0) {
+      unsigned long long* d = g.dbg + (size_t)blockIdx.x * 8;
+      d[4] = (unsigned long long)t_wait, d[5] = (unsigned long long)(clock64() - t_ebegin), d[6] = (unsigned long long)t_pre;
     }
   }
   tc_fence_before();

@@ -39,6 +39,7 @@ for task in "$@"; do
          n=${arg%%:*}; wl=512; [[ "$arg" == *:* ]] && wl=${arg#*:}
          timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --workload $wl --steps ${STEPS:-5} --warmup 3 > gpurun_out/${TAG}_bench_${wl}_${n}gpu.json 2> gpurun_out/${TAG}_bench_${wl}_${n}gpu.err
          tail -c 1800 gpurun_out/${TAG}_bench_${wl}_${n}gpu.json; tail -2 gpurun_out/${TAG}_bench_${wl}_${n}gpu.err ;;
+    gemmtrace) timeout 600 python scripts/gemm_trace.py > gpurun_out/${TAG}_gemm_trace.txt 2>&1; cat gpurun_out/${TAG}_gemm_trace.txt | cut -c1-420 ;;
     micro) timeout 900 python scripts/micro_bench.py > gpurun_out/${TAG}_micro.log 2>&1; tail -40 gpurun_out/${TAG}_micro.log ;;
     launches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip ${SKIP:-30000} -c ${COUNT:-9000} --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1
               python scripts/agg_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches.txt; head -34 gpurun_out/${TAG}_launches.txt; rm -f gpurun_out/${TAG}_launches.csv ;;
