@@ -163,11 +163,141 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmArgs& g, const EpiTi
   __syncwarp();
 }
 
+// Lean drain for the common case -- EPI_FAST, vectorised fp16 output, identity row map, the warp's 32 rows all inside M,
+// chunks of exactly 64 or 32 columns, row vector (if any) float4-readable.  The generic drain below spends ~980 warp
+// instructions per tile on ~64 output columns per lane, most of them addressing, predication and register moves
+// (profiles/r01s2_gemm_k320_ncu_full.txt: 19 % arithmetic); the clock64 role breakdown of round 2
+// (profiles/r02_gemm_role_trace_before_lean_epilogue.txt) shows the K <= 640 GEMMs waiting on exactly this: epilogue warps
+// 94 % busy (drain 61-86 %), the MMA warp idle 32-44 % of the time for a free accumulator stage.  Here every address is
+// hoisted out of the loops, there are no per-element guards and the accumulators are loaded straight into float registers.
+template <int NP>
+__device__ __forceinline__ bool epilogue_lean_ok(const GemmArgs& g, const EpiTile& t) {
+  if (!t.vec_ok || g.up || t.m_base + 32 > g.M || t.ncols > t.NO - t.ocol_tile) return false;
+  if (g.rowvec && ((g.ldv & 3) || (t.ocol_tile & 3) || ((t.m_base + 31) / g.rows_per_vec != t.m_base / g.rows_per_vec))) return false;
+  return (t.ncols & 31) == 0;  // chunks of 64 columns, the last one possibly 32
+}
+template <int NP>
+__device__ __forceinline__ void epilogue_drain_lean(const GemmArgs& g, const EpiTile& t, uint32_t trow, uint32_t wbuf, int lane,
+                                                    int half) {
+  const uint32_t bias_s = wbuf + EPI_STAGE_BYTES;
+  const int sw = lane & 7, unit = lane & 7, r0 = lane >> 3;
+  const uint32_t my_row = wbuf + (uint32_t)lane * 128u;
+  // per-lane addresses of the coalesced pass (8 lanes per row, 4 rows per instruction): row r0 + 4 i, 16-byte unit `unit`
+  const uint32_t ld_off = wbuf + (uint32_t)r0 * 128u + (uint32_t)((unit ^ (r0 & 7)) << 4);  // + i * 512: (r0 + 4i) & 7 ...
+  __half* const out_base = g.out + t.zoff + (t.m_base + r0) * g.ldo + t.ocol_tile + unit * 8;
+  const long long out_step = 4 * g.ldo;
+  const __half* const res_base = g.res ? g.res + t.zoff + (t.r_base + r0) * g.ldr + t.ocol_tile + unit * 8 : nullptr;
+  const long long res_step = 4 * g.ldr;
+  const float* const rv = g.rowvec ? g.rowvec + (long long)t.z * g.rowvec_zs + (t.m_base / g.rows_per_vec) * g.ldv + t.ocol_tile
+                                   : nullptr;
+#pragma unroll
+  for (int ci = 0; ci < 2; ++ci) {
+    const int c0 = half * 64 + ci * (NP * 64);
+    if (c0 >= t.ncols) break;
+    const int cvalid = min(64, t.ncols - c0);  // 64 or 32 (warp-uniform)
+    if (ci == 1 && g.res) {  // chunk 0's residual was staged by epilogue_prefetch; stage this chunk's now
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + r0;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (unit * 8 < cvalid) val = __ldg(reinterpret_cast<const uint4*>(res_base + i * res_step + c0));
+        sts128(wbuf + (uint32_t)row * 128u + (uint32_t)((unit ^ (row & 7)) << 4), val);
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h * 32 >= cvalid) break;
+      float v[32];
+      tmem_ld32f(trow + (uint32_t)(c0 + h * 32), v);
+      tmem_ld_wait();
+      if (g.bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = lds128f(bias_s + (uint32_t)(ci * 64 + h * 32 + 4 * j) * 4u);
+          v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+        }
+      }
+      if (rv) {
+        const float4* r4 = reinterpret_cast<const float4*>(rv + c0 + h * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(r4 + j);
+          v[4 * j] += b.x, v[4 * j + 1] += b.y, v[4 * j + 2] += b.z, v[4 * j + 3] += b.w;
+        }
+      }
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) {
+        const uint32_t a = my_row + (uint32_t)(((h * 4 + u4) ^ sw) << 4);
+        if (g.res) {
+          const uint4 u = lds128(a);
+          const float2 f0 = unpack_h2(u.x), f1 = unpack_h2(u.y), f2 = unpack_h2(u.z), f3 = unpack_h2(u.w);
+          v[u4 * 8 + 0] += f0.x, v[u4 * 8 + 1] += f0.y, v[u4 * 8 + 2] += f1.x, v[u4 * 8 + 3] += f1.y;
+          v[u4 * 8 + 4] += f2.x, v[u4 * 8 + 5] += f2.y, v[u4 * 8 + 6] += f3.x, v[u4 * 8 + 7] += f3.y;
+        }
+        uint4 o;
+        o.x = pack_h2(v[u4 * 8 + 0], v[u4 * 8 + 1]);
+        o.y = pack_h2(v[u4 * 8 + 2], v[u4 * 8 + 3]);
+        o.z = pack_h2(v[u4 * 8 + 4], v[u4 * 8 + 5]);
+        o.w = pack_h2(v[u4 * 8 + 6], v[u4 * 8 + 7]);
+        sts128(a, o);
+      }
+    }
+    __syncwarp();
+    // staging tile -> HBM: 8 lanes x 16 B per row, 4 rows per instruction; statistics from the same registers
+    uint4 val[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + r0;
+      val[i] = lds128(wbuf + (uint32_t)row * 128u + (uint32_t)((unit ^ (row & 7)) << 4));
+    }
+    if (unit * 8 < cvalid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(out_base + i * out_step + c0) = val[i];
+    }
+    if (g.stats) {
+      float cs[8], cq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[j] = cq[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t w[4] = {val[i].x, val[i].y, val[i].z, val[i].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_h2(w[e]);
+          cs[2 * e] += f.x, cq[2 * e] = fmaf(f.x, f.x, cq[2 * e]);
+          cs[2 * e + 1] += f.y, cq[2 * e + 1] = fmaf(f.y, f.y, cq[2 * e + 1]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+        cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 8);
+        cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+        cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], 16);
+      }
+      if (lane < 8 && unit * 8 < cvalid) {
+        float4* sp = reinterpret_cast<float4*>(g.stats + ((t.m_base >> 5) * g.N + t.ocol_tile + c0 + unit * 8) * 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sp[j] = make_float4(cs[2 * j], cq[2 * j], cs[2 * j + 1], cq[2 * j + 1]);
+      }
+    }
+  }
+  __syncwarp();  // staging tile / bias strip may be refilled by the next tile's prefetch
+}
+
 // Phase B -- drains this warp's 32 accumulator rows (TMEM lanes q*32..q*32+31).
 //   trow : TMEM address of (lane quadrant, accumulator stage, column 0)
 template <int MODE, int NP>
 __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile& t, uint32_t trow, uint32_t wbuf, int lane,
                                                int half, int n_tile) {
+  if (MODE == EPI_FAST) {
+    if (epilogue_lean_ok<NP>(g, t)) {  // warp-uniform
+      epilogue_drain_lean<NP>(g, t, trow, wbuf, lane, half);
+      return;
+    }
+  }
   const int BN = g.BN;
   const long long m = t.m_base + lane;  // the row this thread owns next to TMEM
   const bool row_ok = m < g.M;
