@@ -329,6 +329,8 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
       CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GENERIC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
       CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_FAST, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
       CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_GEGLU, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_LEAN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+      CUDA_OK(cudaFuncSetAttribute(gemm_persist_kernel<EPI_LEAN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     }
     // short-K GEMMs are epilogue-bound: 3 epilogue warps per lane quadrant (448 threads) instead of 2
     const int np = (g.nk <= c.gemm_epi3_max_nk && g.BN > 64 && g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f) ? 3 : 2;
@@ -345,7 +347,15 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
       if (np == 3) gemm_persist_kernel<EPI_GEGLU, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
       else gemm_persist_kernel<EPI_GEGLU, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
     } else if (g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f) {
-      if (np == 3) gemm_persist_kernel<EPI_FAST, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
+      // every tile full and vectorisable -> the kernel with the lean drain only (gemm_epilogue.cuh)
+      const long long zo = g.zs_outer | g.zs_inner;
+      const bool lean = c.gemm_lean && g.out != nullptr && !g.up && g.M % GEMM_BM == 0 && g.N % g.BN == 0 && g.BN % 16 == 0 &&
+                        (g.N & 7) == 0 && (g.ldo & 7) == 0 && (zo & 7) == 0 && (!g.res || (g.ldr & 7) == 0) &&
+                        (!g.rowvec || ((g.ldv & 3) == 0 && g.rows_per_vec % 32 == 0 && (g.rowvec_zs & 3) == 0));
+      if (lean) {
+        if (np == 3) gemm_persist_kernel<EPI_LEAN, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
+        else gemm_persist_kernel<EPI_LEAN, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
+      } else if (np == 3) gemm_persist_kernel<EPI_FAST, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
       else gemm_persist_kernel<EPI_FAST, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
     } else {
       gemm_persist_kernel<EPI_GENERIC, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);

@@ -96,6 +96,7 @@ struct Ctx {
   int attn_poly = 0;     // attention v3/v4: exponentials per 8 evaluated on the FMA pipe (measured slower: off)
   int cfg_share = 1;     // samplers: compute the context-independent head of the UNet once per CFG pair
   int conv_tma_stride2 = 1;  // stride-2 3x3 convs as implicit GEMM through strided TMA boxes (0: explicit im2col)
+  int gemm_lean = 1;     // lean-drain kernel for launches whose every tile is full and vectorisable
   int gemm_mcast = 1;    // weight-tile TMA multicast across a cluster of M tiles for the split-K convs (gemm_mcast.cuh)
   int gemm_splitk = 1;   // 3-way split-K for the long-K 3x3 convs of <= 8x8 maps (slice count from the per-sample shape only)
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)

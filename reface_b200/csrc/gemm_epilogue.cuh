@@ -19,7 +19,8 @@ namespace rfb {
 static constexpr int EPI_STAGE_BYTES = 4096;               // one staging tile
 static constexpr int EPI_WARP_BYTES = 4096 + 512;          // staging tile + bias strip per epilogue warp
 
-enum EpiMode { EPI_FAST = 0, EPI_GEGLU = 1, EPI_GENERIC = 2 };
+// EPI_LEAN: EPI_FAST's arithmetic for launches whose EVERY tile meets the lean drain's conditions (checked on the host)
+enum EpiMode { EPI_FAST = 0, EPI_GEGLU = 1, EPI_GENERIC = 2, EPI_LEAN = 3 };
 
 // exact-erf GELU with a cheap erf (Abramowitz-Stegun 7.1.26, |err| < 1.5e-7: far below the fp16 output ulp)
 // exact-erf GELU in 8 instructions and one MUFU: with u = |x| and E(u) = 1 - Phi(u) = 0.5 * erfc(u / sqrt 2),
@@ -163,19 +164,13 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmArgs& g, const EpiTi
   __syncwarp();
 }
 
-// Lean drain for the common case -- EPI_FAST, vectorised fp16 output, identity row map, the warp's 32 rows all inside M,
-// chunks of exactly 64 or 32 columns, row vector (if any) float4-readable.  The generic drain below spends ~980 warp
+// Lean drain for the common case -- EPI_FAST, vectorised fp16 output, identity row map, M % 128 == 0, N % BN == 0,
+// BN % 16 == 0, row vector (if any) float4-readable and constant over 32-row groups (engine.cu: epi_lean_ok).  The generic drain below spends ~980 warp
 // instructions per tile on ~64 output columns per lane, most of them addressing, predication and register moves
 // (profiles/r01s2_gemm_k320_ncu_full.txt: 19 % arithmetic); the clock64 role breakdown of round 2
 // (profiles/r02_gemm_role_trace_before_lean_epilogue.txt) shows the K <= 640 GEMMs waiting on exactly this: epilogue warps
 // 94 % busy (drain 61-86 %), the MMA warp idle 32-44 % of the time for a free accumulator stage.  Here every address is
 // hoisted out of the loops, there are no per-element guards and the accumulators are loaded straight into float registers.
-template <int NP>
-__device__ __forceinline__ bool epilogue_lean_ok(const GemmArgs& g, const EpiTile& t) {
-  if (!t.vec_ok || g.up || t.m_base + 32 > g.M || t.ncols > t.NO - t.ocol_tile) return false;
-  if (g.rowvec && ((g.ldv & 3) || (t.ocol_tile & 3) || ((t.m_base + 31) / g.rows_per_vec != t.m_base / g.rows_per_vec))) return false;
-  return (t.ncols & 31) == 0;  // chunks of 64 columns, the last one possibly 32
-}
 template <int NP>
 __device__ __forceinline__ void epilogue_drain_lean(const GemmArgs& g, const EpiTile& t, uint32_t trow, uint32_t wbuf, int lane,
                                                     int half) {
@@ -292,11 +287,9 @@ __device__ __forceinline__ void epilogue_drain_lean(const GemmArgs& g, const Epi
 template <int MODE, int NP>
 __device__ __forceinline__ void epilogue_drain(const GemmArgs& g, const EpiTile& t, uint32_t trow, uint32_t wbuf, int lane,
                                                int half, int n_tile) {
-  if (MODE == EPI_FAST) {
-    if (epilogue_lean_ok<NP>(g, t)) {  // warp-uniform
-      epilogue_drain_lean<NP>(g, t, trow, wbuf, lane, half);
-      return;
-    }
+  if (MODE == EPI_LEAN) {  // compile-time: the lean kernel carries no generic drain (registers)
+    epilogue_drain_lean<NP>(g, t, trow, wbuf, lane, half);
+    return;
   }
   const int BN = g.BN;
   const long long m = t.m_base + lane;  // the row this thread owns next to TMEM
