@@ -168,6 +168,11 @@ attn_flash3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // programmatic dependent launch: the trigger comes AFTER this grid's TMEM allocation (a dependent CTA that becomes
+  // co-resident can then never hold columns a CTA of this grid still waits for); everything above overlapped the
+  // previous kernel's tail, nothing below may run before it has completed
+  pdl_trigger();
+  pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
   const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + Cfg::P_COL;
@@ -401,8 +406,8 @@ static void launch_flash3(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, 
     CUDA_OK(cudaMemsetAsync(c.dbg_buf, 0, (size_t)c.num_sms * 8 * sizeof(unsigned long long), c.stream));
     dbg = c.dbg_buf;
   }
-  if (c.attn_poly) attn_flash3_kernel<DP, 2><<<grid, 320, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg);
-  else attn_flash3_kernel<DP, 0><<<grid, 320, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg);
+  if (c.attn_poly) launch_pdl(c, attn_flash3_kernel<DP, 2>, grid, dim3(320), Cfg::SMEM, tq, tk, tv, out, ldo, L, heads, d, sl, dbg);
+  else launch_pdl(c, attn_flash3_kernel<DP, 0>, grid, dim3(320), Cfg::SMEM, tq, tk, tv, out, ldo, L, heads, d, sl, dbg);
   CUDA_OK(cudaGetLastError());
   c.launches++;
   if (c.profile) {
@@ -488,6 +493,11 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // programmatic dependent launch: the trigger comes AFTER this grid's TMEM allocation (a dependent CTA that becomes
+  // co-resident can then never hold columns a CTA of this grid still waits for); everything above overlapped the
+  // previous kernel's tail, nothing below may run before it has completed
+  pdl_trigger();
+  pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
 
@@ -770,8 +780,8 @@ static void launch_flash4(Ctx& c, const CUtensorMap& tq, const CUtensorMap& tk, 
     dbg = c.dbg_buf;
   }
 #define RFB_FLASH4(POLY_, PP_)                                                                                    \
-  attn_flash4_kernel<DP, POLY_, NS, PP_><<<grid, 576, Cfg::SMEM, c.stream>>>(tq, tk, tv, out, ldo, L, heads, d, sl, dbg, \
-                                                                             c.attn_stagger)
+  launch_pdl(c, attn_flash4_kernel<DP, POLY_, NS, PP_>, grid, dim3(576), Cfg::SMEM, tq, tk, tv, out, ldo, L, heads, d, sl, dbg, \
+             c.attn_stagger)
   if (c.attn_poly) {
     if (c.attn_pingpong) RFB_FLASH4(2, 1);
     else RFB_FLASH4(2, 0);

@@ -206,6 +206,7 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "gemm_splitk") c.gemm_splitk = (int)value;
   else if (k == "gemm_mcast") c.gemm_mcast = (int)value;
   else if (k == "gemm_lean") c.gemm_lean = (int)value;
+  else if (k == "pdl") c.pdl = (int)value;
   else if (k == "conv_tma_stride2") c.conv_tma_stride2 = (int)value;
   else if (k == "ln_vec") c.ln_vec = (int)value;
   else if (k == "gemm_pair") c.gemm_pair = (int)value;

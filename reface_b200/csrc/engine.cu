@@ -256,9 +256,11 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     cfg.blockDim = dim3(GEMMP_THREADS);
     cfg.dynamicSmemBytes = psmem;
     cfg.stream = c.stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)mcast_cs, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see launch_pdl (engine.h)
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at, cfg.numAttrs = 1;
 #define RFB_MCAST(MODE_, CS_)                                                                                          \
   do {                                                                                                                 \
@@ -273,6 +275,7 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     }                                                                                                                  \
     const int clusters = std::min(units, c.once_flags[key + "_max"]);                                                  \
     cfg.gridDim = dim3((unsigned)(clusters * CS_));                                                                    \
+    cfg.numAttrs = c.pdl ? 2 : 1;                                                                                      \
     CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, g, m_groups, n_tiles, units));                                     \
   } while (0)
     if (fast) {
@@ -344,8 +347,8 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     const int ctas = std::min(total, c.num_sms);
     const int thr = 64 + np * 128;
     if (g.geglu) {
-      if (np == 3) gemm_persist_kernel<EPI_GEGLU, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
-      else gemm_persist_kernel<EPI_GEGLU, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
+      if (np == 3) launch_pdl(c, gemm_persist_kernel<EPI_GEGLU, 3>, dim3(ctas), dim3(thr), psmem, tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
+      else launch_pdl(c, gemm_persist_kernel<EPI_GEGLU, 2>, dim3(ctas), dim3(thr), psmem, tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
     } else if (g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f) {
       // every tile full and vectorisable -> the kernel with the lean drain only (gemm_epilogue.cuh)
       const long long zo = g.zs_outer | g.zs_inner;
@@ -353,12 +356,12 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
                         (g.N & 7) == 0 && (g.ldo & 7) == 0 && (zo & 7) == 0 && (!g.res || (g.ldr & 7) == 0) &&
                         (!g.rowvec || ((g.ldv & 3) == 0 && g.rows_per_vec % 32 == 0 && (g.rowvec_zs & 3) == 0));
       if (lean) {
-        if (np == 3) gemm_persist_kernel<EPI_LEAN, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
-        else gemm_persist_kernel<EPI_LEAN, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
-      } else if (np == 3) gemm_persist_kernel<EPI_FAST, 3><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
-      else gemm_persist_kernel<EPI_FAST, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
+        if (np == 3) launch_pdl(c, gemm_persist_kernel<EPI_LEAN, 3>, dim3(ctas), dim3(thr), psmem, tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
+        else launch_pdl(c, gemm_persist_kernel<EPI_LEAN, 2>, dim3(ctas), dim3(thr), psmem, tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
+      } else if (np == 3) launch_pdl(c, gemm_persist_kernel<EPI_FAST, 3>, dim3(ctas), dim3(thr), psmem, tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
+      else launch_pdl(c, gemm_persist_kernel<EPI_FAST, 2>, dim3(ctas), dim3(thr), psmem, tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
     } else {
-      gemm_persist_kernel<EPI_GENERIC, 2><<<ctas, thr, psmem, c.stream>>>(tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
+      launch_pdl(c, gemm_persist_kernel<EPI_GENERIC, 2>, dim3(ctas), dim3(thr), psmem, tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
     }
   }
   LAUNCH_CHECK(c);
@@ -401,12 +404,12 @@ static void splitk_finish(Ctx& c, const float* part, int ks, long long M, int N,
                           float* stats) {
   if (M % 32 == 0 && N % 128 == 0 && (!e.res || (e.ldr & 3) == 0)) {
     dim3 grid((unsigned)(M / 32), (unsigned)(N / 128));
-    splitk_reduce_stats_kernel<<<grid, 128, 0, c.stream>>>(part, ks, M, N, e.bias, e.rowvec,
+    launch_pdl(c, splitk_reduce_stats_kernel, grid, dim3(128), 0, part, ks, M, N, e.bias, e.rowvec,
                                                           e.rows_per_vec > 0 ? e.rows_per_vec : 1, e.ldv, e.res, e.ldr, out, ldo,
                                                           stats);
   } else {
     RFB_CHECK(stats == nullptr, "split-K statistics need M % 32 == 0 and N % 128 == 0");
-    splitk_reduce_kernel<<<grid_for(M * (N / 4)), 256, 0, c.stream>>>(part, ks, M, N, e.bias, e.rowvec,
+    launch_pdl(c, splitk_reduce_kernel, dim3(grid_for(M * (N / 4))), dim3(256), 0, part, ks, M, N, e.bias, e.rowvec,
                                                                        e.rows_per_vec > 0 ? e.rows_per_vec : 1, e.ldv, e.res,
                                                                        e.ldr, out, ldo);
   }
@@ -746,7 +749,7 @@ float2* gn_affine_from_stats(Ctx& c, const Tens& x1, const Tens& x2, const float
   RFB_CHECK(x1.stats && (!x2.p || x2.stats) && HW % 32 == 0 && C % 32 == 0 && C / 32 <= 256, "GroupNorm: no producer statistics");
   float2* ab = c.alloc_t<float2>((size_t)N * C);
   GnStatSrc ss{x1.stats, x2.p ? x2.stats : nullptr, x1.c, (x2.p && x2.n != x1.n) ? x2.n : 0};
-  gn_finalize3_kernel<<<dim3(32, (unsigned)N), 256, 0, c.stream>>>(ss, gamma, beta, ab, HW / 32, HW, C, 32, eps);
+  launch_pdl(c, gn_finalize3_kernel, dim3(32, (unsigned)N), dim3(256), 0, ss, gamma, beta, ab, HW / 32, HW, C, 32, eps);
   LAUNCH_CHECK(c);
   return ab;
 }
@@ -773,7 +776,7 @@ Tens groupnorm2(Ctx& c, const Tens& x1, const Tens& x2, const float* gamma, cons
     const int want = std::max(1, (c.gn_apply_bps * c.num_sms) / std::max(1, N));
     const int slab = std::max(R, (HW + want - 1) / want);
     dim3 g3((unsigned)((HW + slab - 1) / slab), (unsigned)N);
-    gn_apply3_kernel<<<g3, cv * R, 0, c.stream>>>(src, ab, y.p, HW, C, silu ? 1 : 0, slab);
+    launch_pdl(c, gn_apply3_kernel, g3, dim3(cv * R), 0, src, ab, y.p, HW, C, silu ? 1 : 0, slab);
     LAUNCH_CHECK(c);
     c.release(mk);
     return y;
@@ -851,7 +854,7 @@ Tens conv1x1_gn_folded(Ctx& c, const Tens& x, const float* gn_gamma, const float
   const int kp = Cin, cout_p = round_up(Cout, 32);
   __half* Wn = c.alloc_t<__half>((size_t)N * cout_p * kp);
   float* biasn = c.alloc_t<float>((size_t)N * Cout);
-  gn_fold_weights_kernel<<<dim3((unsigned)((cout_p + 7) / 8), (unsigned)N), 256, 0, c.stream>>>(w32, bias, ab, Wn, biasn, Cin,
+  launch_pdl(c, gn_fold_weights_kernel, dim3((unsigned)((cout_p + 7) / 8), (unsigned)N), dim3(256), 0, w32, bias, ab, Wn, biasn, Cin,
                                                                                              Cout, kp, cout_p);
   LAUNCH_CHECK(c);
   GemmArgs g;
@@ -883,7 +886,7 @@ template <int LPR, int VPL>
 static void launch_ln_vec(Ctx& c, const __half* x, const float* gamma, const float* beta, __half* y, long long rows,
                           long long ldx, long long ldy, float eps) {
   const long long rows_per_block = 8 * (32 / LPR);
-  layernorm_vec_kernel<LPR, VPL><<<(unsigned)((rows + rows_per_block - 1) / rows_per_block), 256, 0, c.stream>>>(
+  launch_pdl(c, layernorm_vec_kernel<LPR, VPL>, dim3((unsigned)((rows + rows_per_block - 1) / rows_per_block)), dim3(256), 0, 
       x, gamma, beta, y, rows, ldx, ldy, eps);
   LAUNCH_CHECK(c);
 }
@@ -922,7 +925,7 @@ void cross_attn_small(Ctx& c, const __half* q, const float* kc, const float* vc,
     CUDA_OK(cudaFuncSetAttribute(cross_attn_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   RFB_CHECK(smem <= 200 * 1024, "cross-attention: context does not fit shared memory");
   dim3 grid((unsigned)((L * heads + 255) / 256), (unsigned)N);
-  cross_attn_small_kernel<16><<<grid, 256, smem, c.stream>>>(q, kc, vc, out, L, T, C, heads,
+  launch_pdl(c, cross_attn_small_kernel<16>, grid, dim3(256), smem, q, kc, vc, out, L, T, C, heads,
                                                              1.0f / sqrtf((float)(C / heads)));
   LAUNCH_CHECK(c);
 }
@@ -959,11 +962,11 @@ void linear_small(Ctx& c, const float* x, long long ldx, int R, const Lin32& w, 
     float* os = out + (long long)r0 * ldo;
     const float* rs = res ? res + (long long)r0 * ldo : nullptr;
     if (r <= 2)
-      linear_small_kernel<2><<<grid, 256, 0, c.stream>>>(xs, w.w, w.b, os, r, w.in, w.out, ldx, ldo, act_in, act_out, rs);
+      launch_pdl(c, linear_small_kernel<2>, grid, dim3(256), 0, xs, w.w, w.b, os, r, w.in, w.out, ldx, ldo, act_in, act_out, rs);
     else if (r <= 4)
-      linear_small_kernel<4><<<grid, 256, 0, c.stream>>>(xs, w.w, w.b, os, r, w.in, w.out, ldx, ldo, act_in, act_out, rs);
+      launch_pdl(c, linear_small_kernel<4>, grid, dim3(256), 0, xs, w.w, w.b, os, r, w.in, w.out, ldx, ldo, act_in, act_out, rs);
     else
-      linear_small_kernel<16><<<grid, 256, 0, c.stream>>>(xs, w.w, w.b, os, r, w.in, w.out, ldx, ldo, act_in, act_out, rs);
+      launch_pdl(c, linear_small_kernel<16>, grid, dim3(256), 0, xs, w.w, w.b, os, r, w.in, w.out, ldx, ldo, act_in, act_out, rs);
     LAUNCH_CHECK(c);
   }
 }
@@ -972,7 +975,7 @@ void timestep_embedding(Ctx& c, const long long* t, float* out, int N, int dim) 
   LAUNCH_CHECK(c);
 }
 void concat9(Ctx& c, const float* x, const float* z, const float* mask, float* out, int B, int HW, int dup) {
-  concat9_kernel<<<grid_for((long long)dup * B * 9 * HW), 256, 0, c.stream>>>(x, z, mask, out, B, HW, dup);
+  launch_pdl(c, concat9_kernel, dim3(grid_for((long long)dup * B * 9 * HW)), dim3(256), 0, x, z, mask, out, B, HW, dup);
   LAUNCH_CHECK(c);
 }
 void cfg_ddim_update(Ctx& c, const float* x, const float* eps2, const float* noise, float* x_prev, float* pred_x0,
@@ -990,7 +993,7 @@ void eps_from_taps(Ctx& c, const float* taps, const float* bias, float* eps, int
 void taps_cfg_ddim_update(Ctx& c, const float* x, const float* taps, const float* bias, const float* noise, float* x_prev,
                           float* pred_x0, int B, int L, float scale, float a_t, float a_prev, float sigma,
                           float sqrt_one_minus_at, int has_uncond) {
-  taps_cfg_ddim_update_kernel<<<grid_for((long long)B * L * L, 128), 128, 0, c.stream>>>(
+  launch_pdl(c, taps_cfg_ddim_update_kernel, dim3(grid_for((long long)B * L * L, 128)), dim3(128), 0, 
       x, taps, bias, noise, x_prev, pred_x0, B, L, scale, a_t, a_prev, sigma, sqrt_one_minus_at, has_uncond);
   LAUNCH_CHECK(c);
 }

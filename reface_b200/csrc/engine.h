@@ -5,9 +5,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 namespace rfb {
@@ -96,6 +98,7 @@ struct Ctx {
   int attn_poly = 0;     // attention v3/v4: exponentials per 8 evaluated on the FMA pipe (measured slower: off)
   int cfg_share = 1;     // samplers: compute the context-independent head of the UNet once per CFG pair
   int conv_tma_stride2 = 1;  // stride-2 3x3 convs as implicit GEMM through strided TMA boxes (0: explicit im2col)
+  int pdl = 1;           // programmatic dependent launch between the kernels of the loop (launch_pdl below)
   int gemm_lean = 1;     // lean-drain kernel for launches whose every tile is full and vectorisable
   int gemm_mcast = 1;    // weight-tile TMA multicast across a cluster of M tiles for the split-K convs (gemm_mcast.cuh)
   int gemm_splitk = 1;   // 3-way split-K for the long-K 3x3 convs of <= 8x8 maps (slice count from the per-sample shape only)
@@ -170,6 +173,22 @@ struct Ctx {
       throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " in " #expr " at " \
                                __FILE__ ":" + std::to_string(__LINE__));                                  \
   } while (0)
+
+// Launch on the context's stream with the programmatic-stream-serialization attribute (option "pdl"): the kernel may be
+// scheduled while its predecessor drains and must call pdl_wait() (ptx.cuh) before it touches anything the predecessor
+// wrote or still reads.  ONLY for kernels that do so; every other launch keeps full stream serialization.  Stream
+// capture turns the attribute into programmatic edges of the graph.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(Ctx& c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = c.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = c.pdl ? 1 : 0;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+}
 
 // ---- weight packing (device side, at build time)
 // [O,I,KH,KW] -> implicit-GEMM layout; oscale (device, [O]) optionally folds a per-output-channel scale (BatchNorm)

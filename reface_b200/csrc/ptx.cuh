@@ -200,6 +200,14 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
 // ============================================================================ 2-CTA (cta_group::2) support
 namespace rfb {
 
+// Programmatic dependent launch (launch_pdl in engine.h).  pdl_trigger lets the NEXT kernel of the stream be scheduled as
+// soon as every CTA of this grid has issued it (its CTAs then occupy SMs as this grid's CTAs retire and run their
+// prologue); pdl_wait returns once the PREVIOUS kernel of the stream has completed and its writes are visible.  Rule:
+// nothing before pdl_wait may read memory another kernel writes, or write global memory at all.  Both are no-ops in a
+// launch without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -127,6 +127,37 @@ def test_sampling_loop_cuda_graph_replays_are_bit_exact(unet_engine):
         eng.set_option("cfg_share", 1)
 
 
+def test_programmatic_dependent_launch_is_bit_exact(unet_engine):
+    """Option "pdl" (default on): the kernels of the loop are launched with the programmatic-stream-serialization
+    attribute, so a kernel's CTAs are scheduled (and run their prologue: barrier init, TMEM allocation, descriptor
+    prefetch) while the previous kernel drains, and wait in `griddepcontrol.wait` before touching memory.  A missing wait
+    would be a race between consecutive kernels: the eager loop, the captured graph and repeated replays must all give
+    the bits of the fully serialised launches (pdl=0), at a shape that fills the GPU (L=64, N=2*4) and at a tiny one."""
+    eng = unet_engine
+    g = _g("ddim_S5_L16")
+    small = (g["x_T"], g["z"], g["mask"], g["c"], g["uc"])
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    B, L = 4, 64
+    big = tuple(t.cuda() for t in (torch.randn(B, 4, L, L, generator=gen), torch.randn(B, 4, L, L, generator=gen),
+                                   (torch.rand(B, 1, L, L, generator=gen) > 0.5).float(),
+                                   torch.randn(B, 1, 768, generator=gen), torch.randn(B, 1, 768, generator=gen)))
+    for args, S in ((small, 5), (big, 4)):
+        eng.set_option("pdl", 0)
+        eng.set_option("use_graph", 0)
+        try:
+            ref = eng.ddim_sample(*args, S=S, scale=3.5, log_every_t=2)[0].clone()
+            eng.set_option("pdl", 1)
+            assert torch.equal(eng.ddim_sample(*args, S=S, scale=3.5, log_every_t=2)[0], ref)
+            eng.set_option("use_graph", 1)
+            r0 = eng.graph_replays
+            for i in range(4):
+                assert torch.equal(eng.ddim_sample(*args, S=S, scale=3.5, log_every_t=2)[0], ref), i
+            assert eng.graph_replays - r0 == 3
+        finally:
+            eng.set_option("pdl", 1)
+            eng.set_option("use_graph", 1)
+
+
 def test_fused_output_conv_cfg_ddim_update_equals_separate_kernels(unet_engine, oracle):
     """Inside the sampler the UNet's output convolution (a [N*L*L,320]x[320,36] tap GEMM) is finished by the update
     kernel itself: 9-tap gather + bias -> CFG combine -> x_{t-1} / pred_x0 (ddim.py:346,363-374), eps never stored.
