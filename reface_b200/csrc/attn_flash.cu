@@ -168,10 +168,8 @@ attn_flash3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // programmatic dependent launch: the trigger comes AFTER this grid's TMEM allocation (a dependent CTA that becomes
-  // co-resident can then never hold columns a CTA of this grid still waits for); everything above overlapped the
-  // previous kernel's tail, nothing below may run before it has completed
-  pdl_trigger();
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail, nothing below may run before
+  // that kernel has completed
   pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
@@ -493,10 +491,8 @@ attn_flash4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // programmatic dependent launch: the trigger comes AFTER this grid's TMEM allocation (a dependent CTA that becomes
-  // co-resident can then never hold columns a CTA of this grid still waits for); everything above overlapped the
-  // previous kernel's tail, nothing below may run before it has completed
-  pdl_trigger();
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail, nothing below may run before
+  // that kernel has completed
   pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));

@@ -308,7 +308,6 @@ struct GnStatSrc {
 __global__ void __launch_bounds__(256)
 gn_finalize3_kernel(const GnStatSrc st, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float2* __restrict__ ab, int P, int HW, int C, int G, float eps) {
-  pdl_trigger();
   pdl_wait();
   // grid (G, N): one block folds ONE group (cpg <= 256 contiguous channels) of one sample.  Thread t owns channel
   // (t mod cpg) and partial rows t / cpg, t / cpg + R, ... (four independent loads in flight): consecutive threads read
@@ -374,7 +373,6 @@ gn_finalize3_kernel(const GnStatSrc st, const float* __restrict__ gamma, const f
 __global__ void __launch_bounds__(512, 2)  // <= 64 registers: the 90-register first version ran one block per SM and was
                                            // latency-bound at 21 % warp occupancy (profiles/r02_gn3_ncu_full.txt)
 gn_apply3_kernel(const GnSrc src, const float2* __restrict__ ab, __half* __restrict__ y, int HW, int C, int silu, int slab) {
-  pdl_trigger();
   pdl_wait();
   const int n = blockIdx.y;
   const int cv = C >> 3;
@@ -429,7 +427,6 @@ gn_apply3_kernel(const GnSrc src, const float2* __restrict__ ab, __half* __restr
 __global__ void gn_fold_weights_kernel(const float* __restrict__ w32, const float* __restrict__ bias,
                                        const float2* __restrict__ ab, __half* __restrict__ Wn, float* __restrict__ biasn,
                                        int Cin, int Cout, int kp, int cout_p) {
-  pdl_trigger();
   pdl_wait();
   const int n = blockIdx.y;
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -637,7 +634,6 @@ template <int LPR, int VPL>
 __global__ void __launch_bounds__(256)
 layernorm_vec_kernel(const __half* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __half* __restrict__ y, long long rows, long long ldx, long long ldy, float eps) {
-  pdl_trigger();
   pdl_wait();
   constexpr int RPW = 32 / LPR;
   constexpr int C = 8 * LPR * VPL;
@@ -779,7 +775,6 @@ template <int TMAX>
 __global__ void cross_attn_small_kernel(const __half* __restrict__ q, const float* __restrict__ kc,
                                         const float* __restrict__ vc, __half* __restrict__ out, int L, int T, int C,
                                         int heads, float scale) {
-  pdl_trigger();
   pdl_wait();
   extern __shared__ float kv[];  // [2][T][C]
   const int n = blockIdx.y;
@@ -850,7 +845,6 @@ __global__ void linear_small_kernel(const float* __restrict__ x, const float* __
                                     const float* __restrict__ bias, float* __restrict__ out, int R, int K, int O,
                                     long long ldx, long long ldo, int act_in, int act_out,
                                     const float* __restrict__ res) {
-  pdl_trigger();
   pdl_wait();
   constexpr int KC = 512;
   __shared__ __align__(16) float xs[RMAX][KC];
@@ -917,7 +911,6 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, float
 // x9[n] = cat(x[n%B], z[n%B], mask[n%B]) for n < dup*B   [ref: ldm/models/diffusion/ddim.py:330,338]
 __global__ void concat9_kernel(const float* __restrict__ x, const float* __restrict__ z, const float* __restrict__ mask,
                                float* __restrict__ out, int B, int HW, int dup) {
-  pdl_trigger();
   pdl_wait();
   const long long total = (long long)dup * B * 9 * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -992,7 +985,6 @@ __global__ void taps_cfg_ddim_update_kernel(const float* __restrict__ x, const f
                                             const float* __restrict__ bias, const float* __restrict__ noise,
                                             float* __restrict__ x_prev, float* __restrict__ pred_x0, int B, int L, float scale,
                                             float a_t, float a_prev, float sigma, float sqrt_one_minus_at, int has_uncond) {
-  pdl_trigger();
   pdl_wait();
   const float sqrt_at = __fsqrt_rn(a_t);
   const float sqrt_aprev = __fsqrt_rn(a_prev);
@@ -1070,7 +1062,6 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __res
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int ks, long long M, int N,
                                      const float* __restrict__ bias, const float* __restrict__ rowvec, int rpv, int ldv,
                                      const __half* __restrict__ res, long long ldr, __half* __restrict__ out, long long ldo) {
-  pdl_trigger();
   pdl_wait();
   const int nv = N >> 2;
   const long long total = M * nv;
@@ -1109,7 +1100,6 @@ __global__ void __launch_bounds__(128)
 splitk_reduce_stats_kernel(const float* __restrict__ part, int ks, long long M, int N, const float* __restrict__ bias,
                            const float* __restrict__ rowvec, int rpv, int ldv, const __half* __restrict__ res, long long ldr,
                            __half* __restrict__ out, long long ldo, float* __restrict__ stats) {
-  pdl_trigger();
   pdl_wait();
   __shared__ float sh[4][32][8];
   const int cg = threadIdx.x & 31, rq = threadIdx.x >> 5;

@@ -275,7 +275,7 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     }                                                                                                                  \
     const int clusters = std::min(units, c.once_flags[key + "_max"]);                                                  \
     cfg.gridDim = dim3((unsigned)(clusters * CS_));                                                                    \
-    cfg.numAttrs = c.pdl ? 2 : 1;                                                                                      \
+    cfg.numAttrs = c.pdl_now() ? 2 : 1;                                                                                 \
     CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, g, m_groups, n_tiles, units));                                     \
   } while (0)
     if (fast) {

@@ -98,7 +98,11 @@ struct Ctx {
   int attn_poly = 0;     // attention v3/v4: exponentials per 8 evaluated on the FMA pipe (measured slower: off)
   int cfg_share = 1;     // samplers: compute the context-independent head of the UNet once per CFG pair
   int conv_tma_stride2 = 1;  // stride-2 3x3 convs as implicit GEMM through strided TMA boxes (0: explicit im2col)
-  int pdl = 1;           // programmatic dependent launch between the kernels of the loop (launch_pdl below)
+  // programmatic dependent launch between consecutive kernels (launch_pdl below).  1: eager launches only -- measured
+  // on one box, interleaved: eager UNet forward 18.17 -> 17.41 ms, but the graph-replayed bench 9.32 -> 9.15 faces/s
+  // (the graph's own kernel-to-kernel edges are cheaper than the release of griddepcontrol.wait); 2: captured graphs too
+  int pdl = 1;
+  bool pdl_now() const { return pdl == 2 || (pdl == 1 && (gstream == nullptr || stream != gstream)); }
   int gemm_lean = 1;     // lean-drain kernel for launches whose every tile is full and vectorisable
   int gemm_mcast = 1;    // weight-tile TMA multicast across a cluster of M tiles for the split-K convs (gemm_mcast.cuh)
   int gemm_splitk = 1;   // 3-way split-K for the long-K 3x3 convs of <= 8x8 maps (slice count from the per-sample shape only)
@@ -186,7 +190,7 @@ inline void launch_pdl(Ctx& c, void (*kern)(KArgs...), dim3 grid, dim3 block, si
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at, cfg.numAttrs = c.pdl ? 1 : 0;
+  cfg.attrs = at, cfg.numAttrs = c.pdl_now() ? 1 : 0;
   CUDA_OK(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
 }
 

@@ -86,10 +86,8 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // programmatic dependent launch: the trigger comes AFTER this grid's TMEM allocation (a dependent CTA that becomes
-  // co-resident can then never hold columns a CTA of this grid still waits for); everything above overlapped the
-  // previous kernel's tail, nothing below may run before it has completed
-  pdl_trigger();
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail, nothing below may run before
+  // that kernel has completed
   pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
@@ -188,6 +186,7 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
       }
     }
+    pdl_trigger();  // this CTA's MMAs are all issued: the next kernel may be scheduled behind the grid's last epilogues
     if (g.dbg && lane == 0) {
       unsigned long long* d = g.dbg + (size_t)blockIdx.x * 8;
       d[0] = (unsigned long long)(clock64() - t_begin), d[1] = (unsigned long long)t_full, d[2] = (unsigned long long)t_acc, d[7] = ti;

@@ -200,11 +200,14 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
 // ============================================================================ 2-CTA (cta_group::2) support
 namespace rfb {
 
-// Programmatic dependent launch (launch_pdl in engine.h).  pdl_trigger lets the NEXT kernel of the stream be scheduled as
-// soon as every CTA of this grid has issued it (its CTAs then occupy SMs as this grid's CTAs retire and run their
-// prologue); pdl_wait returns once the PREVIOUS kernel of the stream has completed and its writes are visible.  Rule:
-// nothing before pdl_wait may read memory another kernel writes, or write global memory at all.  Both are no-ops in a
-// launch without the attribute.
+// Programmatic dependent launch (launch_pdl in engine.h).  pdl_wait returns once the PREVIOUS kernel of the stream has
+// completed and its writes are visible: nothing before it may read memory another kernel writes, or write global memory
+// at all.  pdl_trigger lets the NEXT kernel be scheduled once every CTA of this grid has issued it or exited (its CTAs
+// then take SMs as this grid's CTAs retire and run their prologue up to their own pdl_wait).  The GEMM kernels issue it
+// when their last MMA is out; an EARLY trigger (first instruction of every kernel) measured 1.8 % slower over the
+// graph-replayed loop -- small dependent blocks then sit next to the running GEMM CTAs for its whole duration
+// (profiles/r02_pdl_ab.txt) -- and a kernel that allocates TMEM must not trigger before its allocation (a co-resident
+// dependent could hold the columns a CTA of this grid still waits for).  No-ops in a launch without the attribute.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

@@ -22,6 +22,12 @@ for task in "$@"; do
            echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log; grep -E "rel err|drift|decoded pixel|full path|vae (512|1024)|cond \(|passed|failed|Error|error|rc=" gpurun_out/${TAG}_pytest.log | tail -40 ;;
     smoke) timeout 600 python -u __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${TAG}_smoke.log ;;
     bench) timeout 900 python bench.py --steps ${STEPS:-5} --warmup 3 $arg > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 3000 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err ;;
+    benchab) # benchab:<OPTION>:<v1>,<v2>[,..]  bench.py with engine option OPTION at each value, interleaved twice (same box)
+         opt=${arg%%:*}; IFS=',' read -ra VALS <<< "${arg#*:}"; envname=RFB_$(echo $opt | tr a-z A-Z)
+         for r in 1 2; do for v in "${VALS[@]}"; do
+           env $envname=$v timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_${opt}${v}_$r.json 2> gpurun_out/${TAG}_bench_${opt}${v}_$r.err
+           python -c "import json,sys; d=json.load(open(sys.argv[1])); print(sys.argv[2], round(d['value'],3), d['unit'], round(d['ms_per_step'],1), 'ms/step', d['clocks'])" gpurun_out/${TAG}_bench_${opt}${v}_$r.json "$opt=$v" | tee -a gpurun_out/${TAG}_benchab_$opt.txt
+         done; done ;;
     bench1024) timeout 1200 python bench.py --workload 1024 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_1024.json 2> gpurun_out/${TAG}_bench_1024.err; tail -c 2500 gpurun_out/${TAG}_bench_1024.json; tail -3 gpurun_out/${TAG}_bench_1024.err ;;
     benchvideo) timeout 1200 python bench.py --workload video --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_video.json 2> gpurun_out/${TAG}_bench_video.err; tail -c 2500 gpurun_out/${TAG}_bench_video.json; tail -3 gpurun_out/${TAG}_bench_video.err ;;
     ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; tail -c 1500 gpurun_out/${TAG}_bench_ref.json ;;

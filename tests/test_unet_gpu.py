@@ -128,7 +128,7 @@ def test_sampling_loop_cuda_graph_replays_are_bit_exact(unet_engine):
 
 
 def test_programmatic_dependent_launch_is_bit_exact(unet_engine):
-    """Option "pdl" (default on): the kernels of the loop are launched with the programmatic-stream-serialization
+    """Option "pdl" (1, the default: eager launches; 2: inside captured graphs as well): the kernels of the loop are launched with the programmatic-stream-serialization
     attribute, so a kernel's CTAs are scheduled (and run their prologue: barrier init, TMEM allocation, descriptor
     prefetch) while the previous kernel drains, and wait in `griddepcontrol.wait` before touching memory.  A missing wait
     would be a race between consecutive kernels: the eager loop, the captured graph and repeated replays must all give
@@ -148,6 +148,7 @@ def test_programmatic_dependent_launch_is_bit_exact(unet_engine):
             ref = eng.ddim_sample(*args, S=S, scale=3.5, log_every_t=2)[0].clone()
             eng.set_option("pdl", 1)
             assert torch.equal(eng.ddim_sample(*args, S=S, scale=3.5, log_every_t=2)[0], ref)
+            eng.set_option("pdl", 2)
             eng.set_option("use_graph", 1)
             r0 = eng.graph_replays
             for i in range(4):
