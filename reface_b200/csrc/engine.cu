@@ -559,6 +559,9 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
     if (c.gemm_mcast && ks > 1 && stride == 1 && M % 128 == 0) {
       const long long mt = M / 128;
       cs = mt % 8 == 0 ? 8 : (mt % 4 == 0 ? 4 : (mt % 2 == 0 ? 2 : 0));
+    } else if (c.gemm_mcast_big > 1 && ks == 1 && stride == 1 && M % (128 * c.gemm_mcast_big) == 0 &&
+               g.BN % c.gemm_mcast_big == 0 && (g.BN / c.gemm_mcast_big) % 8 == 0) {
+      cs = c.gemm_mcast_big;  // experiment: the long-K convs of the large maps (MMA warp waits ~32 % for operands)
     }
     const uint64_t db[2] = {(uint64_t)w.kp, (uint64_t)round_up(w.cout, 32)};
     const uint64_t sb[1] = {(uint64_t)w.kp * 2};

@@ -16,6 +16,8 @@ def read():
     eng._ck(eng.lib.rfb_debug_read(eng.h, buf, 148 * 8))
     v = list(buf)
     rows = [v[i * 8:(i + 1) * 8] for i in range(148) if v[i * 8]]
+    if int(os.environ.get("RFB_GEMM_PAIR", 0)):   # gemm_pair_kernel: the MMA counters live in the leader (even) CTA of a pair
+        rows = [v[i * 8:(i + 1) * 8] for i in range(0, 148, 2) if v[i * 8 + 7]]
     avg = lambda j: sum(r[j] for r in rows) / max(1, len(rows))
     return dict(mma_total=avg(0), wait_full=avg(1), wait_acc=avg(2), prod_wait_empty=avg(3), epi_wait_acc=avg(4), epi_total=avg(5),
                 epi_prefetch=avg(6), tiles=avg(7), ctas=len(rows))
@@ -41,7 +43,8 @@ def report(name, fn):
 
 
 g = lambda *s: torch.randn(*s, device="cuda").half().float()
-for (M, K, N, res, geglu) in [(65536, 320, 320, False, False), (65536, 320, 320, True, False), (65536, 320, 960, False, False),
+LONGK = int(os.environ.get("LONGK", 0))       # only the long-K shapes
+for (M, K, N, res, geglu) in [(65536, 1280, 320, True, False), (16384, 2560, 640, True, False), (4096, 5120, 1280, True, False)] if LONGK else [(65536, 320, 320, False, False), (65536, 320, 320, True, False), (65536, 320, 960, False, False),
                              (65536, 320, 2560, False, True), (65536, 1280, 320, True, False), (16384, 640, 640, True, False),
                              (4096, 1280, 1280, True, False)]:
     x, w, b = g(M, K), g(N, K) / math.sqrt(K), torch.randn(N, device="cuda")
