@@ -238,11 +238,28 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   const bool pair_ok = c.gemm_pair && g.cstride <= 1 && !g.up && !g.nk1 && Bplain != nullptr && grid.z == 1 && grid.x >= 2 &&
                        (g.a_mode == A_PLAIN || g.a_mode == A_CONV3) && g.b_mode == B_PLAIN && g.nk >= c.gemm_pair_min_nk &&
                        (long long)grid.x * grid.y >= c.num_sms / 2;
+  // Long-K launches are bound by L2->SM operand delivery (clock64 role trace: the MMA warp waits 26-37 % of its time for
+  // operands while the ring is not full; profiles/r02_gemm_role_trace_long_k.txt): pairs of CTAs on consecutive M tiles
+  // share every weight tile by TMA multicast (each fetches half of it), -9..-14 % per launch.  A work-distribution
+  // choice from the launch shape only; the arithmetic of a tile is the 1-CTA kernel's.
+  CUtensorMap tmB_mc;
+  const CUtensorMap* tmBp = &tmB;
+  if (mcast_cs == 0 && c.gemm_mcast_big > 1 && Bplain != nullptr && grid.z == 1 && !g.nk1 && !g.up && g.cstride <= 1 &&
+      g.b_mode == B_PLAIN && (g.a_mode == A_PLAIN || g.a_mode == A_CONV3) && g.nk >= c.gemm_mcast_min_nk &&
+      grid.x % c.gemm_mcast_big == 0 && g.BN % c.gemm_mcast_big == 0 && (g.BN / c.gemm_mcast_big) % 8 == 0 &&
+      (long long)grid.x * grid.y >= c.num_sms && !(c.gemm_pair && g.nk >= c.gemm_pair_min_nk)) {
+    mcast_cs = c.gemm_mcast_big;
+    const uint64_t db[2] = {(uint64_t)kp, (uint64_t)nrows_w};
+    const uint64_t sb[1] = {(uint64_t)kp * 2};
+    const uint32_t bb[2] = {64, (uint32_t)(g.BN / mcast_cs)};
+    tmB_mc = make_tmap(c, Bplain, 2, db, sb, bb);
+    tmBp = &tmB_mc;
+  }
   if (mcast_cs > 1) {
     // cluster of mcast_cs CTAs on consecutive M tiles sharing every weight tile by TMA multicast (gemm_mcast.cuh);
-    // tmB must have been built with a box of BN / mcast_cs rows
+    // the B map has a box of BN / mcast_cs rows
     RFB_CHECK(grid.x % mcast_cs == 0 && (g.BN / mcast_cs) % 8 == 0 && g.BN % mcast_cs == 0 && g.b_mode == B_PLAIN &&
-                  (g.a_mode == A_PLAIN || (g.a_mode == A_CONV3 && g.cstride == 1 && !g.up)) && !g.nk1 && !g.geglu,
+                  (g.a_mode == A_PLAIN || (g.a_mode == A_CONV3 && g.cstride == 1 && !g.up)) && !g.nk1,
               "multicast GEMM: shape not supported");
     const bool fast = g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f;
     const int budget = (227 - 3) * 1024 - 4 * 2 * EPI_WARP_BYTES;
@@ -276,9 +293,12 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     const int clusters = std::min(units, c.once_flags[key + "_max"]);                                                  \
     cfg.gridDim = dim3((unsigned)(clusters * CS_));                                                                    \
     cfg.numAttrs = c.pdl_now() ? 2 : 1;                                                                                 \
-    CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, g, m_groups, n_tiles, units));                                     \
+    CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, tmA, *tmBp, g, m_groups, n_tiles, units));                                     \
   } while (0)
-    if (fast) {
+    if (g.geglu) {
+      RFB_CHECK(mcast_cs == 2, "multicast GEGLU GEMM: cluster of 2 only");
+      RFB_MCAST(EPI_GEGLU, 2);
+    } else if (fast) {
       if (mcast_cs == 8) RFB_MCAST(EPI_FAST, 8);
       else if (mcast_cs == 4) RFB_MCAST(EPI_FAST, 4);
       else RFB_MCAST(EPI_FAST, 2);
@@ -559,9 +579,6 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
     if (c.gemm_mcast && ks > 1 && stride == 1 && M % 128 == 0) {
       const long long mt = M / 128;
       cs = mt % 8 == 0 ? 8 : (mt % 4 == 0 ? 4 : (mt % 2 == 0 ? 2 : 0));
-    } else if (c.gemm_mcast_big > 1 && ks == 1 && stride == 1 && M % (128 * c.gemm_mcast_big) == 0 &&
-               g.BN % c.gemm_mcast_big == 0 && (g.BN / c.gemm_mcast_big) % 8 == 0) {
-      cs = c.gemm_mcast_big;  // experiment: the long-K convs of the large maps (MMA warp waits ~32 % for operands)
     }
     const uint64_t db[2] = {(uint64_t)w.kp, (uint64_t)round_up(w.cout, 32)};
     const uint64_t sb[1] = {(uint64_t)w.kp * 2};

@@ -104,7 +104,9 @@ struct Ctx {
   int pdl = 1;
   bool pdl_now() const { return pdl == 2 || (pdl == 1 && (gstream == nullptr || stream != gstream)); }
   int gemm_lean = 1;     // lean-drain kernel for launches whose every tile is full and vectorisable
-  int gemm_mcast_big = 0;  // cluster size (2, 4, 8) for weight-tile multicast on the un-split long-K convs as well
+  // weight-tile multicast for every long-K GEMM / conv that fills the GPU: cluster size (0: off) and the K blocks from
+  // which a launch counts as long-K (short-K launches are epilogue-bound)
+  int gemm_mcast_big = 2, gemm_mcast_min_nk = 16;
   int gemm_mcast = 1;    // weight-tile TMA multicast across a cluster of M tiles for the split-K convs (gemm_mcast.cuh)
   int gemm_splitk = 1;   // 3-way split-K for the long-K 3x3 convs of <= 8x8 maps (slice count from the per-sample shape only)
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)

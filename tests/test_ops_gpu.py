@@ -290,6 +290,32 @@ def test_split_k_is_batch_independent(engine, batch):
     assert torch.equal(y_nomc, y)
 
 
+def test_long_k_weight_multicast_is_bit_identical(engine):
+    """Every long-K launch (K >= 1024) that fills the GPU runs as clusters of 2 CTAs on consecutive M tiles that share
+    each weight tile by TMA multicast (option gemm_mcast_big; launch_gemm in engine.cu): plain linears with bias +
+    residual, GEGLU, 3x3 convolutions with a time-embedding row vector and GroupNorm statistics in the epilogue.  Work
+    distribution only: the bits are the 1-CTA kernel's, and the results stay batch-independent."""
+    x, w, b = h(rn(4096, 5120, seed=1)), h(rn(1280, 5120, seed=2) / math.sqrt(5120)), rn(1280, seed=3)
+    r = h(rn(4096, 1280, seed=4))
+    xg, wg, bg = h(rn(4096, 1280, seed=5)), h(rn(2 * 5120, 1280, seed=6) / math.sqrt(1280)), rn(2 * 5120, seed=7)
+    xc, wc, bc = h(rn(8, 640, 32, 32, seed=8)), h(rn(640, 640, 3, 3, seed=9) / math.sqrt(9 * 640)), rn(640, seed=10)
+
+    def run():
+        return (engine.op_linear(x, w, b, residual=r), engine.op_linear(xg, wg, bg, geglu=True),
+                engine.op_conv2d(xc, wc, bc), engine.op_conv2d(xc[:2], wc, bc))
+    on = run()
+    engine.set_option("gemm_mcast_big", 0)
+    try:
+        off = run()
+    finally:
+        engine.set_option("gemm_mcast_big", 2)
+    for a, o in zip(on, off):
+        assert torch.equal(a, o)
+    assert torch.equal(on[2][:2], on[3])                          # 64 M tiles vs 16: same bits per sample
+    assert rel(on[0], F.linear(x, w, b) + r) < 4e-3
+    assert rel(on[2], F.conv2d(xc, wc, bc, padding=1)) < 4e-3
+
+
 def test_paste_back_bit_exact(engine, oracle):
     """rfb_paste_back vs the Pillow-written fixture (bit exact) and vs the oracle at the real sizes
     (512 -> 1024 resize, 720p frame, two frames with different coefficients)."""
