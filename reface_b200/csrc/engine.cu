@@ -199,6 +199,14 @@ int pick_bn(Ctx& c, long long M, int N, bool geglu, int K, bool allow16) {
   return best;
 }
 
+// EPI_FAST launches whose every tile is full and vectorisable take the kernel with the lean drain only (gemm_epilogue.cuh)
+static bool epi_lean_ok(const Ctx& c, const GemmArgs& g) {
+  const long long zo = g.zs_outer | g.zs_inner;
+  return c.gemm_lean && g.out != nullptr && !g.up && g.M % GEMM_BM == 0 && g.N % g.BN == 0 && g.BN % 16 == 0 &&
+         (g.N & 7) == 0 && (g.ldo & 7) == 0 && (zo & 7) == 0 && (!g.res || (g.ldr & 7) == 0) &&
+         (!g.rowvec || ((g.ldv & 3) == 0 && g.rows_per_vec % 32 == 0 && (g.rowvec_zs & 3) == 0));
+}
+
 // Bplain/kp/nrows_w: the plain 2-D weight operand (lets the 2-CTA kernel rebuild the B map with a half-height box)
 static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, dim3 grid, double kalg,
                         const __half* Bplain = nullptr, int kp = 0, int nrows_w = 0, const CUtensorMap* tmA2p = nullptr,
@@ -299,7 +307,8 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
       RFB_CHECK(mcast_cs == 2, "multicast GEGLU GEMM: cluster of 2 only");
       RFB_MCAST(EPI_GEGLU, 2);
     } else if (fast) {
-      if (mcast_cs == 8) RFB_MCAST(EPI_FAST, 8);
+      if (mcast_cs == 2 && epi_lean_ok(c, g)) RFB_MCAST(EPI_LEAN, 2);
+      else if (mcast_cs == 8) RFB_MCAST(EPI_FAST, 8);
       else if (mcast_cs == 4) RFB_MCAST(EPI_FAST, 4);
       else RFB_MCAST(EPI_FAST, 2);
     } else {
@@ -371,11 +380,7 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
       else launch_pdl(c, gemm_persist_kernel<EPI_GEGLU, 2>, dim3(ctas), dim3(thr), psmem, tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
     } else if (g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f) {
       // every tile full and vectorisable -> the kernel with the lean drain only (gemm_epilogue.cuh)
-      const long long zo = g.zs_outer | g.zs_inner;
-      const bool lean = c.gemm_lean && g.out != nullptr && !g.up && g.M % GEMM_BM == 0 && g.N % g.BN == 0 && g.BN % 16 == 0 &&
-                        (g.N & 7) == 0 && (g.ldo & 7) == 0 && (zo & 7) == 0 && (!g.res || (g.ldr & 7) == 0) &&
-                        (!g.rowvec || ((g.ldv & 3) == 0 && g.rows_per_vec % 32 == 0 && (g.rowvec_zs & 3) == 0));
-      if (lean) {
+      if (epi_lean_ok(c, g)) {
         if (np == 3) launch_pdl(c, gemm_persist_kernel<EPI_LEAN, 3>, dim3(ctas), dim3(thr), psmem, tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
         else launch_pdl(c, gemm_persist_kernel<EPI_LEAN, 2>, dim3(ctas), dim3(thr), psmem, tmA, tmB, tmA2, g, m_tiles, n_tiles, total);
       } else if (np == 3) launch_pdl(c, gemm_persist_kernel<EPI_FAST, 3>, dim3(ctas), dim3(thr), psmem, tmA, tmB, tmA2, g, m_tiles, n_tiles, total);

@@ -93,6 +93,7 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------ TMA producer
     const uint32_t tx = GEMM_A_STAGE_BYTES + b_stage_bytes;
     uint32_t st = 0, sp = 0;
+    long long t_empty = 0;  // clock64 role counters as in gemm_persist_kernel (option gemm_debug)
     for (int u = cluster_id; u < total_units; u += num_clusters) {
       const int z = u / per_z;
       const int rem = u - z * per_z;
@@ -115,7 +116,9 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int kb = 0; kb < g.nk; ++kb) {
         const uint32_t s = st, ph = sp;
         if (++st == (uint32_t)S) st = 0, sp ^= 1u;
+        const long long tw0 = g.dbg ? clock64() : 0;
         mbar_wait(bars + 8u * (S + s), ph ^ 1u);  // all CS consumers have released this slot
+        if (g.dbg) t_empty += clock64() - tw0;
         const uint32_t full = bars + 8u * s;
         if (elect_one()) {
           mbar_expect_tx(full, tx);
@@ -135,19 +138,26 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
       }
     }
+    if (g.dbg && lane == 0) g.dbg[(size_t)blockIdx.x * 8 + 3] = (unsigned long long)t_empty;
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = idesc_f16(GEMM_BM, (uint32_t)BN);
     uint32_t ti = 0, st = 0, sp = 0;
+    long long t_full = 0, t_acc = 0;
+    const long long t_begin = g.dbg ? clock64() : 0;
     for (int u = cluster_id; u < total_units; u += num_clusters, ++ti) {
       const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+      long long tw0 = g.dbg ? clock64() : 0;
       mbar_wait(bar_acce + 8u * as, aph ^ 1u);
+      if (g.dbg) t_acc += clock64() - tw0;
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * 256u;
       for (int kb = 0; kb < g.nk; ++kb) {
         const uint32_t s = st, ph = sp;
         if (++st == (uint32_t)S) st = 0, sp ^= 1u;
+        tw0 = g.dbg ? clock64() : 0;
         mbar_wait(bars + 8u * s, ph);
+        if (g.dbg) t_full += clock64() - tw0;
         tc_fence_after();
         if (elect_one()) {
           const uint64_t da = smem_desc_k_sw128(sA + s * GEMM_A_STAGE_BYTES);
@@ -162,6 +172,10 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
     pdl_trigger();  // as in gemm_persist_kernel
+    if (g.dbg && lane == 0) {
+      unsigned long long* d = g.dbg + (size_t)blockIdx.x * 8;
+      d[0] = (unsigned long long)(clock64() - t_begin), d[1] = (unsigned long long)t_full, d[2] = (unsigned long long)t_acc, d[7] = ti;
+    }
   } else {
     // -------------------------------------------------------------- epilogue (warps 2..9), CTA-local
     const int e = warp - 2;
@@ -169,6 +183,8 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int half = e >> 2;
     const uint32_t stage = epi_stage + (uint32_t)e * EPI_WARP_BYTES;
     uint32_t ti = 0;
+    long long t_wait = 0;
+    const long long t_ebegin = g.dbg ? clock64() : 0;
     float nb[4] = {0.f, 0.f, 0.f, 0.f};
     auto tile_of = [&](int u, int& n_tile) {
       const int z = u / per_z;
@@ -192,13 +208,19 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const EpiTile en = tile_of(u + num_clusters, nt);
         epilogue_lookahead<MODE, NP>(g, en, lane, half, nb);
       }
+      const long long tw0 = g.dbg ? clock64() : 0;
       mbar_wait(bar_accf + 8u * as, aph);
+      if (g.dbg) t_wait += clock64() - tw0;
       tc_fence_after();
       const uint32_t trow = tmem_base + as * 256u + ((uint32_t)(q * 32) << 16);
       epilogue_drain<MODE, NP>(g, et, trow, stage, lane, half, n_tile);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acce + 8u * as);
+    }
+    if (g.dbg && warp == 2 && lane == 0) {
+      g.dbg[(size_t)blockIdx.x * 8 + 4] = (unsigned long long)t_wait;
+      g.dbg[(size_t)blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - t_ebegin);
     }
   }
   tc_fence_before();
