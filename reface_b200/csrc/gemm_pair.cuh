@@ -75,7 +75,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
     uint32_t st = 0, sp = 0;
-    long long t_empty = 0;
+    long long t_empty = 0, t_issue = 0;
     for (int pt = pair_id; pt < total_pairs; pt += num_pairs) {
       const int z = pt / per_z;
       const int rem = pt - z * per_z;
@@ -101,7 +101,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int nv = min(KM, g.nk - kb0);
         const long long t0 = g.dbg ? clock64() : 0;
         mbar_wait(bars + 8u * (S + s), ph ^ 1u);
-        if (g.dbg) t_empty += clock64() - t0;
+        const long long ti0 = g.dbg ? clock64() : 0;
+        if (g.dbg) t_empty += ti0 - t0;
         const uint32_t full = bars + 8u * s;
         if (elect_one()) {
           if (leader) mbar_expect_tx(full, 2u * (uint32_t)nv * (GEMM_A_STAGE_BYTES + b_sub_bytes));
@@ -121,9 +122,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         __syncwarp();
+        if (g.dbg) t_issue += clock64() - ti0;
       }
     }
-    if (g.dbg && lane == 0) g.dbg[(size_t)blockIdx.x * 8 + 3] = (unsigned long long)t_empty;
+    if (g.dbg && lane == 0) {
+      g.dbg[(size_t)blockIdx.x * 8 + 3] = (unsigned long long)t_empty;
+      g.dbg[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)t_issue;
+    }
   } else if (warp == 1) {
     if (leader) {
       // ------------------------------------------------------------ MMA issuer (leader CTA)
@@ -164,7 +169,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (g.dbg && lane == 0) {
         unsigned long long* d = g.dbg + (size_t)blockIdx.x * 8;
         d[0] = (unsigned long long)(clock64() - t_begin), d[1] = (unsigned long long)t_full;
-        d[2] = (unsigned long long)t_acc, d[6] = it, d[7] = ti;
+        d[2] = (unsigned long long)t_acc, d[7] = ti;
       }
     }
   } else {

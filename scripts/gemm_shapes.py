@@ -2,7 +2,10 @@
 import collections, os, re, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if os.environ.get("CHILD") != "1":
-    out = subprocess.run([sys.executable, __file__], env=dict(os.environ, CHILD="1"), capture_output=True, text=True).stdout
+    r = subprocess.run([sys.executable, __file__], env=dict(os.environ, CHILD="1"), capture_output=True, text=True)
+    out = r.stdout
+    if r.returncode != 0:
+        print(r.stderr[-2000:])
     agg = collections.OrderedDict()
     for line in out.splitlines():
         m = re.match(r"PROF kind=(\d+) M=(\d+) N=(\d+) K=(\d+) BN=(\d+) z=(\d+) mode=(\d+) us=([\d.]+) tflops=([\d.]+)", line)

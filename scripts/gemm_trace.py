@@ -23,6 +23,9 @@ def read():
                 epi_prefetch=avg(6), tiles=avg(7), ctas=len(rows))
 
 
+ISSUE = int(os.environ.get("ISSUE", 0))   # multicast / pair kernels: slot 6 = cycles the producer spends issuing its TMA loads
+
+
 def report(name, fn):
     fn(); torch.cuda.synchronize()
     eng.set_option("gemm_debug", 1)
@@ -38,6 +41,7 @@ def report(name, fn):
     t = max(d["tiles"], 1)
     print(f"{name:44s} {us:7.1f} us/call(incl. casts) | per tile: MMA warp {d['mma_total']/t:7.0f} cyc (wait operands {100*d['wait_full']/d['mma_total']:4.1f} %, "
           f"wait acc stage {100*d['wait_acc']/d['mma_total']:4.1f} %) | producer waits for a slot {100*d['prod_wait_empty']/d['mma_total']:4.1f} % | "
+          + (f"producer TMA issue {100*d['epi_prefetch']/d['mma_total']:4.1f} % | " if ISSUE else "") +
           f"epilogue warp {d['epi_total']/t:7.0f} cyc (wait acc {100*d['epi_wait_acc']/d['epi_total']:4.1f} %, prefetch {100*d['epi_prefetch']/d['epi_total']:4.1f} %, "
           f"drain {100*(d['epi_total']-d['epi_wait_acc']-d['epi_prefetch'])/d['epi_total']:4.1f} %) tiles/CTA {t:.1f}", flush=True)
 

@@ -300,9 +300,11 @@ def test_long_k_weight_multicast_is_bit_identical(engine):
     xg, wg, bg = h(rn(4096, 1280, seed=5)), h(rn(2 * 5120, 1280, seed=6) / math.sqrt(1280)), rn(2 * 5120, seed=7)
     xc, wc, bc = h(rn(8, 640, 32, 32, seed=8)), h(rn(640, 640, 3, 3, seed=9) / math.sqrt(9 * 640)), rn(640, seed=10)
 
+    xd, wd, bd = h(rn(4, 320, 64, 64, seed=11)), h(rn(320, 320, 3, 3, seed=12) / math.sqrt(9 * 320)), rn(320, seed=13)
+
     def run():
         return (engine.op_linear(x, w, b, residual=r), engine.op_linear(xg, wg, bg, geglu=True),
-                engine.op_conv2d(xc, wc, bc), engine.op_conv2d(xc[:2], wc, bc))
+                engine.op_conv2d(xc, wc, bc), engine.op_conv2d(xc[:2], wc, bc), engine.op_conv2d(xd, wd, bd))
     on = run()
     engine.set_option("gemm_mcast_big", 0)
     try:
@@ -311,6 +313,17 @@ def test_long_k_weight_multicast_is_bit_identical(engine):
         engine.set_option("gemm_mcast_big", 2)
     for a, o in zip(on, off):
         assert torch.equal(a, o)
+    # the convolutions additionally share the ACTIVATION tile between two N tiles (gemm_mcast_a: 2 = clusters of 2 x 2,
+    # 1 = 1 x 2, 0 = weight sharing only): each CTA issues half of the 4-D box and multicasts it
+    for mode in (1, 0):
+        engine.set_option("gemm_mcast_a", mode)
+        try:
+            alt = run()
+        finally:
+            engine.set_option("gemm_mcast_a", 2)
+        for a, o in zip(on, alt):
+            assert torch.equal(a, o), mode
+    assert rel(on[4], F.conv2d(xd, wd, bd, padding=1)) < 4e-3
     assert torch.equal(on[2][:2], on[3])                          # 64 M tiles vs 16: same bits per sample
     assert rel(on[0], F.linear(x, w, b) + r) < 4e-3
     assert rel(on[2], F.conv2d(xc, wc, bc, padding=1)) < 4e-3
