@@ -283,7 +283,7 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     const int units = m_groups * (n_tiles / mcast_cn) * (int)grid.z;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.blockDim = dim3(GEMMP_THREADS);
+    cfg.blockDim = dim3(GEMMC_THREADS);
     cfg.dynamicSmemBytes = psmem;
     cfg.stream = c.stream;
     cudaLaunchAttribute at[2];

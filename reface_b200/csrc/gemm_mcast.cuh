@@ -8,8 +8,10 @@
 // own 128 x 64 A tile, but only 1/CS of the B tile, with cp.async.bulk.tensor ... .multicast::cluster, so that the slice
 // lands in the shared memory of all CS CTAs.  L2->SM weight traffic drops by CS.
 //
-// Protocol per CTA (roles as in gemm_persist.cuh: warp0 TMA producer, warp1 MMA issuer, warps 2.. epilogue):
-//   full[s]   count 1 + transaction bytes of the WHOLE stage (own A tile + all CS slices of B: every peer's multicast
+// Protocol per CTA (warp0 TMA producer of the activation tiles, warp1 MMA issuer, warps 2..9 epilogue, warp 10 TMA
+// producer of the weight slices):
+//   full[s]   count 2 (one arrive.expect_tx per producer warp) + transaction bytes of the WHOLE stage (A tile + all CS
+//             slices of B: every peer's multicast
 //             signals the barrier at the same offset in every destination CTA)
 //   empty[s]  count CS: a slot may be overwritten by any peer, so every CTA's MMA warp releases it in ALL CTAs
 //             (tcgen05.commit ... .multicast::cluster) and a producer refills it only when all CS consumers are done
@@ -55,9 +57,12 @@ __device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
 }
 
 // units: (z, m_group, n_tile), n_tile fastest; a cluster takes unit blockIdx.x / CS + i * (gridDim.x / CS)
+static constexpr int GEMMC_B_WARP = GEMMP_THREADS / 32;  // warps: 0 TMA (activations), 1 MMA, 2..9 epilogue, 10 TMA (weights)
+static constexpr int GEMMC_THREADS = GEMMP_THREADS + 32;
+
 // n_tiles: N tiles per unit row = CN * (number of N groups)
 template <int MODE, int CS, int CN = 1>
-__global__ void __launch_bounds__(GEMMP_THREADS, 1)
+__global__ void __launch_bounds__(GEMMC_THREADS, 1)
 gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g,
                   const int m_groups, const int n_tiles, const int total_units) {
   static_assert(CN == 1 || CN == 2, "activation sharing: pairs of N tiles");
@@ -87,7 +92,7 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
-      mbar_init(bars + 8u * i, 1);
+      mbar_init(bars + 8u * i, 2);  // the two producer warps
       mbar_init(bars + 8u * (S + i), CS + CN - 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -115,9 +120,14 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n_groups = n_tiles / CN;
   const int per_z = m_groups * n_groups;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    const uint32_t tx = GEMM_A_STAGE_BYTES + b_stage_bytes;
+  if (warp == 0 || warp == GEMMC_B_WARP) {
+    // ------------------------------------------------------------ TMA producers: warp 0 loads the activation tiles,
+    // warp GEMMC_B_WARP the weight slices.  Two warps because a TMA instruction occupies its issuing warp for ~80
+    // (2-D box) to ~240 (4-D conv box) clocks (clock64 trace: one warp issuing both spent 72 % of a conv launch inside
+    // them, 322 of the 441 clocks per K block, and the MMA warp waited 25 % of its time for operands): issued from two
+    // warps the two latencies overlap.  Both arrive on full[s] (count 2) with their own byte counts.
+    const bool load_a = warp == 0;
+    const uint32_t tx = load_a ? GEMM_A_STAGE_BYTES : b_stage_bytes;
     uint32_t st = 0, sp = 0;
     long long t_empty = 0, t_issue = 0;  // clock64 role counters as in gemm_persist_kernel (option gemm_debug)
     for (int u = cluster_id; u < total_units; u += num_clusters) {
@@ -153,7 +163,9 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t dA = sA + s * GEMM_A_STAGE_BYTES + (CN > 1 ? rn * (GEMM_A_STAGE_BYTES / 2) : 0u);
           const uint32_t dB = sB + s * b_stage_bytes + rank * b_slice_rows * 128u;
           const int kg = g.ksplit ? z * g.nk + kb : kb;
-          if (g.a_mode == A_PLAIN) {
+          if (!load_a) {
+            tma_load_2d_mc(dB, &tmB, full, kg * GEMM_BK, n0, MASK);  // this CTA's slice of the weight tile -> all CTAs
+          } else if (g.a_mode == A_PLAIN) {
             tma_load_2d(dA, &tmA, full, kg * GEMM_BK, m0);  // (CN = 1 only)
           } else {
             const int tap = kg / g.cblocks;
@@ -162,15 +174,14 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (CN > 1) tma_load_4d_mc(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn, MASK_A);
             else tma_load_4d(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn);
           }
-          tma_load_2d_mc(dB, &tmB, full, kg * GEMM_BK, n0, MASK);  // this CTA's slice of the weight tile -> all CTAs
         }
         __syncwarp();
         if (g.dbg) t_issue += clock64() - ti0;
       }
     }
-    if (g.dbg && lane == 0) {
+    if (g.dbg && lane == 0 && load_a) {
       g.dbg[(size_t)blockIdx.x * 8 + 3] = (unsigned long long)t_empty;
-      g.dbg[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)t_issue;  // expect_tx + the two TMA instructions
+      g.dbg[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)t_issue;  // expect_tx + the activation TMA instruction
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
