@@ -271,6 +271,8 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     RFB_CHECK(grid.x % mcast_cs == 0 && (g.BN / mcast_cs) % 8 == 0 && g.BN % mcast_cs == 0 && g.b_mode == B_PLAIN &&
                   (g.a_mode == A_PLAIN || (g.a_mode == A_CONV3 && g.cstride == 1 && !g.up)) && !g.nk1,
               "multicast GEMM: shape not supported");
+    RFB_CHECK(!g.a_split || (mcast_cn == 1 && g.a_mode == A_CONV3 && (g.ah_dh > 0) != (g.ah_dn > 0)),
+              "multicast GEMM: split activation box needs a convolution");
     RFB_CHECK(mcast_cn == 1 || (mcast_cn == 2 && mcast_cs <= 2 && g.a_mode == A_CONV3 && grid.y % 2 == 0 && !g.geglu &&
                                 (g.ah_dh > 0) != (g.ah_dn > 0)),
               "multicast GEMM: activation sharing not supported for this launch");
@@ -614,11 +616,18 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
       if (g.bimg >= 2) g.ah_dn = g.bimg / 2, ba_h[3] = (uint32_t)g.ah_dn;
       else g.ah_dh = g.bh / 2, ba_h[2] = (uint32_t)g.ah_dh;
       cs = (c.gemm_mcast_a >= 2 && m_tiles_c % 2 == 0 && g.BN % 2 == 0 && (g.BN / 2) % 8 == 0) ? 2 : 1;
+    } else if (c.gemm_mcast_big > 1 && c.gemm_a_split && ks == 1 && stride == 1 && g.nk >= c.gemm_mcast_min_nk && M % 256 == 0 &&
+               g.BN % 2 == 0 && (g.BN / 2) % 8 == 0 && m_tiles_c * n_tiles_c >= c.num_sms &&
+               !(c.gemm_pair && g.nk >= c.gemm_pair_min_nk) && (g.bimg >= 2 ? g.bimg % 2 == 0 : g.bh % 2 == 0)) {
+      // weight tile shared across two M tiles (as launch_gemm would choose) + the activation box issued as two halves
+      cs = 2, g.a_split = 1;
+      if (g.bimg >= 2) g.ah_dn = g.bimg / 2, ba_h[3] = (uint32_t)g.ah_dn;
+      else g.ah_dh = g.bh / 2, ba_h[2] = (uint32_t)g.ah_dh;
     }
     const uint64_t db[2] = {(uint64_t)w.kp, (uint64_t)round_up(w.cout, 32)};
     const uint64_t sb[1] = {(uint64_t)w.kp * 2};
     const uint32_t bb[2] = {64, (uint32_t)(cs > 1 ? g.BN / cs : g.BN)};
-    CUtensorMap tmA = make_tmap(c, x.p, 4, da, sa, cn > 1 ? ba_h : ba, stride > 1 ? ea : nullptr);
+    CUtensorMap tmA = make_tmap(c, x.p, 4, da, sa, (cn > 1 || g.a_split) ? ba_h : ba, stride > 1 ? ea : nullptr);
     CUtensorMap tmB = make_tmap(c, w.w, 2, db, sb, bb);
     dim3 grid((unsigned)m_tiles_c, (unsigned)n_tiles_c, (unsigned)ks);
     launch_gemm(c, tmA, tmB, g, grid, 9.0 * w.cin / ks, w.w, w.kp, round_up(w.cout, 32), nullptr, cs, 0, cn);

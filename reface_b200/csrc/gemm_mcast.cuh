@@ -57,8 +57,11 @@ __device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
 }
 
 // units: (z, m_group, n_tile), n_tile fastest; a cluster takes unit blockIdx.x / CS + i * (gridDim.x / CS)
-static constexpr int GEMMC_B_WARP = GEMMP_THREADS / 32;  // warps: 0 TMA (activations), 1 MMA, 2..9 epilogue, 10 TMA (weights)
-static constexpr int GEMMC_THREADS = GEMMP_THREADS + 32;
+// warps: 0 TMA (activations), 1 MMA, 2..9 epilogue, 10 TMA (weights), 11 TMA (second half of the activation box when
+// GemmArgs::a_split: the 4-D conv box costs its issuing warp ~2.3 clocks per pixel row)
+static constexpr int GEMMC_B_WARP = GEMMP_THREADS / 32;
+static constexpr int GEMMC_A2_WARP = GEMMC_B_WARP + 1;
+static constexpr int GEMMC_THREADS = GEMMP_THREADS + 64;
 
 // n_tiles: N tiles per unit row = CN * (number of N groups)
 template <int MODE, int CS, int CN = 1>
@@ -92,7 +95,7 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
-      mbar_init(bars + 8u * i, 2);  // the two producer warps
+      mbar_init(bars + 8u * i, g.a_split ? 3 : 2);  // the producer warps
       mbar_init(bars + 8u * (S + i), CS + CN - 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -120,14 +123,17 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n_groups = n_tiles / CN;
   const int per_z = m_groups * n_groups;
 
-  if (warp == 0 || warp == GEMMC_B_WARP) {
+  if (warp == GEMMC_A2_WARP && !g.a_split) {
+    // idle
+  } else if (warp == 0 || warp == GEMMC_B_WARP || warp == GEMMC_A2_WARP) {
     // ------------------------------------------------------------ TMA producers: warp 0 loads the activation tiles,
     // warp GEMMC_B_WARP the weight slices.  Two warps because a TMA instruction occupies its issuing warp for ~80
     // (2-D box) to ~240 (4-D conv box) clocks (clock64 trace: one warp issuing both spent 72 % of a conv launch inside
     // them, 322 of the 441 clocks per K block, and the MMA warp waited 25 % of its time for operands): issued from two
     // warps the two latencies overlap.  Both arrive on full[s] (count 2) with their own byte counts.
-    const bool load_a = warp == 0;
-    const uint32_t tx = load_a ? GEMM_A_STAGE_BYTES : b_stage_bytes;
+    const bool load_a = warp != GEMMC_B_WARP;
+    const uint32_t ahalf = warp == GEMMC_A2_WARP ? 1u : 0u;  // a_split (CN = 1): which half of the box this warp loads
+    const uint32_t tx = !load_a ? b_stage_bytes : (g.a_split ? GEMM_A_STAGE_BYTES / 2 : GEMM_A_STAGE_BYTES);
     uint32_t st = 0, sp = 0;
     long long t_empty = 0, t_issue = 0;  // clock64 role counters as in gemm_persist_kernel (option gemm_debug)
     for (int u = cluster_id; u < total_units; u += num_clusters) {
@@ -150,6 +156,7 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m0 = m_tile * GEMM_BM;
       const int n0 = n_tile * BN + (int)(rank * b_slice_rows);
       if (CN > 1) ch += (int)rn * g.ah_dh, cn += (int)rn * g.ah_dn;  // my half of the A box (tmA has the half-size box)
+      else if (g.a_split) ch += (int)ahalf * g.ah_dh, cn += (int)ahalf * g.ah_dn;
       for (int kb = 0; kb < g.nk; ++kb) {
         const uint32_t s = st, ph = sp;
         if (++st == (uint32_t)S) st = 0, sp ^= 1u;
@@ -160,7 +167,7 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t full = bars + 8u * s;
         if (elect_one()) {
           mbar_expect_tx(full, tx);
-          const uint32_t dA = sA + s * GEMM_A_STAGE_BYTES + (CN > 1 ? rn * (GEMM_A_STAGE_BYTES / 2) : 0u);
+          const uint32_t dA = sA + s * GEMM_A_STAGE_BYTES + (CN > 1 ? rn : ahalf) * (GEMM_A_STAGE_BYTES / 2);
           const uint32_t dB = sB + s * b_stage_bytes + rank * b_slice_rows * 128u;
           const int kg = g.ksplit ? z * g.nk + kb : kb;
           if (!load_a) {
@@ -179,7 +186,7 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (g.dbg) t_issue += clock64() - ti0;
       }
     }
-    if (g.dbg && lane == 0 && load_a) {
+    if (g.dbg && lane == 0 && warp == 0) {
       g.dbg[(size_t)blockIdx.x * 8 + 3] = (unsigned long long)t_empty;
       g.dbg[(size_t)blockIdx.x * 8 + 6] = (unsigned long long)t_issue;  // expect_tx + the activation TMA instruction
     }
