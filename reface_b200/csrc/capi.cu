@@ -209,8 +209,6 @@ int rfb_set_option(rfb_ctx* h, const char* key, long long value) {
   else if (k == "pdl") c.pdl = (int)value;
   else if (k == "gemm_mcast_big") c.gemm_mcast_big = (int)value;
   else if (k == "gemm_mcast_min_nk") c.gemm_mcast_min_nk = (int)value;
-  else if (k == "gemm_mcast_a") c.gemm_mcast_a = (int)value;
-  else if (k == "gemm_a_split") c.gemm_a_split = (int)value;
   else if (k == "conv_tma_stride2") c.conv_tma_stride2 = (int)value;
   else if (k == "ln_vec") c.ln_vec = (int)value;
   else if (k == "gemm_pair") c.gemm_pair = (int)value;

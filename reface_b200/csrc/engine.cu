@@ -210,7 +210,7 @@ static bool epi_lean_ok(const Ctx& c, const GemmArgs& g) {
 // Bplain/kp/nrows_w: the plain 2-D weight operand (lets the 2-CTA kernel rebuild the B map with a half-height box)
 static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmArgs g, dim3 grid, double kalg,
                         const __half* Bplain = nullptr, int kp = 0, int nrows_w = 0, const CUtensorMap* tmA2p = nullptr,
-                        int mcast_cs = 0, double kalg_ref = 0, int mcast_cn = 1) {
+                        int mcast_cs = 0, double kalg_ref = 0) {
   const CUtensorMap& tmA2 = tmA2p ? *tmA2p : tmA;
   if (g.ctw <= 0) g.ctw = 3;
   RFB_CHECK(!g.up || (!g.res && !g.rowvec && !g.out32 && !g.ksplit), "folded upsample conv: plain fp16 epilogue only");
@@ -263,26 +263,19 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     tmB_mc = make_tmap(c, Bplain, 2, db, sb, bb);
     tmBp = &tmB_mc;
   }
-  if (mcast_cs > 1 || mcast_cn > 1) {
+  if (mcast_cs > 1) {
     // cluster of mcast_cs CTAs on consecutive M tiles sharing every weight tile by TMA multicast (gemm_mcast.cuh);
-    // the B map has a box of BN / mcast_cs rows.  mcast_cn = 2: x 2 consecutive N tiles sharing the activation tile
-    // (convolutions only; tmA then has the half-size box and g.ah_dh / g.ah_dn the offset of the second half)
-    mcast_cs = std::max(mcast_cs, 1);
+    // the B map has a box of BN / mcast_cs rows
     RFB_CHECK(grid.x % mcast_cs == 0 && (g.BN / mcast_cs) % 8 == 0 && g.BN % mcast_cs == 0 && g.b_mode == B_PLAIN &&
                   (g.a_mode == A_PLAIN || (g.a_mode == A_CONV3 && g.cstride == 1 && !g.up)) && !g.nk1,
               "multicast GEMM: shape not supported");
-    RFB_CHECK(!g.a_split || (mcast_cn == 1 && g.a_mode == A_CONV3 && (g.ah_dh > 0) != (g.ah_dn > 0)),
-              "multicast GEMM: split activation box needs a convolution");
-    RFB_CHECK(mcast_cn == 1 || (mcast_cn == 2 && mcast_cs <= 2 && g.a_mode == A_CONV3 && grid.y % 2 == 0 && !g.geglu &&
-                                (g.ah_dh > 0) != (g.ah_dn > 0)),
-              "multicast GEMM: activation sharing not supported for this launch");
     const bool fast = g.act == 0 && !g.relu_after_res && g.out32 == nullptr && g.alpha == 1.0f;
     const int budget = (227 - 3) * 1024 - 4 * 2 * EPI_WARP_BYTES;
     g.stages = c.force_stages ? c.force_stages : std::max(2, std::min(8, budget / stage_bytes));
     const size_t psmem = gemmp_smem_bytes(g.stages, g.BN, 2);
     RFB_CHECK(psmem <= 227 * 1024, "GEMM smem over budget");
     const int m_groups = (int)grid.x / mcast_cs, n_tiles = (int)grid.y;
-    const int units = m_groups * (n_tiles / mcast_cn) * (int)grid.z;
+    const int units = m_groups * n_tiles * (int)grid.z;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.blockDim = dim3(GEMMC_THREADS);
@@ -290,49 +283,38 @@ static void launch_gemm(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     cfg.stream = c.stream;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)(mcast_cs * mcast_cn), at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = (unsigned)mcast_cs, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see launch_pdl (engine.h)
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at, cfg.numAttrs = 1;
-#define RFB_MCAST(MODE_, CS_, CN_)                                                                                     \
+#define RFB_MCAST(MODE_, CS_)                                                                                          \
   do {                                                                                                                 \
-    auto kfn = gemm_mcast_kernel<MODE_, CS_, CN_>;                                                                     \
-    const std::string key = std::string("gemm_mcast_") + #MODE_ + "_" + #CS_ + "_" + #CN_;                             \
+    auto kfn = gemm_mcast_kernel<MODE_, CS_>;                                                                          \
+    const std::string key = std::string("gemm_mcast_") + #MODE_ + "_" + #CS_;                                          \
     if (c.first_use(key.c_str())) {                                                                                    \
       CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));                     \
-      cfg.gridDim = dim3((unsigned)(c.num_sms / (CS_ * CN_) * (CS_ * CN_)));                                           \
+      cfg.gridDim = dim3((unsigned)(c.num_sms / CS_ * CS_));                                                           \
       int nc = 0;                                                                                                      \
       if (cudaOccupancyMaxActiveClusters(&nc, kfn, &cfg) != cudaSuccess || nc < 1) nc = 1, cudaGetLastError();        \
       c.once_flags[key + "_max"] = nc;                                                                                 \
     }                                                                                                                  \
     const int clusters = std::min(units, c.once_flags[key + "_max"]);                                                  \
-    cfg.gridDim = dim3((unsigned)(clusters * CS_ * CN_));                                                              \
+    cfg.gridDim = dim3((unsigned)(clusters * CS_));                                                                    \
     cfg.numAttrs = c.pdl_now() ? 2 : 1;                                                                                \
     CUDA_OK(cudaLaunchKernelEx(&cfg, kfn, tmA, *tmBp, g, m_groups, n_tiles, units));                                   \
   } while (0)
-    const bool lean = fast && epi_lean_ok(c, g);
-    if (mcast_cn == 2) {  // convolutions of the large maps: activation halves shared across two N tiles
-      if (mcast_cs == 2) {
-        if (lean) RFB_MCAST(EPI_LEAN, 2, 2);
-        else if (fast) RFB_MCAST(EPI_FAST, 2, 2);
-        else RFB_MCAST(EPI_GENERIC, 2, 2);
-      } else {
-        if (lean) RFB_MCAST(EPI_LEAN, 1, 2);
-        else if (fast) RFB_MCAST(EPI_FAST, 1, 2);
-        else RFB_MCAST(EPI_GENERIC, 1, 2);
-      }
-    } else if (g.geglu) {
+    if (g.geglu) {
       RFB_CHECK(mcast_cs == 2, "multicast GEGLU GEMM: cluster of 2 only");
-      RFB_MCAST(EPI_GEGLU, 2, 1);
+      RFB_MCAST(EPI_GEGLU, 2);
     } else if (fast) {
-      if (mcast_cs == 2 && lean) RFB_MCAST(EPI_LEAN, 2, 1);
-      else if (mcast_cs == 8) RFB_MCAST(EPI_FAST, 8, 1);
-      else if (mcast_cs == 4) RFB_MCAST(EPI_FAST, 4, 1);
-      else RFB_MCAST(EPI_FAST, 2, 1);
+      if (mcast_cs == 2 && epi_lean_ok(c, g)) RFB_MCAST(EPI_LEAN, 2);
+      else if (mcast_cs == 8) RFB_MCAST(EPI_FAST, 8);
+      else if (mcast_cs == 4) RFB_MCAST(EPI_FAST, 4);
+      else RFB_MCAST(EPI_FAST, 2);
     } else {
-      if (mcast_cs == 8) RFB_MCAST(EPI_GENERIC, 8, 1);
-      else if (mcast_cs == 4) RFB_MCAST(EPI_GENERIC, 4, 1);
-      else RFB_MCAST(EPI_GENERIC, 2, 1);
+      if (mcast_cs == 8) RFB_MCAST(EPI_GENERIC, 8);
+      else if (mcast_cs == 4) RFB_MCAST(EPI_GENERIC, 4);
+      else RFB_MCAST(EPI_GENERIC, 2);
     }
 #undef RFB_MCAST
   } else if (pair_ok) {
@@ -603,34 +585,13 @@ Tens conv3x3_t(Ctx& c, const Tens& x, const ConvW& w, Epi e, int stride, int pad
       const long long mt = M / 128;
       cs = mt % 8 == 0 ? 8 : (mt % 4 == 0 ? 4 : (mt % 2 == 0 ? 2 : 0));
     }
-    // Un-split long-K convolutions that fill the GPU: the producer is bound by the TMA unit's row rate on the 4-D
-    // activation box (gemm_mcast.cuh) -> pairs of N tiles share the activation tile, each CTA issuing half of its rows
-    // (option gemm_mcast_a: 1 = clusters of 1 x 2, 2 = 2 x 2 with the weight tile shared across two M tiles as well)
-    const long long m_tiles_c = (M + 127) / 128, n_tiles_c = (w.cout + g.BN - 1) / g.BN;
-    int cn = 1;
-    uint32_t ba_h[4] = {ba[0], ba[1], ba[2], ba[3]};
-    if (c.gemm_mcast_big > 1 && c.gemm_mcast_a > 0 && ks == 1 && stride == 1 && g.nk >= c.gemm_mcast_min_nk &&
-        M % 128 == 0 && n_tiles_c % 2 == 0 && m_tiles_c * n_tiles_c >= c.num_sms && !(c.gemm_pair && g.nk >= c.gemm_pair_min_nk) &&
-        (g.bimg >= 2 ? g.bimg % 2 == 0 : g.bh % 2 == 0)) {
-      cn = 2;
-      if (g.bimg >= 2) g.ah_dn = g.bimg / 2, ba_h[3] = (uint32_t)g.ah_dn;
-      else g.ah_dh = g.bh / 2, ba_h[2] = (uint32_t)g.ah_dh;
-      cs = (c.gemm_mcast_a >= 2 && m_tiles_c % 2 == 0 && g.BN % 2 == 0 && (g.BN / 2) % 8 == 0) ? 2 : 1;
-    } else if (c.gemm_mcast_big > 1 && c.gemm_a_split && ks == 1 && stride == 1 && g.nk >= c.gemm_mcast_min_nk && M % 256 == 0 &&
-               g.BN % 2 == 0 && (g.BN / 2) % 8 == 0 && m_tiles_c * n_tiles_c >= c.num_sms &&
-               !(c.gemm_pair && g.nk >= c.gemm_pair_min_nk) && (g.bimg >= 2 ? g.bimg % 2 == 0 : g.bh % 2 == 0)) {
-      // weight tile shared across two M tiles (as launch_gemm would choose) + the activation box issued as two halves
-      cs = 2, g.a_split = 1;
-      if (g.bimg >= 2) g.ah_dn = g.bimg / 2, ba_h[3] = (uint32_t)g.ah_dn;
-      else g.ah_dh = g.bh / 2, ba_h[2] = (uint32_t)g.ah_dh;
-    }
     const uint64_t db[2] = {(uint64_t)w.kp, (uint64_t)round_up(w.cout, 32)};
     const uint64_t sb[1] = {(uint64_t)w.kp * 2};
     const uint32_t bb[2] = {64, (uint32_t)(cs > 1 ? g.BN / cs : g.BN)};
-    CUtensorMap tmA = make_tmap(c, x.p, 4, da, sa, (cn > 1 || g.a_split) ? ba_h : ba, stride > 1 ? ea : nullptr);
+    CUtensorMap tmA = make_tmap(c, x.p, 4, da, sa, ba, stride > 1 ? ea : nullptr);
     CUtensorMap tmB = make_tmap(c, w.w, 2, db, sb, bb);
-    dim3 grid((unsigned)m_tiles_c, (unsigned)n_tiles_c, (unsigned)ks);
-    launch_gemm(c, tmA, tmB, g, grid, 9.0 * w.cin / ks, w.w, w.kp, round_up(w.cout, 32), nullptr, cs, 0, cn);
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)((w.cout + g.BN - 1) / g.BN), (unsigned)ks);
+    launch_gemm(c, tmA, tmB, g, grid, 9.0 * w.cin / ks, w.w, w.kp, round_up(w.cout, 32), nullptr, cs);
     if (ks > 1) {
       splitk_finish(c, part, ks, M, w.cout, e_full, y.p, y.c, e_full.stats_out);
       c.release(mk_split);

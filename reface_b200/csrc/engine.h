@@ -107,10 +107,6 @@ struct Ctx {
   // weight-tile multicast for every long-K GEMM / conv that fills the GPU: cluster size (0: off) and the K blocks from
   // which a launch counts as long-K (short-K launches are epilogue-bound)
   int gemm_mcast_big = 2, gemm_mcast_min_nk = 16;
-  // long-K convs: activation halves shared across 2 N tiles (1: clusters of 1x2, 2: 2x2) -- measured no faster than
-  // sharing the weight tile only (profiles/r02_gemm_cluster_variants.txt): off
-  int gemm_mcast_a = 0;
-  int gemm_a_split = 1;  // long-K convs: the 4-D activation box is issued as two half boxes by two producer warps
   int gemm_mcast = 1;    // weight-tile TMA multicast across a cluster of M tiles for the split-K convs (gemm_mcast.cuh)
   int gemm_splitk = 1;   // 3-way split-K for the long-K 3x3 convs of <= 8x8 maps (slice count from the per-sample shape only)
   int gemm_wave_bn = 1;  // long-K GEMMs: wave-quantisation-aware tile width (multiples of 16)

@@ -19,15 +19,9 @@
 // The CTAs of a cluster walk the same sequence of (K slice, M group, N tile) units in lock step; A tiles, accumulators
 // and epilogues stay private, so the arithmetic (and every bit of the result) is that of gemm_persist_kernel.
 //
-// CN = 2 (3x3 convolutions of the large maps): the cluster is CS x CN CTAs on CS consecutive M tiles x CN consecutive N
-// tiles, and the ACTIVATION tile is shared as well -- the two CTAs of an M tile each load one half of the 4-D box (64 of
-// its 128 pixels) and multicast it to the other.  Reason (clock64 role trace, profiles/r02_gemm_role_trace_long_k.txt):
-// the producer warp of a conv launch spends 72 % of its time inside the TMA instructions themselves -- the TMA unit
-// works through a 4-D box at ~2 clocks per 128-byte row (a 2-D box: ~0.8), 128 A rows + BN B rows per K block take as
-// long as the K block's MMAs (328 clocks at BN = 160) and the MMA warp waits 22-33 % of its time for operands.  Halving
-// the rows each CTA issues puts the TMA unit back under the MMA time.  A slot of CTA X is then written by every CTA that
-// shares an M tile or an N tile with X (CS + CN - 1 CTAs, X included): empty[s] counts that many arrivals and X's MMA
-// warp releases the slot in exactly those CTAs.
+// Measured and removed again (profiles/r02_gemm_cluster_variants.txt): sharing the ACTIVATION tile between two N tiles as
+// well (clusters of 1 x 2 and 2 x 2) and issuing the 4-D activation box as two half boxes from two warps -- the
+// activation-side TMA instruction occupies its warp for ~300 clocks per K block whatever its row count.
 #pragma once
 #include "gemm_persist.cuh"
 
@@ -41,14 +35,6 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
-                                               int c3, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
-      : "memory");
-}
 // completion of all prior MMAs of this thread arrives on the mbarrier at this offset in every CTA of `mask`
 __device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -57,27 +43,21 @@ __device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
 }
 
 // units: (z, m_group, n_tile), n_tile fastest; a cluster takes unit blockIdx.x / CS + i * (gridDim.x / CS)
-// warps: 0 TMA (activations), 1 MMA, 2..9 epilogue, 10 TMA (weights), 11 TMA (second half of the activation box when
-// GemmArgs::a_split: the 4-D conv box costs its issuing warp ~2.3 clocks per pixel row)
+// warps: 0 TMA (activations), 1 MMA, 2..9 epilogue, 10 TMA (weights)
 static constexpr int GEMMC_B_WARP = GEMMP_THREADS / 32;
-static constexpr int GEMMC_A2_WARP = GEMMC_B_WARP + 1;
-static constexpr int GEMMC_THREADS = GEMMP_THREADS + 64;
+static constexpr int GEMMC_THREADS = GEMMP_THREADS + 32;
 
-// n_tiles: N tiles per unit row = CN * (number of N groups)
-template <int MODE, int CS, int CN = 1>
+template <int MODE, int CS>
 __global__ void __launch_bounds__(GEMMC_THREADS, 1)
 gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g,
                   const int m_groups, const int n_tiles, const int total_units) {
-  static_assert(CN == 1 || CN == 2, "activation sharing: pairs of N tiles");
   constexpr int NP = 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int S = g.stages;
   const int BN = g.BN;
-  const uint32_t crank = cluster_ctarank();
-  const uint32_t rank = crank % CS;  // position among the CS M tiles of the cluster
-  const uint32_t rn = crank / CS;    // position among its CN N tiles
+  const uint32_t rank = cluster_ctarank();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;
   const uint32_t sB = base + (uint32_t)S * GEMM_A_STAGE_BYTES;
@@ -88,15 +68,12 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t bar_acce = bar_accf + 16u;
   const uint32_t tptr = bar_acce + 16u;
   const uint32_t epi_stage = (tptr + 16u + 1023u) & ~1023u;
-  // multicast masks: the CTAs on my N tile (B slices), on my M tile (A halves), and every CTA I exchange tiles with
-  const uint16_t MASK = (uint16_t)(((1u << CS) - 1u) << (rn * CS));
-  const uint16_t MASK_A = (uint16_t)((1u << rank) | (CN > 1 ? (1u << (rank + CS)) : 0u));
-  const uint16_t MASK_E = (uint16_t)(MASK | MASK_A);
+  constexpr uint16_t MASK = (uint16_t)((1u << CS) - 1u);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
-      mbar_init(bars + 8u * i, g.a_split ? 3 : 2);  // the producer warps
-      mbar_init(bars + 8u * (S + i), CS + CN - 1);
+      mbar_init(bars + 8u * i, 2);  // the two producer warps
+      mbar_init(bars + 8u * (S + i), CS);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_accf + 8u * i, 1);
@@ -118,28 +95,24 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr));
-  const int cluster_id = blockIdx.x / (CS * CN);
-  const int num_clusters = gridDim.x / (CS * CN);
-  const int n_groups = n_tiles / CN;
-  const int per_z = m_groups * n_groups;
+  const int cluster_id = blockIdx.x / CS;
+  const int num_clusters = gridDim.x / CS;
+  const int per_z = m_groups * n_tiles;
 
-  if (warp == GEMMC_A2_WARP && !g.a_split) {
-    // idle
-  } else if (warp == 0 || warp == GEMMC_B_WARP || warp == GEMMC_A2_WARP) {
+  if (warp == 0 || warp == GEMMC_B_WARP) {
     // ------------------------------------------------------------ TMA producers: warp 0 loads the activation tiles,
     // warp GEMMC_B_WARP the weight slices.  Two warps because a TMA instruction occupies its issuing warp for ~80
     // (2-D box) to ~240 (4-D conv box) clocks (clock64 trace: one warp issuing both spent 72 % of a conv launch inside
     // them, 322 of the 441 clocks per K block, and the MMA warp waited 25 % of its time for operands): issued from two
     // warps the two latencies overlap.  Both arrive on full[s] (count 2) with their own byte counts.
-    const bool load_a = warp != GEMMC_B_WARP;
-    const uint32_t ahalf = warp == GEMMC_A2_WARP ? 1u : 0u;  // a_split (CN = 1): which half of the box this warp loads
-    const uint32_t tx = !load_a ? b_stage_bytes : (g.a_split ? GEMM_A_STAGE_BYTES / 2 : GEMM_A_STAGE_BYTES);
+    const bool load_a = warp == 0;
+    const uint32_t tx = load_a ? GEMM_A_STAGE_BYTES : b_stage_bytes;
     uint32_t st = 0, sp = 0;
     long long t_empty = 0, t_issue = 0;  // clock64 role counters as in gemm_persist_kernel (option gemm_debug)
     for (int u = cluster_id; u < total_units; u += num_clusters) {
       const int z = u / per_z;
       const int rem = u - z * per_z;
-      const int mg = rem / n_groups, n_tile = (rem - mg * n_groups) * CN + (int)rn;
+      const int mg = rem / n_tiles, n_tile = rem - mg * n_tiles;
       const int m_tile = mg * CS + (int)rank;
       int cw = 0, ch = 0, cn = 0;
       if (g.a_mode == A_CONV3) {
@@ -155,8 +128,6 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       const int m0 = m_tile * GEMM_BM;
       const int n0 = n_tile * BN + (int)(rank * b_slice_rows);
-      if (CN > 1) ch += (int)rn * g.ah_dh, cn += (int)rn * g.ah_dn;  // my half of the A box (tmA has the half-size box)
-      else if (g.a_split) ch += (int)ahalf * g.ah_dh, cn += (int)ahalf * g.ah_dn;
       for (int kb = 0; kb < g.nk; ++kb) {
         const uint32_t s = st, ph = sp;
         if (++st == (uint32_t)S) st = 0, sp ^= 1u;
@@ -167,19 +138,18 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t full = bars + 8u * s;
         if (elect_one()) {
           mbar_expect_tx(full, tx);
-          const uint32_t dA = sA + s * GEMM_A_STAGE_BYTES + (CN > 1 ? rn : ahalf) * (GEMM_A_STAGE_BYTES / 2);
+          const uint32_t dA = sA + s * GEMM_A_STAGE_BYTES;
           const uint32_t dB = sB + s * b_stage_bytes + rank * b_slice_rows * 128u;
           const int kg = g.ksplit ? z * g.nk + kb : kb;
           if (!load_a) {
             tma_load_2d_mc(dB, &tmB, full, kg * GEMM_BK, n0, MASK);  // this CTA's slice of the weight tile -> all CTAs
           } else if (g.a_mode == A_PLAIN) {
-            tma_load_2d(dA, &tmA, full, kg * GEMM_BK, m0);  // (CN = 1 only)
+            tma_load_2d(dA, &tmA, full, kg * GEMM_BK, m0);
           } else {
             const int tap = kg / g.cblocks;
             const int cb = kg - tap * g.cblocks;
             const int dy = tap / 3 - g.cpad_t, dx = tap % 3 - g.cpad_l;
-            if (CN > 1) tma_load_4d_mc(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn, MASK_A);
-            else tma_load_4d(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn);
+            tma_load_4d(dA, &tmA, full, cb * GEMM_BK, cw + dx, ch + dy, cn);
           }
         }
         __syncwarp();
@@ -216,7 +186,7 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
             mma_f16_ss(tacc, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
-          mma_commit_mc(bars + 8u * (S + s), MASK_E);  // slot released in every CTA that writes into it
+          mma_commit_mc(bars + 8u * (S + s), MASK);  // slot free in every CTA of the cluster once these MMAs retire
           if (kb == g.nk - 1) mma_commit(bar_accf + 8u * as);
         }
         __syncwarp();
@@ -240,8 +210,8 @@ gemm_mcast_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     auto tile_of = [&](int u, int& n_tile) {
       const int z = u / per_z;
       const int rem = u - z * per_z;
-      const int mg = rem / n_groups;
-      n_tile = (rem - mg * n_groups) * CN + (int)rn;
+      const int mg = rem / n_tiles;
+      n_tile = rem - mg * n_tiles;
       return epi_tile_info<MODE>(g, q, mg * CS + (int)rank, n_tile, z);
     };
     if (cluster_id < total_units) {

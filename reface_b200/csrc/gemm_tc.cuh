@@ -20,8 +20,6 @@ struct GemmArgs {
   int a_mode, b_mode;
   // A_CONV3 geometry: tile = bimg images x bh rows x bw cols (=128 output pixels), K = taps x cblocks x 64
   int cblocks, bw, bh, bimg, tiles_w, tiles_h;
-  int ah_dh, ah_dn;  // gemm_mcast_kernel with CN = 2 or a_split: row / image offset of the second half of the A box
-  int a_split;       // gemm_mcast_kernel: the activation box is loaded as two half boxes by two producer warps
   int cstride, cpad_l, cpad_t;  // conv stride (1 or 2) and left / top padding: input coordinate = stride * out + tap - pad
   // taps per kernel row: 3 for a 3x3 convolution; 2 for the FOLDED nearest-2x-upsample + 3x3 convolution (`up` = 1): the
   // grid's z is the output phase (py, px) = (z >> 1, z & 1), tap (a, b) reads input pixel (y + a - 1 + py, x + b - 1 + px)

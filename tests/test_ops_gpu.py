@@ -313,17 +313,6 @@ def test_long_k_weight_multicast_is_bit_identical(engine):
         engine.set_option("gemm_mcast_big", 2)
     for a, o in zip(on, off):
         assert torch.equal(a, o)
-    # the convolutions issue their 4-D activation box as two halves from two producer warps (gemm_a_split) and can
-    # additionally share the ACTIVATION tile between two N tiles (gemm_mcast_a: 2 = clusters of 2 x 2, 1 = 1 x 2; off by
-    # default: measured no faster)
-    for opt, val, dflt in (("gemm_mcast_a", 1, 0), ("gemm_mcast_a", 2, 0), ("gemm_a_split", 0, 1)):
-        engine.set_option(opt, val)
-        try:
-            alt = run()
-        finally:
-            engine.set_option(opt, dflt)
-        for a, o in zip(on, alt):
-            assert torch.equal(a, o), (opt, val)
     assert rel(on[4], F.conv2d(xd, wd, bd, padding=1)) < 4e-3
     assert torch.equal(on[2][:2], on[3])                          # 64 M tiles vs 16: same bits per sample
     assert rel(on[0], F.linear(x, w, b) + r) < 4e-3
