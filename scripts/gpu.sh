@@ -39,7 +39,7 @@ for task in "$@"; do
     ncu) # ncu:<WHAT>:<kernel regex>  one --set full capture of the matching kernels of scripts/ncu_ops.py
          what=${arg%%:*}; kre=${arg#*:}
          WHAT=$what timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kre -c ${COUNT:-2} -o gpurun_out/${TAG}_$what -f python scripts/ncu_ops.py > gpurun_out/${TAG}_ncu_$what.log 2>&1
-         python scripts/ncu_summary.py gpurun_out/${TAG}_$what.ncu-rep > gpurun_out/${TAG}_${what}_ncu_full.txt 2>&1; cat gpurun_out/${TAG}_${what}_ncu_full.txt | head -60 ;;
+         python scripts/ncu_summary.py gpurun_out/${TAG}_$what.ncu-rep --traffic gpurun_out/${TAG}_${what}_traffic.json > gpurun_out/${TAG}_${what}_ncu_full.txt 2>&1; cat gpurun_out/${TAG}_${what}_ncu_full.txt | head -60 ;;
     trace) PINGPONG=${arg:-1} timeout 300 python scripts/attn_trace.py > gpurun_out/${TAG}_attn_trace_pp${arg:-1}.txt 2>&1; cat gpurun_out/${TAG}_attn_trace_pp${arg:-1}.txt | cut -c1-260 | head -26 ;;
     scale) # scale:<N>[:<workload>]  bench.py on N GPUs of this box (one rank per GPU, torchrun)
          n=${arg%%:*}; wl=512; [[ "$arg" == *:* ]] && wl=${arg#*:}
