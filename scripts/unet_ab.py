@@ -10,7 +10,7 @@ from reface_b200.runtime import Engine
 
 N = int(os.environ.get("N", 16)); L = int(os.environ.get("L", 64)); REPS = int(os.environ.get("REPS", 5))
 DEFAULTS = {"attn_flash": 4, "attn_poly": 0, "attn_stagger": 0, "gn_fused": 1, "gn_cluster": 16, "gn_threads": 512, "ln_vec": 1,
-            "gemm_pair": 0, "gemm_wave_bn": 1, "gn_epi_stats": 1, "gemm_splitk": 1, "attn_pingpong": 0, "gn_fold": 1, "gemm_mcast": 1, "gemm_lean": 1, "pdl": 1}
+            "gemm_pair": 0, "gemm_wave_bn": 1, "gn_epi_stats": 1, "gemm_splitk": 1, "attn_pingpong": 0, "gn_fold": 1, "gemm_mcast": 1, "gemm_lean": 1, "pdl": 1, "gemm_mcast_big": 2}
 dev = torch.device("cuda", 0)
 flat = synth.random_flat(dev, 0)
 sd = {k: v for k, v in synth.state_dict_from_flat(flat).items() if k.startswith("model.diffusion_model.")}
