@@ -46,3 +46,20 @@ def test_host_schedule_matches_reference_tables(oracle):
             assert np.array_equal(sch[k], o[k]), k
     assert len(ddim_schedule(30)["timesteps"]) == 31      # util.py:48-49, assert commented out at :55
     assert np.array_equal(ddim_schedule(50)["alphas_cumprod"], g["alphas_cumprod"])
+
+
+def test_option_names_used_by_scripts_and_tests_exist():
+    """Engine options are strings parsed in capi.cu (rfb_set_option).  Every name the scripts' defaults, the GPU tests and
+    the documentation set must be one the library knows -- an unknown name raises on the GPU box only, which costs a
+    GPU run to find out."""
+    import glob
+    capi = open(os.path.join(ROOT, "reface_b200", "csrc", "capi.cu")).read()
+    known = set(re.findall(r'k == "([a-z0-9_]+)"', capi))
+    assert {"use_graph", "pdl", "gemm_lean", "gemm_mcast", "gemm_mcast_big", "gemm_splitk", "attn_flash"} <= known
+    used = set()
+    for path in glob.glob(os.path.join(ROOT, "tests", "*.py")) + glob.glob(os.path.join(ROOT, "scripts", "*.py")):
+        src = open(path).read()
+        used |= set(re.findall(r'set_option\("([a-z0-9_]+)"', src))
+    defaults = re.search(r"DEFAULTS = \{(.*?)\}", open(os.path.join(ROOT, "scripts", "unet_ab.py")).read(), re.S).group(1)
+    used |= set(re.findall(r'"([a-z0-9_]+)":', defaults))
+    assert used and not (used - known), f"unknown engine options: {sorted(used - known)}"
