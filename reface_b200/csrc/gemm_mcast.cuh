@@ -1,18 +1,19 @@
 // Cluster variant of the persistent tcgen05 GEMM / implicit-GEMM convolution with TMA MULTICAST of the weight tile.
 //
-// The long-K 3x3 convolutions of the small maps (8x8: M = 64 rows per sample, 16x16: 256) have few M tiles and a weight
-// operand that dwarfs the activation operand: every CTA of gemm_persist_kernel re-reads the same BN x K weight tile
-// through L2 (M = 1024, N = 1280, K = 11520 as 3 K-slices of 128x256 tiles: 3 MB of operands per CTA, 2 MB of it weights
-// that 7 other CTAs fetch as well; the kernel ran at ~8.5 TB/s of L2->SM traffic and 40 % of its MMA time).  Here the CS
-// CTAs that work on the same (N tile, K slice) and on CS consecutive M tiles form a thread-block cluster: each loads its
-// own 128 x 64 A tile, but only 1/CS of the B tile, with cp.async.bulk.tensor ... .multicast::cluster, so that the slice
-// lands in the shared memory of all CS CTAs.  L2->SM weight traffic drops by CS.
+// The CS CTAs that work on the same (N tile, K slice) and on CS consecutive M tiles form a thread-block cluster: each loads
+// its own 128 x 64 A tile, but only 1/CS of the B tile, with cp.async.bulk.tensor ... .multicast::cluster, so that the
+// slice lands in the shared memory of all CS CTAs.  Two uses (launch_gemm / conv3x3_t in engine.cu):
+//  * every long-K launch (K >= 1024) that fills the GPU, as clusters of 2: the clock64 role trace of the 1-CTA kernel
+//    shows its MMA warp waiting 20-37 % of the time for operands while the ring is not full -- operand delivery bounds
+//    these launches, and fetching each weight tile once per pair of CTAs takes 9-14 % off them
+//    (profiles/r02_gemm_role_trace_long_k.txt, r02_gemm_mcast_long_k_shapes.txt);
+//  * the split-K slices of the 3x3 convolutions of the <= 8x8 maps (M = 64 rows per sample: few M tiles, a weight
+//    operand that dwarfs the activation operand), as clusters of up to 8 (time-neutral there, kept for the L2 traffic).
 //
 // Protocol per CTA (warp0 TMA producer of the activation tiles, warp1 MMA issuer, warps 2..9 epilogue, warp 10 TMA
 // producer of the weight slices):
 //   full[s]   count 2 (one arrive.expect_tx per producer warp) + transaction bytes of the WHOLE stage (A tile + all CS
-//             slices of B: every peer's multicast
-//             signals the barrier at the same offset in every destination CTA)
+//             slices of B: every peer's multicast signals the barrier at the same offset in every destination CTA)
 //   empty[s]  count CS: a slot may be overwritten by any peer, so every CTA's MMA warp releases it in ALL CTAs
 //             (tcgen05.commit ... .multicast::cluster) and a producer refills it only when all CS consumers are done
 //   acc_full / acc_empty: CTA-local, as in the 1-CTA kernel
